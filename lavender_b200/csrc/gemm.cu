@@ -1,0 +1,385 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//   D[M,N] = epilogue(alpha * A·Bᵀ),  fp16 operands staged by TMA (128B swizzle), fp32 accumulators in TMEM.
+//   warp 0: TMA producer | warp 1: MMA issuer | warp 2: TMEM allocator | warps 4-11: two epilogue warpgroups,
+//   one per TMEM accumulator stage, so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Both operands may be K-major or MN-major (UMMA descriptor bit), which gives forward (K,K), dgrad (K,MN)
+// and wgrad (MN,MN; split-K with fp32 atomics) from one kernel without transposed copies.
+#include <algorithm>
+
+#include "runtime.h"
+#include "sm100.cuh"
+
+namespace lav {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 fp16 = one 128-byte swizzle atom
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 128 + kEpiWarps * 32;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = 196608 / STAGE_BYTES;  // 4 / 6 / 8 for BN = 256 / 128 / 64
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual 1 KB alignment
+  static constexpr int TMEM_COLS = 2 * BN;                                    // 2 accumulator stages
+  static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of 2");
+};
+
+struct GemmParams {
+  int M, N, K;
+  int m_blocks, n_blocks, k_blocks, splits, kb_per_split;
+  LavGemmEpilogue epi;
+};
+
+struct TileCoord {
+  int m_blk, n_blk, kb0, kb1;
+};
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int item) {
+  TileCoord t;
+  t.n_blk = item % p.n_blocks;
+  int r = item / p.n_blocks;
+  t.m_blk = r % p.m_blocks;
+  int split = r / p.m_blocks;
+  t.kb0 = split * p.kb_per_split;
+  t.kb1 = min(p.k_blocks, t.kb0 + p.kb_per_split);
+  return t;
+}
+
+// One 32-column chunk of one accumulator row: bias / activation / residual / store.
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&acc)[32], int row, int col0) {
+  const LavGemmEpilogue& e = p.epi;
+  const int ncols = min(32, p.N - col0);
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * e.alpha;
+  if (e.bias) {
+    if (ncols == 32) {
+      const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 b = __ldg(b4 + j);
+        v[4 * j] += b.x, v[4 * j + 1] += b.y, v[4 * j + 2] += b.z, v[4 * j + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) v[j] += __ldg(e.bias + col0 + j);
+    }
+  }
+  if (e.act == LAV_ACT_GELU) {
+    if (e.aux) {
+      __half* a = reinterpret_cast<__half*>(e.aux) + (size_t)row * e.ldaux + col0;
+      if (ncols == 32 && (e.ldaux & 7) == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 u;
+          u.x = pack_half2(v[8 * j], v[8 * j + 1]), u.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
+          u.z = pack_half2(v[8 * j + 4], v[8 * j + 5]), u.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
+          reinterpret_cast<uint4*>(a)[j] = u;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < ncols) a[j] = __float2half_rn(v[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  } else if (e.act == LAV_ACT_GELU_BWD) {
+    const __half* a = reinterpret_cast<const __half*>(e.aux) + (size_t)row * e.ldaux + col0;
+    if (ncols == 32 && (e.ldaux & 7) == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 u = reinterpret_cast<const uint4*>(a)[j];
+        const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float2 f = __half22float2(h[q]);
+          v[8 * j + 2 * q] *= gelu_erf_grad(f.x);
+          v[8 * j + 2 * q + 1] *= gelu_erf_grad(f.y);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) v[j] *= gelu_erf_grad(__half2float(a[j]));
+    }
+  }
+  if (e.row_scale) {
+    const float s = __ldg(e.row_scale + row / e.rows_per_scale);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= s;
+  }
+  const int orow = e.row_map ? __ldg(e.row_map + row) : row;
+  if (e.residual) {
+    const float* r = e.residual + (size_t)orow * e.ldres + col0;
+    if (ncols == 32 && (e.ldres & 3) == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 x = reinterpret_cast<const float4*>(r)[j];
+        v[4 * j] += x.x, v[4 * j + 1] += x.y, v[4 * j + 2] += x.z, v[4 * j + 3] += x.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) v[j] += r[j];
+    }
+  }
+  if (e.out_dtype == LAV_OUT_F16) {
+    __half* o = reinterpret_cast<__half*>(e.out) + (size_t)orow * e.ldo + col0;
+    if (ncols == 32 && (e.ldo & 7) == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 u;
+        u.x = pack_half2(v[8 * j], v[8 * j + 1]), u.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
+        u.z = pack_half2(v[8 * j + 4], v[8 * j + 5]), u.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
+        reinterpret_cast<uint4*>(o)[j] = u;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) o[j] = __float2half_rn(v[j]);
+    }
+  } else {
+    float* o = reinterpret_cast<float*>(e.out) + (size_t)orow * e.ldo + col0;
+    if (e.accumulate == LAV_ACCUMULATE) {
+      if (p.splits > 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < ncols) atomicAdd(o + j, v[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < ncols) o[j] += v[j];
+      }
+    } else if (ncols == 32 && (e.ldo & 3) == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) o[j] = v[j];
+    }
+  }
+}
+
+template <int BN, int AMAJ, int BMAJ>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::STAGES;
+  uint64_t* tmem_full = bars + 2 * Cfg::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tmem_full + s, 1);
+      mbar_init(tmem_empty + s, 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total = p.m_blocks * p.n_blocks * p.splits;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer (one lane)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        const TileCoord t = decode_tile(p, item);
+        for (int kb = t.kb0; kb < t.kb1; ++kb) {
+          mbar_wait(empty + stage, phase ^ 1, 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          mbar_arrive_expect_tx(full + stage, Cfg::STAGE_BYTES);
+          if (AMAJ == LAV_MAJOR_K) {
+            tma_load_2d(sa, &tmA, full + stage, kb * BK, t.m_blk * BM);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d(sa + j * (BK * 128), &tmA, full + stage, t.m_blk * BM + j * 64, kb * BK);
+          }
+          if (BMAJ == LAV_MAJOR_K) {
+            tma_load_2d(sb, &tmB, full + stage, kb * BK, t.n_blk * BN);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(sb + j * (BK * 128), &tmB, full + stage, t.n_blk * BN + j * 64, kb * BK);
+          }
+          if (++stage == Cfg::STAGES) stage = 0, phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer (one lane)
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BM, BN, AMAJ, BMAJ);
+      // K-major: 8-row atoms are 1024 B apart (SBO); MN-major: 64-element atoms are BK*128 B apart (LBO),
+      // 8-k-row groups 1024 B apart (SBO).
+      constexpr uint32_t a_lbo = (AMAJ == LAV_MAJOR_K) ? 0 : BK * 128;
+      constexpr uint32_t b_lbo = (BMAJ == LAV_MAJOR_K) ? 0 : BK * 128;
+      constexpr uint32_t a_kstep = (AMAJ == LAV_MAJOR_K) ? 32 : 16 * 128;  // bytes per UMMA_K = 16
+      constexpr uint32_t b_kstep = (BMAJ == LAV_MAJOR_K) ? 32 : 16 * 128;
+      int stage = 0;
+      uint32_t phase = 0;
+      int iter = 0;
+      for (int item = blockIdx.x; item < total; item += gridDim.x, ++iter) {
+        const TileCoord t = decode_tile(p, item);
+        const int as = iter & 1;
+        mbar_wait(tmem_empty + as, ((iter >> 1) & 1) ^ 1, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = t.kb0; kb < t.kb1; ++kb) {
+          mbar_wait(full + stage, phase, 3);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ad = make_smem_desc(sa + k * a_kstep, a_lbo, 1024, SWZ_128B);
+            const uint64_t bd = make_smem_desc(sb + k * b_kstep, b_lbo, 1024, SWZ_128B);
+            umma_f16_ss(d_tmem, ad, bd, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty + stage);  // frees the smem slot once these MMAs have read it
+          if (kb == t.kb1 - 1) umma_commit(tmem_full + as);
+          if (++stage == Cfg::STAGES) stage = 0, phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------ epilogue: warpgroup g drains accumulator stage g
+    const int wg = (warp - 4) >> 2;
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int iter = 0;
+    for (int item = blockIdx.x; item < total; item += gridDim.x, ++iter) {
+      if ((iter & 1) != wg) continue;
+      const TileCoord t = decode_tile(p, item);
+      mbar_wait(tmem_full + wg, (iter >> 1) & 1, 4);
+      tc_fence_after();
+      const int row = t.m_blk * BM + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + wg * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = t.n_blk * BN + c * 32;
+        if (col0 >= p.N) break;
+        uint32_t acc[32];
+        tmem_ld_32x32(taddr + c * 32, acc);
+        tmem_ld_wait();
+        if (row < p.M) epilogue_chunk(p, acc, row, col0);
+      }
+      tc_fence_before();
+      mbar_arrive(tmem_empty + wg);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+template <int BN, int AMAJ, int BMAJ>
+static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (AMAJ == LAV_MAJOR_K)
+    rc = encode_tmap_2d_f16(&tmA, A, p.M, p.K, lda, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B);
+  else
+    rc = encode_tmap_2d_f16(&tmA, A, p.K, p.M, lda, BK, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  if (BMAJ == LAV_MAJOR_K)
+    rc = encode_tmap_2d_f16(&tmB, B, p.N, p.K, ldb, BN, BK, CU_TENSOR_MAP_SWIZZLE_128B);
+  else
+    rc = encode_tmap_2d_f16(&tmB, B, p.K, p.N, ldb, BK, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  p.n_blocks = (p.N + BN - 1) / BN;
+  auto kern = gemm_f16_kernel<BN, AMAJ, BMAJ>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LAV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int total = p.m_blocks * p.n_blocks * p.splits;
+  const int grid = std::min(total, sm_count());
+  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  LAV_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return LAV_OK;
+}
+
+template <int BN>
+static int dispatch_major(const void* A, int64_t lda, int a_major, const void* B, int64_t ldb, int b_major,
+                          GemmParams& p, cudaStream_t s) {
+  if (a_major == LAV_MAJOR_K && b_major == LAV_MAJOR_K) return launch_gemm<BN, 0, 0>(A, lda, B, ldb, p, s);
+  if (a_major == LAV_MAJOR_K && b_major == LAV_MAJOR_MN) return launch_gemm<BN, 0, 1>(A, lda, B, ldb, p, s);
+  if (a_major == LAV_MAJOR_MN && b_major == LAV_MAJOR_MN) return launch_gemm<BN, 1, 1>(A, lda, B, ldb, p, s);
+  return launch_gemm<BN, 1, 0>(A, lda, B, ldb, p, s);
+}
+
+}  // namespace lav
+
+extern "C" int lav_gemm_f16(const void* A, int64_t lda, int a_major, const void* B, int64_t ldb, int b_major, int M,
+                            int N, int K, const LavGemmEpilogue* epi, int split_k, void* stream) {
+  using namespace lav;
+  LAV_REQUIRE(A && B && epi && epi->out, "lav_gemm_f16: null pointer");
+  LAV_REQUIRE(M > 0 && N > 0 && K > 0, "lav_gemm_f16: empty problem %dx%dx%d", M, N, K);
+  LAV_REQUIRE((a_major | b_major) >= 0 && a_major <= 1 && b_major <= 1, "lav_gemm_f16: bad major");
+  LAV_REQUIRE(!(epi->accumulate == LAV_ACCUMULATE && epi->out_dtype != LAV_OUT_F32),
+              "lav_gemm_f16: accumulation needs an fp32 output");
+  LAV_REQUIRE(!(epi->act != LAV_ACT_NONE && split_k > 1), "lav_gemm_f16: activation with split-K");
+  LAV_REQUIRE(!(epi->act == LAV_ACT_GELU_BWD && !epi->aux), "lav_gemm_f16: GELU_BWD needs aux");
+  GemmParams p;
+  p.M = M, p.N = N, p.K = K;
+  p.m_blocks = (M + BM - 1) / BM;
+  p.k_blocks = (K + BK - 1) / BK;
+  p.epi = *epi;
+  // tile width: 256 when N is large, 64 for narrow outputs (less padding waste / more CTAs)
+  int bn = 128;
+  if (N <= 64) bn = 64;
+  else if (N >= 512 && (N % 256 == 0 || N > 2048)) bn = 256;
+  const int n_blocks = (N + bn - 1) / bn;
+  int splits = split_k;
+  if (splits <= 0) {  // auto: fill the machine when the output has few tiles but the contraction is long
+    const int tiles = p.m_blocks * n_blocks;
+    splits = 1;
+    if (epi->accumulate == LAV_ACCUMULATE && epi->act == LAV_ACT_NONE && tiles < 2 * sm_count())
+      splits = std::max(1, std::min((2 * sm_count() + tiles - 1) / tiles, p.k_blocks / 4));
+  }
+  splits = std::max(1, std::min(splits, p.k_blocks));
+  LAV_REQUIRE(splits == 1 || epi->accumulate == LAV_ACCUMULATE, "lav_gemm_f16: split-K needs LAV_ACCUMULATE");
+  p.kb_per_split = (p.k_blocks + splits - 1) / splits;
+  p.splits = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  switch (bn) {
+    case 64: return dispatch_major<64>(A, lda, a_major, B, ldb, b_major, p, s);
+    case 256: return dispatch_major<256>(A, lda, a_major, B, ldb, b_major, p, s);
+    default: return dispatch_major<128>(A, lda, a_major, B, ldb, b_major, p, s);
+  }
+}

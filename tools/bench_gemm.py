@@ -1,0 +1,90 @@
+"""Micro-benchmark of lav_gemm_f16 on the shapes of the hot path (CUDA events, L2 flushed between runs)."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from lavender_b200 import ops, _lib as L  # noqa: E402
+
+
+def timeit(fn, iters=10, flush=None):
+    for _ in range(3):
+        fn()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def main():
+    torch.manual_seed(0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    rows = []
+    shapes = [  # (tag, M, N, K, mode)
+        ("swin_s0_qkv", 125440, 384, 128, "fwd"), ("swin_s0_fc1_gelu", 125440, 512, 128, "gelu"),
+        ("swin_s0_fc2_res", 125440, 128, 512, "res"), ("swin_s2_qkv", 7840, 1536, 512, "fwd"),
+        ("swin_s2_fc1_gelu", 7840, 2048, 512, "gelu"), ("swin_s2_fc2_res", 7840, 512, 2048, "res"),
+        ("bert_qkv_vtm", 9056, 2304, 768, "fwd"), ("bert_ffn1_vtm", 9056, 3072, 768, "gelu"),
+        ("bert_ffn2_vtm", 9056, 768, 3072, "fwd32"), ("mlm_decoder", 1352, 30522, 768, "fwd32"),
+        ("square_8k", 8192, 8192, 8192, "fwd"),
+        ("swin_s2_fc1_dgrad", 7840, 512, 2048, "dgrad"), ("swin_s2_fc1_wgrad", 2048, 512, 7840, "wgrad"),
+        ("swin_s0_qkv_wgrad", 384, 128, 125440, "wgrad"), ("bert_ffn1_wgrad", 3072, 768, 9056, "wgrad"),
+    ]
+    for tag, M, N, K, mode in shapes:
+        if mode == "wgrad":
+            a = torch.randn(K, M, device="cuda").half()
+            b = torch.randn(K, N, device="cuda").half()
+            out = torch.zeros(M, N, device="cuda")
+            fn = lambda: ops.gemm(a, b, out, M=M, N=N, K=K, a_major=1, b_major=1, accumulate=True)
+        elif mode == "dgrad":
+            a = torch.randn(M, K, device="cuda").half()
+            b = torch.randn(K, N, device="cuda").half()
+            out = torch.zeros(M, N, device="cuda").half()
+            fn = lambda: ops.gemm(a, b, out, M=M, N=N, K=K, b_major=1)
+        else:
+            a = torch.randn(M, K, device="cuda").half()
+            b = torch.randn(N, K, device="cuda").half()
+            bias = torch.randn(N, device="cuda")
+            if mode == "fwd":
+                out = torch.zeros(M, N, device="cuda").half()
+                fn = lambda: ops.gemm(a, b, out, M=M, N=N, K=K, bias=bias)
+            elif mode == "fwd32":
+                out = torch.zeros(M, N, device="cuda")
+                fn = lambda: ops.gemm(a, b, out, M=M, N=N, K=K, bias=bias)
+            elif mode == "gelu":
+                out = torch.zeros(M, N, device="cuda").half()
+                aux = torch.zeros(M, N, device="cuda").half()
+                fn = lambda: ops.gemm(a, b, out, M=M, N=N, K=K, bias=bias, act=L.ACT_GELU, aux=aux)
+            else:
+                out = torch.zeros(M, N, device="cuda")
+                res = torch.randn(M, N, device="cuda")
+                fn = lambda: ops.gemm(a, b, out, M=M, N=N, K=K, bias=bias, residual=res)
+        ms = timeit(fn, flush=flush)
+        tf = 2.0 * M * N * K / ms / 1e9
+        # torch (cuBLAS) for comparison on the plain product
+        if mode == "wgrad":
+            ms_t = timeit(lambda: torch.matmul(a.t(), b), flush=flush)
+        elif mode == "dgrad":
+            ms_t = timeit(lambda: torch.matmul(a, b), flush=flush)
+        else:
+            ms_t = timeit(lambda: torch.matmul(a, b.t()), flush=flush)
+        rows.append(dict(tag=tag, M=M, N=N, K=K, mode=mode, ms=round(ms, 4), tflops=round(tf, 1),
+                         cublas_ms=round(ms_t, 4), cublas_tflops=round(2.0 * M * N * K / ms_t / 1e9, 1)))
+        print(rows[-1], flush=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "bench_gemm.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
