@@ -89,6 +89,71 @@ typedef struct LavGemmEpilogue {
 int lav_gemm_f16(const void* A, int64_t lda, int a_major, const void* B, int64_t ldb, int b_major, int M, int N,
                  int K, const LavGemmEpilogue* epi, int split_k, void* stream);
 
+
+/* ---- LayerNorm (one warp per row, fp32 statistics) -------------------------------------------------
+ * Forward of nn.LayerNorm at video_swin.py:209 (norm1), :246 (norm2), :284 (PatchMerging.norm), :402, :477,
+ * model.py:85 and the HF BERT LayerNorms.  Output row r (width G*C) is the concatenation of G source rows
+ * of width C taken at row_map[r*G+g] (identity when row_map == NULL).  G=1 with a row map folds
+ * torch.roll + window_partition (video_swin.py:218-227) into the load; G=4 folds the PatchMerging
+ * gather/concat (video_swin.py:278-282).  Writes fp16 and/or fp32 outputs and the per-row mean / rstd. */
+int lav_layernorm_fwd(const float* x, int64_t ldx, const int32_t* row_map, int G, int C, const float* gamma,
+                      const float* beta, float eps, void* y16, int64_t ldy16, float* y32, int64_t ldy32,
+                      float* mean, float* rstd, int rows, void* stream);
+
+/* Backward of the above (autograd of nn.LayerNorm in the reference).  dy is fp16 (dy_is_f32=0) or fp32.
+ *   dx32[src row] = LN'(dy) (+ add32[src row])      — scatter through the same row map
+ *   dx16[r]       = the same value as fp16, row r     — operand of the following dgrad / wgrad GEMMs
+ *   dgamma / dbeta (fp32, accumulated with atomics; both or neither). */
+int lav_layernorm_bwd(const void* dy, int64_t lddy, int dy_is_f32, const float* x, int64_t ldx,
+                      const int32_t* row_map, int G, int C, const float* gamma, const float* mean,
+                      const float* rstd, const float* add32, int64_t ldadd, float* dx32, int64_t lddx32,
+                      void* dx16, int64_t lddx16, float* dgamma, float* dbeta, int rows, void* stream);
+
+/* out16[r, 0:C] = fp16( alpha * row_scale[r / rows_per_scale] * x[row_map[r], 0:C] )
+ * (gradient gather for window-major GEMM operands; DropPath scale of video_swin.py:46-54 in backward). */
+int lav_scale_cast_f16(const float* x, int64_t ldx, const int32_t* row_map, const float* row_scale,
+                       int rows_per_scale, float alpha, void* out16, int64_t ldo, int rows, int C, void* stream);
+
+/* flat fp32 -> fp16 copy (per-step fp16 shadow of the fp32 master parameters; autocast's weight cast,
+ * agent.py:219) */
+int lav_cast_f32_to_f16(const float* src, void* dst, int64_t n, void* stream);
+
+/* out[c] += alpha * sum_r x16[r, c]  (bias gradients of every nn.Linear on the path) */
+int lav_colsum_f16(const void* x16, int64_t ld, int rows, int N, float* out, float alpha, void* stream);
+
+/* ---- fused attention (tcgen05 + TMA) ---------------------------------------------------------------
+ * O = softmax(scale * Q K^T + bias) V for `nprob` independent problems of L tokens each whose rows are
+ * contiguous in the fused QKV activation [rows_total, ld] (Q/K/V of head h at columns *_off + h*head_dim).
+ *   - WindowAttention3D.forward video_swin.py:147-167: head_dim 32, L = 245 (<= 256); `bias16` is the dense
+ *     [ncls][nheads][256][256] fp16 tensor of lav_relpos_bias_expand (relative position bias :153-155 + shift
+ *     mask :157-160 + -inf on padded keys); problem p uses class prob_class[p % class_period].
+ *   - HF BertSelfAttention (model.py:242): head_dim 64, L <= 384; key_bias is the additive [nprob][384] fp32
+ *     row (0 for kept keys, -inf for masked / padded keys) of get_extended_attention_mask (model.py:239).
+ * Writes O (fp16, [rows_total, ldo], head h at column h*head_dim) and lse[h][row] = log-sum-exp (fp32). */
+int lav_attn_fwd_f16(const void* qkv, int64_t ld, int64_t rows_total, int q_off, int k_off, int v_off, int head_dim,
+                     int nheads, int nprob, int L, float scale, const void* bias16, int NPb,
+                     const int32_t* prob_class, int class_period, const float* key_bias, void* out16, int64_t ldo,
+                     float* lse, void* stream);
+
+/* Backward of the above.  dq_acc: fp32 [rows_total, nheads*head_dim], zeroed by the caller (dQ is reduced
+ * over key chunks with atomics); dK and dV are written as fp16 into dqkv16 at k_off / v_off.  When ds16 is
+ * given ([nprob][nheads][NPs][NPs] fp16) the gradient wrt the pre-softmax logits is stored for
+ * lav_relpos_bias_grad. */
+int lav_attn_bwd_f16(const void* qkv, int64_t ld, int64_t rows_total, int q_off, int k_off, int v_off, int head_dim,
+                     int nheads, int nprob, int L, float scale, const void* bias16, int NPb,
+                     const int32_t* prob_class, int class_period, const float* key_bias, int NPk,
+                     const void* out16, int64_t ldo, const void* dout16, int64_t lddo, const float* lse,
+                     float* dq_acc, int64_t lddq, void* dqkv16, int64_t lddqkv, void* ds16, int NPs, void* stream);
+
+/* dense16[cls][h][i][j] = table[rel_index[i*L+j]][h] + (labels[cls][i] != labels[cls][j] ? -100 : 0), -inf for
+ * j >= L (video_swin.py:153-160 and compute_mask :290-305); labels may be NULL (unshifted block, ncls = 1). */
+int lav_relpos_bias_expand(const float* table, int nheads, const int32_t* rel_index, int L, const uint8_t* labels,
+                           int ncls, void* dense16, int NP, void* stream);
+
+/* dtable[rel_index[i*L+j]][h] += sum_p ds16[p][h][i][j]  (gradient of relative_position_bias_table) */
+int lav_relpos_bias_grad(const void* ds16, int nprob, int nheads, int NP, int L, const int32_t* rel_index,
+                         float* dtable, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,6 +40,22 @@ SIGNATURES = {
     "lav_device_info": (c_int, [c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "lav_gemm_f16": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_int, c_int, c_int,
                              ctypes.POINTER(GemmEpilogue), c_int, c_void_p]),
+    "lav_layernorm_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p,
+                                  c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p]),
+    "lav_layernorm_bwd": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
+                                  c_void_p, c_void_p, c_int, c_void_p]),
+    "lav_scale_cast_f16": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_float, c_void_p, c_int64, c_int,
+                                   c_int, c_void_p]),
+    "lav_cast_f32_to_f16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "lav_colsum_f16": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_float, c_void_p]),
+    "lav_attn_fwd_f16": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                                 c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "lav_attn_bwd_f16": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                                 c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64, c_void_p,
+                                 c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_void_p]),
+    "lav_relpos_bias_expand": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    "lav_relpos_bias_grad": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
 }
 
 

@@ -1,0 +1,360 @@
+// Fused attention backward for sm_100a (recompute from the saved log-sum-exp; nothing [N,N]-shaped is kept from
+// the forward).  One CTA per (128-key chunk c, head, problem); it keeps K_c / V_c resident and loops over the
+// 128-row query tiles t:
+//     S  = Q_t K_cᵀ , dP = dO_t V_cᵀ                 (tcgen05 -> TMEM)
+//     P  = exp(scale*S + bias - lse) , dS = P ∘ (dP - delta)          (registers, thread = query row)
+//     dV_c += Pᵀ dO_t , dK_c += dSᵀ Q_t , dQ_t = dS K_c               (tcgen05; P/dS staged in smem as fp16)
+// dQ_t is reduced over the key chunks with fp32 atomics into `dq_acc`; dK/dV are written once as fp16.
+// For the Swin relative-position bias the per-window dS is also written out (fp16) and reduced over windows by
+// relpos_bias_grad_kernel (autograd's index_put of video_swin.py:153 in the reference).
+#include "runtime.h"
+#include "sm100.cuh"
+
+namespace lav {
+
+constexpr int kAttnBwdThreads = 160;
+
+struct AttnBwdParams {
+  int L, nheads, nprob;
+  int q_off, k_off, v_off;
+  float scale;
+  const __half* bias16; int NPb;
+  const int32_t* prob_class; int period;
+  const float* key_bias; int NPk;           // [nprob][NPk]
+  const __half* out; int64_t ldo;           // forward output O
+  const __half* dout; int64_t lddo;         // dO
+  const float* lse; int64_t rows_total;
+  float* dq_acc; int64_t lddq;              // fp32 [rows_total, nheads*HD], pre-zeroed
+  __half* dqkv; int64_t lddqkv;             // dK / dV written at k_off / v_off
+  __half* ds_out; int NPs;                  // optional [nprob][nheads][NPs][NPs]
+};
+
+template <int HD>
+struct AttnBwdCfg {
+  static constexpr int ROWB = HD * 2;
+  static constexpr int TILE = 128 * ROWB;
+  static constexpr int OFF_K = 0, OFF_V = TILE, OFF_Q = 2 * TILE, OFF_DO = 4 * TILE;  // Q, dO double-buffered
+  static constexpr int OFF_P = 6 * TILE, OFF_DS = OFF_P + 32768, OFF_BAR = OFF_DS + 32768;
+  static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
+  static constexpr uint32_t SWZ = (HD == 64) ? SWZ_128B : SWZ_64B;
+  static constexpr uint32_t SBO = 8 * ROWB;
+  static constexpr int COL_S = 0, COL_DP = 128, COL_DQ = 256, COL_DK = 320, COL_DV = 384;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(kAttnBwdThreads, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                const AttnBwdParams p) {
+  using Cfg = AttnBwdCfg<HD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);  // 0 kv | 1,2 q/dO buf | 3 S,dP | 4 P,dS | 5 mma2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x, h = blockIdx.y, prob = blockIdx.z;
+  const int row0 = prob * p.L;
+  const int nqt = (p.L + 127) / 128;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQKV);
+      tma_prefetch_desc(&tmDO);
+      mbar_init(bars + 0, 1);
+      mbar_init(bars + 1, 1);
+      mbar_init(bars + 2, 1);
+      mbar_init(bars + 3, 1);
+      mbar_init(bars + 4, 128);
+      mbar_init(bars + 5, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      auto load_q = [&](int t) {
+        const int b = t & 1;
+        mbar_arrive_expect_tx(bars + 1 + b, 2 * Cfg::TILE);
+        tma_load_2d(smem + Cfg::OFF_Q + b * Cfg::TILE, &tmQKV, bars + 1 + b, p.q_off + h * HD, row0 + t * 128);
+        tma_load_2d(smem + Cfg::OFF_DO + b * Cfg::TILE, &tmDO, bars + 1 + b, h * HD, row0 + t * 128);
+      };
+      mbar_arrive_expect_tx(bars + 0, 2 * Cfg::TILE);
+      tma_load_2d(smem + Cfg::OFF_K, &tmQKV, bars + 0, p.k_off + h * HD, row0 + c * 128);
+      tma_load_2d(smem + Cfg::OFF_V, &tmQKV, bars + 0, p.v_off + h * HD, row0 + c * 128);
+      load_q(0);
+      if (nqt > 1) load_q(1);
+      mbar_wait(bars + 0, 0, 20);
+      constexpr uint32_t id_s = make_idesc_f16(128, 128, 0, 0);   // S / dP : K-major x K-major
+      constexpr uint32_t id_t = make_idesc_f16(128, HD, 1, 1);    // dV / dK: MN-major A (P/dS transposed), MN-major B
+      constexpr uint32_t id_q = make_idesc_f16(128, HD, 0, 1);    // dQ     : K-major A (dS), MN-major B (K)
+      const uint32_t sk = smem_u32(smem + Cfg::OFF_K), sv = smem_u32(smem + Cfg::OFF_V);
+      const uint32_t sp = smem_u32(smem + Cfg::OFF_P), sds = smem_u32(smem + Cfg::OFF_DS);
+      for (int t = 0; t < nqt; ++t) {
+        const int b = t & 1;
+        const uint32_t sq = smem_u32(smem + Cfg::OFF_Q + b * Cfg::TILE);
+        const uint32_t sdo = smem_u32(smem + Cfg::OFF_DO + b * Cfg::TILE);
+        mbar_wait(bars + 1 + b, (t >> 1) & 1, 21);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_f16_ss(tmem + Cfg::COL_S, make_smem_desc(sq + k * 32, 0, Cfg::SBO, Cfg::SWZ),
+                      make_smem_desc(sk + k * 32, 0, Cfg::SBO, Cfg::SWZ), id_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_f16_ss(tmem + Cfg::COL_DP, make_smem_desc(sdo + k * 32, 0, Cfg::SBO, Cfg::SWZ),
+                      make_smem_desc(sv + k * 32, 0, Cfg::SBO, Cfg::SWZ), id_s, k > 0);
+        umma_commit(bars + 3);
+        mbar_wait(bars + 4, t & 1, 22);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {  // contraction over the 128 query rows, 16 per MMA
+          const uint64_t b_do = make_smem_desc(sdo + k * 16 * Cfg::ROWB, 0, Cfg::SBO, Cfg::SWZ);
+          const uint64_t b_q = make_smem_desc(sq + k * 16 * Cfg::ROWB, 0, Cfg::SBO, Cfg::SWZ);
+          umma_f16_ss(tmem + Cfg::COL_DV, make_smem_desc(sp + k * 2048, 16384, 1024, SWZ_128B), b_do, id_t,
+                      (t > 0 || k > 0));
+          umma_f16_ss(tmem + Cfg::COL_DK, make_smem_desc(sds + k * 2048, 16384, 1024, SWZ_128B), b_q, id_t,
+                      (t > 0 || k > 0));
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // contraction over the 128 keys of this chunk
+          umma_f16_ss(tmem + Cfg::COL_DQ, make_smem_desc(sds + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024, SWZ_128B),
+                      make_smem_desc(sk + k * 16 * Cfg::ROWB, 0, Cfg::SBO, Cfg::SWZ), id_q, k > 0);
+        umma_commit(bars + 5);
+        if (t + 2 < nqt) {  // refill this Q/dO buffer once the MMAs above have consumed it
+          mbar_wait(bars + 5, t & 1, 23);
+          load_q(t + 2);
+        }
+      }
+    }
+  } else {
+    const int i = warp * 32 + lane;
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    const float sc_log2 = p.scale * 1.4426950408889634f;
+    const int cls = (p.bias16 && p.prob_class) ? p.prob_class[prob % p.period] : 0;
+    const float* kb = p.key_bias ? p.key_bias + (size_t)prob * p.NPk + c * 128 : nullptr;
+    uint8_t* prow = smem + Cfg::OFF_P + i * 128;
+    uint8_t* dsrow = smem + Cfg::OFF_DS + i * 128;
+
+    for (int t = 0; t < nqt; ++t) {
+      const int qi = t * 128 + i;
+      const bool valid = qi < p.L;
+      float lse_l2 = 0.f, delta = 0.f;
+      if (valid) {
+        lse_l2 = p.lse[(size_t)h * p.rows_total + row0 + qi] * 1.4426950408889634f;
+        const uint4* po = reinterpret_cast<const uint4*>(p.out + (size_t)(row0 + qi) * p.ldo + h * HD);
+        const uint4* pd = reinterpret_cast<const uint4*>(p.dout + (size_t)(row0 + qi) * p.lddo + h * HD);
+#pragma unroll
+        for (int j = 0; j < HD / 8; ++j) {
+          uint4 a = po[j], b = pd[j];
+          const __half2* ha = reinterpret_cast<const __half2*>(&a);
+          const __half2* hb = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float2 fa = __half22float2(ha[q]), fb = __half22float2(hb[q]);
+            delta += fa.x * fb.x + fa.y * fb.y;
+          }
+        }
+      }
+      const __half* brow = p.bias16 ? p.bias16 + (((size_t)cls * p.nheads + h) * p.NPb + min(qi, p.NPb - 1)) * p.NPb + c * 128
+                                    : nullptr;
+      __half* dsg = (p.ds_out && valid) ? p.ds_out + (((size_t)prob * p.nheads + h) * p.NPs + qi) * p.NPs + c * 128
+                                        : nullptr;
+      mbar_wait(bars + 3, t & 1, 24);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j0 = 0; j0 < 128; j0 += 32) {
+        uint32_t s[32], dp[32];
+        tmem_ld_32x32(trow + Cfg::COL_S + j0, s);
+        tmem_ld_32x32(trow + Cfg::COL_DP + j0, dp);
+        tmem_ld_wait();
+        float pv[32], dsv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) pv[j] = __uint_as_float(s[j]) * sc_log2 - lse_l2;
+        if (brow) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 u = *reinterpret_cast<const uint4*>(brow + j0 + 8 * j);
+            const __half2* hh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float2 f = __half22float2(hh[q]);
+              pv[8 * j + 2 * q] += f.x * 1.4426950408889634f, pv[8 * j + 2 * q + 1] += f.y * 1.4426950408889634f;
+            }
+          }
+        }
+        if (kb) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) pv[j] += __ldg(kb + j0 + j) * 1.4426950408889634f;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float pe = valid ? exp2f(pv[j]) : 0.f;
+          pv[j] = pe;
+          dsv[j] = pe * (__uint_as_float(dp[j]) - delta);
+        }
+        uint8_t* pa = prow + (j0 >> 6) * 16384;
+        uint8_t* da = dsrow + (j0 >> 6) * 16384;
+        const int chunk0 = (j0 & 63) >> 3;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 u, w;
+          u.x = pack_half2(pv[8 * j], pv[8 * j + 1]), u.y = pack_half2(pv[8 * j + 2], pv[8 * j + 3]);
+          u.z = pack_half2(pv[8 * j + 4], pv[8 * j + 5]), u.w = pack_half2(pv[8 * j + 6], pv[8 * j + 7]);
+          w.x = pack_half2(dsv[8 * j], dsv[8 * j + 1]), w.y = pack_half2(dsv[8 * j + 2], dsv[8 * j + 3]);
+          w.z = pack_half2(dsv[8 * j + 4], dsv[8 * j + 5]), w.w = pack_half2(dsv[8 * j + 6], dsv[8 * j + 7]);
+          const int off = ((chunk0 + j) ^ (i & 7)) << 4;
+          *reinterpret_cast<uint4*>(pa + off) = u;
+          *reinterpret_cast<uint4*>(da + off) = w;
+          if (dsg) reinterpret_cast<uint4*>(dsg + j0)[j] = w;
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bars + 4);
+
+      mbar_wait(bars + 5, t & 1, 25);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < HD; c0 += 32) {
+        uint32_t o[32];
+        tmem_ld_32x32(trow + Cfg::COL_DQ + c0, o);
+        tmem_ld_wait();
+        if (valid) {
+          float* dst = p.dq_acc + (size_t)(row0 + qi) * p.lddq + h * HD + c0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(o[j]) * p.scale);
+        }
+      }
+      tc_fence_before();
+    }
+    // ---- dK_c, dV_c : thread = key row of this chunk
+    const int kj = c * 128 + i;
+    const bool kvalid = kj < p.L;
+#pragma unroll
+    for (int c0 = 0; c0 < HD; c0 += 32) {
+      uint32_t dk[32], dv[32];
+      tmem_ld_32x32(trow + Cfg::COL_DK + c0, dk);
+      tmem_ld_32x32(trow + Cfg::COL_DV + c0, dv);
+      tmem_ld_wait();
+      if (kvalid) {
+        __half* gk = p.dqkv + (size_t)(row0 + kj) * p.lddqkv + p.k_off + h * HD + c0;
+        __half* gv = p.dqkv + (size_t)(row0 + kj) * p.lddqkv + p.v_off + h * HD + c0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 u, w;
+          u.x = pack_half2(__uint_as_float(dk[8 * j]) * p.scale, __uint_as_float(dk[8 * j + 1]) * p.scale);
+          u.y = pack_half2(__uint_as_float(dk[8 * j + 2]) * p.scale, __uint_as_float(dk[8 * j + 3]) * p.scale);
+          u.z = pack_half2(__uint_as_float(dk[8 * j + 4]) * p.scale, __uint_as_float(dk[8 * j + 5]) * p.scale);
+          u.w = pack_half2(__uint_as_float(dk[8 * j + 6]) * p.scale, __uint_as_float(dk[8 * j + 7]) * p.scale);
+          w.x = pack_half2(__uint_as_float(dv[8 * j]), __uint_as_float(dv[8 * j + 1]));
+          w.y = pack_half2(__uint_as_float(dv[8 * j + 2]), __uint_as_float(dv[8 * j + 3]));
+          w.z = pack_half2(__uint_as_float(dv[8 * j + 4]), __uint_as_float(dv[8 * j + 5]));
+          w.w = pack_half2(__uint_as_float(dv[8 * j + 6]), __uint_as_float(dv[8 * j + 7]));
+          reinterpret_cast<uint4*>(gk)[j] = u;
+          reinterpret_cast<uint4*>(gv)[j] = w;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<512>(tmem);
+}
+
+// dtable[rel_index[i][j]][h] += sum_p ds[p][h][i][j]   (i, j < L).  One warp per (h, i) row and slab of problems.
+__global__ void __launch_bounds__(256)
+relpos_bias_grad_kernel(const __half* ds, int nprob, int nheads, int NP, int L, const int32_t* rel_index,
+                        float* dtable, int probs_per_block) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);  // (h, i)
+  if (row >= nheads * L) return;
+  const int h = row / L, i = row - h * L;
+  const int p0 = blockIdx.y * probs_per_block, p1 = min(nprob, p0 + probs_per_block);
+  for (int jb = lane * 8; jb < NP; jb += 256) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int pr = p0; pr < p1; ++pr) {
+      uint4 u = *reinterpret_cast<const uint4*>(ds + (((size_t)pr * nheads + h) * NP + i) * NP + jb);
+      const __half2* hh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float2 f = __half22float2(hh[q]);
+        acc[2 * q] += f.x, acc[2 * q + 1] += f.y;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (jb + q < L) atomicAdd(dtable + (size_t)rel_index[i * L + jb + q] * nheads + h, acc[q]);
+  }
+}
+
+template <int HD>
+static int launch_attn_bwd(const void* qkv, int64_t ld, const AttnBwdParams& p, int nkc, cudaStream_t s) {
+  using Cfg = AttnBwdCfg<HD>;
+  CUtensorMap tq, tdo;
+  const CUtensorMapSwizzle sw = HD == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  int rc = encode_tmap_2d_f16(&tq, qkv, p.rows_total, ld, ld, 128, HD, sw);
+  if (rc) return rc;
+  rc = encode_tmap_2d_f16(&tdo, p.dout, p.rows_total, p.nheads * HD, p.lddo, 128, HD, sw);
+  if (rc) return rc;
+  auto kern = attn_bwd_kernel<HD>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LAV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid(nkc, p.nheads, p.nprob);
+  kern<<<grid, kAttnBwdThreads, Cfg::SMEM_BYTES, s>>>(tq, tdo, p);
+  LAV_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return LAV_OK;
+}
+
+}  // namespace lav
+
+using namespace lav;
+
+extern "C" int lav_attn_bwd_f16(const void* qkv, int64_t ld, int64_t rows_total, int q_off, int k_off, int v_off,
+                                int head_dim, int nheads, int nprob, int L, float scale, const void* bias16, int NPb,
+                                const int32_t* prob_class, int class_period, const float* key_bias, int NPk,
+                                const void* out16, int64_t ldo, const void* dout16, int64_t lddo, const float* lse,
+                                float* dq_acc, int64_t lddq, void* dqkv16, int64_t lddqkv, void* ds16, int NPs,
+                                void* stream) {
+  LAV_REQUIRE(qkv && out16 && dout16 && lse && dq_acc && dqkv16, "lav_attn_bwd_f16: null pointer");
+  LAV_REQUIRE(nprob > 0 && nheads > 0 && L > 0, "lav_attn_bwd_f16: empty problem");
+  LAV_REQUIRE((ldo % 8) == 0 && (lddo % 8) == 0 && (lddqkv % 8) == 0 && (q_off % 8) == 0 && (k_off % 8) == 0 &&
+                  (v_off % 8) == 0, "lav_attn_bwd_f16: offsets / ld must be multiples of 8");
+  LAV_REQUIRE(head_dim == 32 || head_dim == 64, "lav_attn_bwd_f16: head_dim must be 32 or 64");
+  const int nkc = (L + 127) / 128;
+  LAV_REQUIRE(!bias16 || NPb >= nkc * 128, "lav_attn_bwd_f16: dense bias too small");
+  LAV_REQUIRE(!key_bias || NPk >= nkc * 128, "lav_attn_bwd_f16: key_bias too small");
+  LAV_REQUIRE(!ds16 || NPs >= nkc * 128, "lav_attn_bwd_f16: ds workspace too small");
+  AttnBwdParams p;
+  p.L = L, p.nheads = nheads, p.nprob = nprob, p.q_off = q_off, p.k_off = k_off, p.v_off = v_off, p.scale = scale;
+  p.bias16 = (const __half*)bias16, p.NPb = NPb, p.prob_class = prob_class, p.period = class_period > 0 ? class_period : 1;
+  p.key_bias = key_bias, p.NPk = NPk, p.out = (const __half*)out16, p.ldo = ldo, p.dout = (const __half*)dout16;
+  p.lddo = lddo, p.lse = lse, p.rows_total = rows_total, p.dq_acc = dq_acc, p.lddq = lddq;
+  p.dqkv = (__half*)dqkv16, p.lddqkv = lddqkv, p.ds_out = (__half*)ds16, p.NPs = NPs;
+  cudaStream_t s = (cudaStream_t)stream;
+  return head_dim == 32 ? launch_attn_bwd<32>(qkv, ld, p, nkc, s) : launch_attn_bwd<64>(qkv, ld, p, nkc, s);
+}
+
+extern "C" int lav_relpos_bias_grad(const void* ds16, int nprob, int nheads, int NP, int L, const int32_t* rel_index,
+                                    float* dtable, void* stream) {
+  LAV_REQUIRE(ds16 && rel_index && dtable && L <= NP && (NP % 8) == 0, "lav_relpos_bias_grad: bad arguments");
+  const int rows = nheads * L;
+  const int xb = (rows + 7) / 8;
+  int slabs = std::max(1, std::min(nprob, (4 * sm_count() + xb - 1) / xb));
+  const int ppb = (nprob + slabs - 1) / slabs;
+  dim3 grid(xb, (nprob + ppb - 1) / ppb);
+  relpos_bias_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)ds16, nprob, nheads, NP, L, rel_index,
+                                                                 dtable, ppb);
+  LAV_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return LAV_OK;
+}

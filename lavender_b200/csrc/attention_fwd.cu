@@ -1,0 +1,294 @@
+// Fused attention forward for sm_100a:  O = softmax(scale * Q Kᵀ + bias) V   per (problem, head, 128-row q tile).
+//   * problem = one 3-D shifted window (WindowAttention3D.forward, video_swin.py:145-170; L = 245 tokens, hd = 32)
+//               or one BERT sequence (HF BertSelfAttention via model.py:242; L <= 384, hd = 64).
+//   * Q/K/V are column slices of the fused QKV activation [rows, ld] (rows of a problem are contiguous), staged
+//     by TMA; S = Q Kᵀ is a tcgen05 MMA into TMEM (128 x NKC*128 fp32), softmax runs in registers straight from
+//     tcgen05.ld (one thread per query row), P goes to shared memory as fp16 in the UMMA K-major 128B-swizzle
+//     layout, O = P V is a second tcgen05 MMA whose accumulator aliases the dead S columns.
+//   * relative-position bias + shift mask (+ -inf on the padded key columns) come pre-expanded as a dense fp16
+//     [class][head][NP][NP] tensor (lav_relpos_bias_expand); BERT passes an additive per-key fp32 row instead.
+// Nothing of size [B_, nh, N, N] ever reaches HBM.
+#include "runtime.h"
+#include "sm100.cuh"
+
+namespace lav {
+
+constexpr int kAttnThreads = 160;  // warps 0-3: softmax (one TMEM lane quarter each); warp 4: TMA + MMA + TMEM alloc
+
+struct AttnFwdParams {
+  int L, nheads, nprob, HD;
+  int q_off, k_off, v_off;
+  float scale;
+  const __half* bias16; int NPb;           // dense bias [ncls][nheads][NPb][NPb] or null
+  const int32_t* prob_class; int period;   // class of problem p = prob_class[p % period] (null: class 0)
+  const float* key_bias;                   // [nprob][NKC*128] additive (0 / -inf) or null
+  __half* out; int64_t ldo;
+  float* lse; int64_t rows_total;
+};
+
+template <int HD, int NKC>
+struct AttnFwdCfg {
+  static constexpr int ROWB = HD * 2;                    // bytes per Q/K/V smem row == TMA swizzle span
+  static constexpr int Q_BYTES = 128 * ROWB;
+  static constexpr int KV_BYTES = NKC * 128 * ROWB;      // per K or V
+  static constexpr int P_BYTES = 128 * NKC * 128 * 2;
+  static constexpr int OFF_K = Q_BYTES, OFF_V = OFF_K + KV_BYTES, OFF_P = OFF_V + KV_BYTES;
+  static constexpr int OFF_BAR = OFF_P + P_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 64 + 1024;
+  static constexpr int TMEM_COLS = (NKC * 128 <= 256) ? 256 : 512;
+  static constexpr uint32_t SWZ = (HD == 64) ? SWZ_128B : SWZ_64B;
+  static constexpr uint32_t SBO = 8 * ROWB;              // 8-row core-matrix group stride for Q/K/V tiles
+};
+
+template <int HD, int NKC>
+__global__ void __launch_bounds__(kAttnThreads)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p) {
+  using Cfg = AttnFwdCfg<HD, NKC>;
+  constexpr int NP = NKC * 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);  // 0 load, 1 S ready, 2 P ready, 3 O ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x, h = blockIdx.y, prob = blockIdx.z;
+  const int row0 = prob * p.L;  // first token row of this problem
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQKV);
+      mbar_init(bars + 0, 1);
+      mbar_init(bars + 1, 1);
+      mbar_init(bars + 2, 128);
+      mbar_init(bars + 3, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ---- loads
+      mbar_arrive_expect_tx(bars + 0, Cfg::Q_BYTES + 2 * Cfg::KV_BYTES);
+      tma_load_2d(smem, &tmQKV, bars + 0, p.q_off + h * HD, row0 + t * 128);
+#pragma unroll
+      for (int c = 0; c < NKC; ++c) {
+        tma_load_2d(smem + Cfg::OFF_K + c * 128 * Cfg::ROWB, &tmQKV, bars + 0, p.k_off + h * HD, row0 + c * 128);
+        tma_load_2d(smem + Cfg::OFF_V + c * 128 * Cfg::ROWB, &tmQKV, bars + 0, p.v_off + h * HD, row0 + c * 128);
+      }
+      mbar_wait(bars + 0, 0, 10);
+      tc_fence_after();
+      // ---- S_c = Q K_cᵀ  (M=128, N=128, K=HD; both operands K-major)
+      constexpr uint32_t idesc_s = make_idesc_f16(128, 128, 0, 0);
+      const uint32_t sq = smem_u32(smem), sk = smem_u32(smem + Cfg::OFF_K);
+#pragma unroll
+      for (int c = 0; c < NKC; ++c)
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_f16_ss(tmem + c * 128, make_smem_desc(sq + k * 32, 0, Cfg::SBO, Cfg::SWZ),
+                      make_smem_desc(sk + c * 128 * Cfg::ROWB + k * 32, 0, Cfg::SBO, Cfg::SWZ), idesc_s, k > 0);
+      umma_commit(bars + 1);
+      // ---- O = P V  (M=128, N=HD, K=NP; A = P K-major 128B swizzle, B = V MN-major)
+      mbar_wait(bars + 2, 0, 11);
+      tc_fence_after();
+      constexpr uint32_t idesc_o = make_idesc_f16(128, HD, 0, 1);
+      const uint32_t sp = smem_u32(smem + Cfg::OFF_P), sv = smem_u32(smem + Cfg::OFF_V);
+#pragma unroll
+      for (int k = 0; k < NP / 16; ++k)
+        umma_f16_ss(tmem, make_smem_desc(sp + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024, SWZ_128B),
+                    make_smem_desc(sv + k * 16 * Cfg::ROWB, 0, Cfg::SBO, Cfg::SWZ), idesc_o, k > 0);
+      umma_commit(bars + 3);
+    }
+  } else {
+    // ---- softmax: thread = query row
+    const int i = warp * 32 + lane;  // row within the q tile == TMEM lane
+    const int qi = t * 128 + i;      // token index within the problem
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    const float sc = p.scale;
+    const __half* brow = nullptr;
+    if (p.bias16) {
+      const int cls = p.prob_class ? p.prob_class[prob % p.period] : 0;
+      brow = p.bias16 + (((size_t)cls * p.nheads + h) * p.NPb + min(qi, p.NPb - 1)) * p.NPb;
+    }
+    const float* kb = p.key_bias ? p.key_bias + (size_t)prob * NP : nullptr;
+
+    auto biased = [&](const uint32_t(&s)[32], int j0, float(&v)[32]) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(s[j]) * sc;
+      if (brow) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 u = *reinterpret_cast<const uint4*>(brow + j0 + 8 * j);
+          const __half2* hh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float2 f = __half22float2(hh[q]);
+            v[8 * j + 2 * q] += f.x, v[8 * j + 2 * q + 1] += f.y;
+          }
+        }
+      }
+      if (kb) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 f = __ldg(reinterpret_cast<const float4*>(kb + j0) + j);
+          v[4 * j] += f.x, v[4 * j + 1] += f.y, v[4 * j + 2] += f.z, v[4 * j + 3] += f.w;
+        }
+      }
+    };
+
+    mbar_wait(bars + 1, 0, 12);
+    tc_fence_after();
+    float m = -INFINITY;
+#pragma unroll 1
+    for (int j0 = 0; j0 < NP; j0 += 32) {
+      uint32_t s[32];
+      float v[32];
+      tmem_ld_32x32(trow + j0, s);
+      tmem_ld_wait();
+      biased(s, j0, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) m = fmaxf(m, v[j]);
+    }
+    if (m == -INFINITY) m = 0.f;
+    const float mlog = m * 1.4426950408889634f;
+    float l = 0.f;
+    uint8_t* prow = smem + Cfg::OFF_P + i * 128;
+#pragma unroll 1
+    for (int j0 = 0; j0 < NP; j0 += 32) {
+      uint32_t s[32];
+      float v[32];
+      tmem_ld_32x32(trow + j0, s);
+      tmem_ld_wait();
+      biased(s, j0, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        v[j] = exp2f(v[j] * 1.4426950408889634f - mlog);
+        l += v[j];
+      }
+      // P (fp16) -> smem, K-major 128B-swizzle atoms of [128 rows x 64 keys]
+      uint8_t* atom = prow + (j0 >> 6) * 16384;
+      const int chunk0 = (j0 & 63) >> 3;  // first 16-byte chunk inside the 128-byte row
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 u;
+        u.x = pack_half2(v[8 * j], v[8 * j + 1]), u.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
+        u.z = pack_half2(v[8 * j + 4], v[8 * j + 5]), u.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
+        *reinterpret_cast<uint4*>(atom + (((chunk0 + j) ^ (i & 7)) << 4)) = u;
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    mbar_arrive(bars + 2);
+
+    mbar_wait(bars + 3, 0, 13);
+    tc_fence_after();
+    const float inv = 1.f / l;
+    const bool valid = qi < p.L;
+    if (valid && p.lse) p.lse[(size_t)h * p.rows_total + row0 + qi] = m + __logf(l);
+#pragma unroll
+    for (int c0 = 0; c0 < HD; c0 += 32) {
+      uint32_t o[32];
+      tmem_ld_32x32(trow + c0, o);
+      tmem_ld_wait();
+      if (valid) {
+        __half* dst = p.out + (size_t)(row0 + qi) * p.ldo + h * HD + c0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 u;
+          u.x = pack_half2(__uint_as_float(o[8 * j]) * inv, __uint_as_float(o[8 * j + 1]) * inv);
+          u.y = pack_half2(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv);
+          u.z = pack_half2(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv);
+          u.w = pack_half2(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv);
+          reinterpret_cast<uint4*>(dst)[j] = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
+}
+
+template <int HD, int NKC>
+static int launch_attn_fwd(const void* qkv, int64_t ld, int64_t rows_total, const AttnFwdParams& p, cudaStream_t s) {
+  using Cfg = AttnFwdCfg<HD, NKC>;
+  CUtensorMap tm;
+  int rc = encode_tmap_2d_f16(&tm, qkv, rows_total, ld, ld, 128, HD,
+                              HD == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+  if (rc) return rc;
+  auto kern = attn_fwd_kernel<HD, NKC>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LAV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid((p.L + 127) / 128, p.nheads, p.nprob);
+  kern<<<grid, kAttnThreads, Cfg::SMEM_BYTES, s>>>(tm, p);
+  LAV_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return LAV_OK;
+}
+
+// dense[cls][h][i][j] = table[rel_index(i,j)][h] + (label[cls][i] != label[cls][j] ? -100 : 0), -inf for j >= L
+// (video_swin.py:153-160, compute_mask :290-305).  rel_index is passed in (int32 [L][L], the [:N,:N] slice).
+__global__ void relpos_bias_expand_kernel(const float* table, int nheads, const int32_t* rel_index, int L,
+                                          const uint8_t* labels, int ncls, __half* dense, int NP) {
+  const int i = blockIdx.x, h = blockIdx.y, cls = blockIdx.z;
+  __half* drow = dense + (((size_t)cls * nheads + h) * NP + i) * NP;
+  for (int j = threadIdx.x; j < NP; j += blockDim.x) {
+    float v;
+    if (j >= L) v = -INFINITY;
+    else if (i >= L) v = 0.f;
+    else {
+      v = table[(size_t)rel_index[i * L + j] * nheads + h];
+      if (labels && labels[cls * NP + i] != labels[cls * NP + j]) v += -100.0f;
+    }
+    drow[j] = __float2half_rn(v);
+  }
+}
+
+}  // namespace lav
+
+using namespace lav;
+
+extern "C" int lav_attn_fwd_f16(const void* qkv, int64_t ld, int64_t rows_total, int q_off, int k_off, int v_off,
+                                int head_dim, int nheads, int nprob, int L, float scale, const void* bias16, int NPb,
+                                const int32_t* prob_class, int class_period, const float* key_bias, void* out16,
+                                int64_t ldo, float* lse, void* stream) {
+  LAV_REQUIRE(qkv && out16, "lav_attn_fwd_f16: null pointer");
+  LAV_REQUIRE(nprob > 0 && nheads > 0 && L > 0, "lav_attn_fwd_f16: empty problem");
+  LAV_REQUIRE((ldo % 8) == 0 && (q_off % 8) == 0 && (k_off % 8) == 0 && (v_off % 8) == 0,
+              "lav_attn_fwd_f16: offsets / ld must be multiples of 8");
+  AttnFwdParams p;
+  p.L = L, p.nheads = nheads, p.nprob = nprob, p.HD = head_dim;
+  p.q_off = q_off, p.k_off = k_off, p.v_off = v_off, p.scale = scale;
+  p.bias16 = (const __half*)bias16, p.NPb = NPb, p.prob_class = prob_class, p.period = class_period > 0 ? class_period : 1;
+  p.key_bias = key_bias, p.out = (__half*)out16, p.ldo = ldo, p.lse = lse, p.rows_total = rows_total;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (head_dim == 32 && L <= 256) {
+    LAV_REQUIRE(!bias16 || NPb == 256, "lav_attn_fwd_f16: dense bias must be [*, *, 256, 256] for L <= 256");
+    return launch_attn_fwd<32, 2>(qkv, ld, rows_total, p, s);
+  }
+  if (head_dim == 64 && L <= 384) {
+    LAV_REQUIRE(!bias16 || NPb == 384, "lav_attn_fwd_f16: dense bias must be [*, *, 384, 384] for L <= 384");
+    return launch_attn_fwd<64, 3>(qkv, ld, rows_total, p, s);
+  }
+  return set_error(LAV_E_INVALID, "lav_attn_fwd_f16: unsupported (head_dim=%d, L=%d); supported: hd32 L<=256, hd64 L<=384",
+                   head_dim, L);
+}
+
+extern "C" int lav_relpos_bias_expand(const float* table, int nheads, const int32_t* rel_index, int L,
+                                      const uint8_t* labels, int ncls, void* dense16, int NP, void* stream) {
+  LAV_REQUIRE(table && rel_index && dense16 && ncls >= 1 && L <= NP, "lav_relpos_bias_expand: bad arguments");
+  dim3 grid(NP, nheads, ncls);
+  relpos_bias_expand_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(table, nheads, rel_index, L, labels, ncls,
+                                                                   (__half*)dense16, NP);
+  LAV_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return LAV_OK;
+}

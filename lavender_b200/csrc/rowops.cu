@@ -1,0 +1,330 @@
+// HBM-bound row kernels of the hot path: LayerNorm forward/backward (with the window-partition / cyclic-shift /
+// patch-merging gather folded into the row map), fp32->fp16 casts, column sums (bias gradients).
+// One warp per row, 128-bit accesses, fp32 statistics.
+#include "runtime.h"
+#include "sm100.cuh"
+
+namespace lav {
+
+constexpr int kRowThreads = 256;  // 8 warps = 8 rows per CTA
+
+static inline int row_grid(int64_t rows) {
+  int64_t ctas = (rows + (kRowThreads / 32) - 1) / (kRowThreads / 32);
+  int64_t cap = (int64_t)sm_count() * 16;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(ctas, cap));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// LayerNorm forward.  Output row r (width G*C) is the concatenation of G source rows of width C:
+//   src row = map ? map[r*G+g] : r*G+g      (G=1: plain / window gather;  G=4: PatchMerging gather)
+// ---------------------------------------------------------------------------------------------------------
+struct LnFwdParams {
+  const float* x; int64_t ldx;
+  const int32_t* map; int G; int C;
+  const float* gamma; const float* beta; float eps;
+  __half* y16; int64_t ldy16; float* y32; int64_t ldy32;
+  float* mean; float* rstd;
+  int rows;
+};
+
+__global__ void __launch_bounds__(kRowThreads) ln_fwd_kernel(const LnFwdParams p) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = kRowThreads / 32;
+  const int W = p.G * p.C;  // normalised width
+  const int c4 = p.C >> 2;  // float4 per source row
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < p.rows; r += gridDim.x * wpb) {
+    const float4* src[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (g < p.G) {
+        const int64_t sr = p.map ? p.map[(int64_t)r * p.G + g] : (int64_t)r * p.G + g;
+        src[g] = reinterpret_cast<const float4*>(p.x + sr * p.ldx);
+      }
+    float s = 0.f;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (g < p.G)
+        for (int i = lane; i < c4; i += 32) {
+          float4 v = src[g][i];
+          s += (v.x + v.y) + (v.z + v.w);
+        }
+    const float mean = warp_sum(s) / W;
+    float ss = 0.f;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (g < p.G)
+        for (int i = lane; i < c4; i += 32) {
+          float4 v = src[g][i];
+          float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+          ss += (a * a + b * b) + (c * c + d * d);
+        }
+    const float rstd = rsqrtf(warp_sum(ss) / W + p.eps);
+    if (lane == 0) {
+      if (p.mean) p.mean[r] = mean;
+      if (p.rstd) p.rstd[r] = rstd;
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (g < p.G)
+        for (int i = lane; i < c4; i += 32) {
+          const int col = g * p.C + i * 4;
+          float4 v = src[g][i];
+          float4 ga = *reinterpret_cast<const float4*>(p.gamma + col);
+          float4 be = *reinterpret_cast<const float4*>(p.beta + col);
+          float4 o;
+          o.x = (v.x - mean) * rstd * ga.x + be.x;
+          o.y = (v.y - mean) * rstd * ga.y + be.y;
+          o.z = (v.z - mean) * rstd * ga.z + be.z;
+          o.w = (v.w - mean) * rstd * ga.w + be.w;
+          if (p.y32) *reinterpret_cast<float4*>(p.y32 + (int64_t)r * p.ldy32 + col) = o;
+          if (p.y16) {
+            uint2 u = make_uint2(pack_half2(o.x, o.y), pack_half2(o.z, o.w));
+            *reinterpret_cast<uint2*>(p.y16 + (int64_t)r * p.ldy16 + col) = u;
+          }
+        }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// LayerNorm backward (input gradient).  For output row r (same gather as forward):
+//   xhat = (x - mean) * rstd ; a = dy*gamma ; dx = rstd * (a - mean_c(a) - xhat * mean_c(a*xhat))
+//   dx32[src row] = dx (+ add32[src row])   ; dx16[r] = (fp16) of the same value (identity rows, G == 1)
+// dy is fp16 or fp32.  Parameter gradients are produced by ln_bwd_params_kernel.
+// ---------------------------------------------------------------------------------------------------------
+struct LnBwdParams {
+  const void* dy; int64_t lddy; int dy_f32;
+  const float* x; int64_t ldx;
+  const int32_t* map; int G; int C;
+  const float* gamma; const float* mean; const float* rstd;
+  const float* add32; int64_t ldadd;
+  float* dx32; int64_t lddx32;
+  __half* dx16; int64_t lddx16;
+  float* dgamma; float* dbeta;
+  int rows;
+};
+
+__device__ __forceinline__ float4 load_dy4(const LnBwdParams& p, int r, int col) {
+  if (p.dy_f32) return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.dy) + (int64_t)r * p.lddy + col);
+  uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(p.dy) + (int64_t)r * p.lddy + col);
+  float2 a = __half22float2(*reinterpret_cast<__half2*>(&u.x));
+  float2 b = __half22float2(*reinterpret_cast<__half2*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+__global__ void __launch_bounds__(kRowThreads) ln_bwd_kernel(const LnBwdParams p) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = kRowThreads / 32;
+  const int W = p.G * p.C;
+  const int c4 = p.C >> 2;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < p.rows; r += gridDim.x * wpb) {
+    int64_t srow[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (g < p.G) srow[g] = p.map ? p.map[(int64_t)r * p.G + g] : (int64_t)r * p.G + g;
+    const float mean = p.mean[r], rstd = p.rstd[r];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (g < p.G)
+        for (int i = lane; i < c4; i += 32) {
+          const int col = g * p.C + i * 4;
+          float4 v = *reinterpret_cast<const float4*>(p.x + srow[g] * p.ldx + i * 4);
+          float4 d = load_dy4(p, r, col);
+          float4 ga = *reinterpret_cast<const float4*>(p.gamma + col);
+          float a0 = d.x * ga.x, a1 = d.y * ga.y, a2 = d.z * ga.z, a3 = d.w * ga.w;
+          s1 += (a0 + a1) + (a2 + a3);
+          s2 += (a0 * (v.x - mean) + a1 * (v.y - mean)) + (a2 * (v.z - mean) + a3 * (v.w - mean));
+        }
+    s1 = warp_sum(s1) / W;
+    s2 = warp_sum(s2) * rstd / W;  // mean_c(a * xhat)
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (g < p.G)
+        for (int i = lane; i < c4; i += 32) {
+          const int col = g * p.C + i * 4;
+          float4 v = *reinterpret_cast<const float4*>(p.x + srow[g] * p.ldx + i * 4);
+          float4 d = load_dy4(p, r, col);
+          float4 ga = *reinterpret_cast<const float4*>(p.gamma + col);
+          float4 o;
+          o.x = rstd * (d.x * ga.x - s1 - (v.x - mean) * rstd * s2);
+          o.y = rstd * (d.y * ga.y - s1 - (v.y - mean) * rstd * s2);
+          o.z = rstd * (d.z * ga.z - s1 - (v.z - mean) * rstd * s2);
+          o.w = rstd * (d.w * ga.w - s1 - (v.w - mean) * rstd * s2);
+          if (p.add32) {
+            float4 a = *reinterpret_cast<const float4*>(p.add32 + srow[g] * p.ldadd + i * 4);
+            o.x += a.x, o.y += a.y, o.z += a.z, o.w += a.w;
+          }
+          if (p.dx32) *reinterpret_cast<float4*>(p.dx32 + srow[g] * p.lddx32 + i * 4) = o;
+          if (p.dx16)
+            *reinterpret_cast<uint2*>(p.dx16 + (int64_t)r * p.lddx16 + col) =
+                make_uint2(pack_half2(o.x, o.y), pack_half2(o.z, o.w));
+        }
+  }
+}
+
+// dgamma[c] += sum_r dy[r,c]*xhat[r,c] ; dbeta[c] += sum_r dy[r,c].  Block = 32 columns x 8 row lanes.
+__global__ void __launch_bounds__(256) ln_bwd_params_kernel(const LnBwdParams p, int rows_per_block) {
+  __shared__ float sg[8][33], sb[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int W = p.G * p.C;
+  const int col = blockIdx.x * 32 + tx;
+  const int g = col / p.C, cc = col - g * p.C;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(p.rows, r0 + rows_per_block);
+  float ag = 0.f, ab = 0.f;
+  if (col < W) {
+    for (int r = r0 + ty; r < r1; r += 8) {
+      const int64_t sr = p.map ? p.map[(int64_t)r * p.G + g] : (int64_t)r * p.G + g;
+      const float xv = p.x[sr * p.ldx + cc];
+      const float d = p.dy_f32 ? reinterpret_cast<const float*>(p.dy)[(int64_t)r * p.lddy + col]
+                               : __half2float(reinterpret_cast<const __half*>(p.dy)[(int64_t)r * p.lddy + col]);
+      ag += d * (xv - p.mean[r]) * p.rstd[r];
+      ab += d;
+    }
+  }
+  sg[ty][tx] = ag, sb[ty][tx] = ab;
+  __syncthreads();
+  if (ty == 0 && col < W) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) ag += sg[k][tx], ab += sb[k][tx];
+    atomicAdd(p.dgamma + col, ag);
+    atomicAdd(p.dbeta + col, ab);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// out16[r, 0:C] = (fp16)( x[map ? map[r] : r, 0:C] * (scale ? scale[r / rows_per_scale] : 1) * alpha )
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRowThreads)
+scale_cast_kernel(const float* x, int64_t ldx, const int32_t* map, const float* scale, int rows_per_scale, float alpha,
+                  __half* out, int64_t ldo, int rows, int C) {
+  const int lane = threadIdx.x & 31, wpb = kRowThreads / 32;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+    const int64_t sr = map ? map[r] : r;
+    const float s = alpha * (scale ? scale[r / rows_per_scale] : 1.f);
+    const float4* src = reinterpret_cast<const float4*>(x + sr * ldx);
+    for (int i = lane; i < (C >> 2); i += 32) {
+      float4 v = src[i];
+      *reinterpret_cast<uint2*>(out + (int64_t)r * ldo + i * 4) =
+          make_uint2(pack_half2(v.x * s, v.y * s), pack_half2(v.z * s, v.w * s));
+    }
+    for (int c = (C & ~3) + lane; c < C; c += 32) out[(int64_t)r * ldo + c] = __float2half_rn(x[sr * ldx + c] * s);
+  }
+}
+
+// flat fp32 -> fp16 (parameter shadow copy)
+__global__ void __launch_bounds__(256) cast_flat_kernel(const float* __restrict__ src, __half* __restrict__ dst, int64_t n) {
+  const int64_t n4 = n >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(src)[i];
+    reinterpret_cast<uint2*>(dst)[i] = make_uint2(pack_half2(v.x, v.y), pack_half2(v.z, v.w));
+  }
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = __float2half_rn(src[i]);
+}
+
+// out[c] += sum_r x16[r, c]   (bias gradients).  Block = 32 columns x 8 row lanes over a slab of rows.
+__global__ void __launch_bounds__(256)
+colsum_f16_kernel(const __half* x, int64_t ld, int rows, int N, float* out, float alpha, int rows_per_block) {
+  __shared__ float sm[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + tx;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float a = 0.f;
+  if (col < N)
+    for (int r = r0 + ty; r < r1; r += 8) a += __half2float(x[(int64_t)r * ld + col]);
+  sm[ty][tx] = a;
+  __syncthreads();
+  if (ty == 0 && col < N) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) a += sm[k][tx];
+    atomicAdd(out + col, a * alpha);
+  }
+}
+
+static int slab_rows(int rows, int col_blocks) {
+  // enough row slabs to fill the machine a few times, at least 64 rows each
+  int want = std::max(1, (4 * sm_count()) / std::max(1, col_blocks));
+  int rpb = std::max(64, (rows + want - 1) / want);
+  return (rpb + 7) / 8 * 8;
+}
+
+}  // namespace lav
+
+using namespace lav;
+
+extern "C" int lav_layernorm_fwd(const float* x, int64_t ldx, const int32_t* row_map, int G, int C, const float* gamma,
+                                 const float* beta, float eps, void* y16, int64_t ldy16, float* y32, int64_t ldy32,
+                                 float* mean, float* rstd, int rows, void* stream) {
+  LAV_REQUIRE(x && gamma && beta && (y16 || y32), "lav_layernorm_fwd: null pointer");
+  LAV_REQUIRE(G >= 1 && G <= 4 && C > 0 && (C % 4) == 0 && (ldx % 4) == 0, "lav_layernorm_fwd: need C%%4==0, 1<=G<=4");
+  LAV_REQUIRE((!y16 || ldy16 % 4 == 0) && (!y32 || ldy32 % 4 == 0), "lav_layernorm_fwd: output ld must be %%4");
+  if (rows <= 0) return LAV_OK;
+  LnFwdParams p{x, ldx, row_map, G, C, gamma, beta, eps, (__half*)y16, ldy16, y32, ldy32, mean, rstd, rows};
+  ln_fwd_kernel<<<row_grid(rows), kRowThreads, 0, (cudaStream_t)stream>>>(p);
+  LAV_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return LAV_OK;
+}
+
+extern "C" int lav_layernorm_bwd(const void* dy, int64_t lddy, int dy_is_f32, const float* x, int64_t ldx,
+                                 const int32_t* row_map, int G, int C, const float* gamma, const float* mean,
+                                 const float* rstd, const float* add32, int64_t ldadd, float* dx32, int64_t lddx32,
+                                 void* dx16, int64_t lddx16, float* dgamma, float* dbeta, int rows, void* stream) {
+  LAV_REQUIRE(dy && x && gamma && mean && rstd && (dx32 || dx16), "lav_layernorm_bwd: null pointer");
+  LAV_REQUIRE(G >= 1 && G <= 4 && C > 0 && (C % 4) == 0 && (ldx % 4) == 0 && (lddy % 4) == 0,
+              "lav_layernorm_bwd: need C%%4==0, 1<=G<=4, ld%%4==0");
+  LAV_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "lav_layernorm_bwd: dgamma/dbeta must come together");
+  if (rows <= 0) return LAV_OK;
+  LnBwdParams p{dy, lddy, dy_is_f32, x, ldx, row_map, G, C, gamma, mean, rstd, add32, ldadd,
+                dx32, lddx32, (__half*)dx16, lddx16, dgamma, dbeta, rows};
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dgamma) {  // must read x before an in-place dx32 overwrite of the same rows
+    const int cb = (G * C + 31) / 32;
+    const int rpb = slab_rows(rows, cb);
+    dim3 grid(cb, (rows + rpb - 1) / rpb);
+    ln_bwd_params_kernel<<<grid, 256, 0, s>>>(p, rpb);
+    LAV_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  ln_bwd_kernel<<<row_grid(rows), kRowThreads, 0, s>>>(p);
+  LAV_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return LAV_OK;
+}
+
+extern "C" int lav_scale_cast_f16(const float* x, int64_t ldx, const int32_t* row_map, const float* row_scale,
+                                  int rows_per_scale, float alpha, void* out16, int64_t ldo, int rows, int C,
+                                  void* stream) {
+  LAV_REQUIRE(x && out16, "lav_scale_cast_f16: null pointer");
+  LAV_REQUIRE((ldx % 4) == 0 && (ldo % 4) == 0, "lav_scale_cast_f16: ld must be %%4");
+  if (rows <= 0) return LAV_OK;
+  scale_cast_kernel<<<row_grid(rows), kRowThreads, 0, (cudaStream_t)stream>>>(
+      x, ldx, row_map, row_scale, rows_per_scale > 0 ? rows_per_scale : 1, alpha, (__half*)out16, ldo, rows, C);
+  LAV_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return LAV_OK;
+}
+
+extern "C" int lav_cast_f32_to_f16(const float* src, void* dst, int64_t n, void* stream) {
+  LAV_REQUIRE(src && dst, "lav_cast_f32_to_f16: null pointer");
+  LAV_REQUIRE(((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 8) == 0, "lav_cast_f32_to_f16: unaligned");
+  if (n <= 0) return LAV_OK;
+  int grid = (int)std::min<int64_t>((n / 4 + 255) / 256 + 1, (int64_t)sm_count() * 8);
+  cast_flat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, (__half*)dst, n);
+  LAV_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return LAV_OK;
+}
+
+extern "C" int lav_colsum_f16(const void* x16, int64_t ld, int rows, int N, float* out, float alpha, void* stream) {
+  LAV_REQUIRE(x16 && out, "lav_colsum_f16: null pointer");
+  if (rows <= 0 || N <= 0) return LAV_OK;
+  const int cb = (N + 31) / 32;
+  const int rpb = slab_rows(rows, cb);
+  dim3 grid(cb, (rows + rpb - 1) / rpb);
+  colsum_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)x16, ld, rows, N, out, alpha, rpb);
+  LAV_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return LAV_OK;
+}

@@ -53,7 +53,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-__device__ __noinline__ void mbar_timeout(int tag) {
+static __device__ __noinline__ void mbar_timeout(int tag) {
   printf("[lavender_b200] mbarrier wait timed out: block %d thread %d tag %d\n", (int)blockIdx.x,
          (int)threadIdx.x, tag);
   __trap();

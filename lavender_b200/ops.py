@@ -55,3 +55,86 @@ def gemm(a, b, out, *, M, N, K, a_major=L.MAJOR_K, b_major=L.MAJOR_K, bias=None,
                               ctypes.byref(e), split_k, _stream())
     L.check(rc, "lav_gemm_f16")
     return out
+
+
+def _p(t):
+    return t.data_ptr() if t is not None else None
+
+
+def layernorm_fwd(x, gamma, beta, eps, *, rows, C, G=1, row_map=None, out16=None, out32=None, mean=None, rstd=None):
+    """out[r] = LN(concat_g x[row_map[r*G+g]]) (width G*C); x fp32 2-D."""
+    assert x.dtype == torch.float32 and x.stride(-1) == 1
+    rc = L.lib().lav_layernorm_fwd(_p(x), x.stride(0), _p(row_map), G, C, _p(gamma), _p(beta), eps,
+                                   _p(out16), out16.stride(0) if out16 is not None else 0,
+                                   _p(out32), out32.stride(0) if out32 is not None else 0,
+                                   _p(mean), _p(rstd), rows, _stream())
+    L.check(rc, "lav_layernorm_fwd")
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, *, rows, C, G=1, row_map=None, add32=None, dx32=None, dx16=None,
+                  dgamma=None, dbeta=None):
+    assert dy.dtype in (F16, torch.float32) and x.dtype == torch.float32
+    rc = L.lib().lav_layernorm_bwd(_p(dy), dy.stride(0), int(dy.dtype == torch.float32), _p(x), x.stride(0),
+                                   _p(row_map), G, C, _p(gamma), _p(mean), _p(rstd),
+                                   _p(add32), add32.stride(0) if add32 is not None else 0,
+                                   _p(dx32), dx32.stride(0) if dx32 is not None else 0,
+                                   _p(dx16), dx16.stride(0) if dx16 is not None else 0,
+                                   _p(dgamma), _p(dbeta), rows, _stream())
+    L.check(rc, "lav_layernorm_bwd")
+
+
+def scale_cast(x, out16, *, rows, C, row_map=None, row_scale=None, rows_per_scale=1, alpha=1.0):
+    assert x.dtype == torch.float32 and out16.dtype == F16
+    rc = L.lib().lav_scale_cast_f16(_p(x), x.stride(0), _p(row_map), _p(row_scale), rows_per_scale, alpha,
+                                    _p(out16), out16.stride(0), rows, C, _stream())
+    L.check(rc, "lav_scale_cast_f16")
+    return out16
+
+
+def cast_f16(src, dst):
+    assert src.dtype == torch.float32 and dst.dtype == F16 and src.numel() == dst.numel()
+    assert src.is_contiguous() and dst.is_contiguous()
+    L.check(L.lib().lav_cast_f32_to_f16(_p(src), _p(dst), src.numel(), _stream()), "lav_cast_f32_to_f16")
+    return dst
+
+
+def colsum(x16, out, *, rows, N, alpha=1.0):
+    assert x16.dtype == F16 and out.dtype == torch.float32
+    L.check(L.lib().lav_colsum_f16(_p(x16), x16.stride(0), rows, N, _p(out), alpha, _stream()), "lav_colsum_f16")
+
+
+def attn_fwd(qkv, out, lse, *, q_off, k_off, v_off, head_dim, nheads, nprob, L_tok, scale, bias16=None,
+             prob_class=None, key_bias=None):
+    _chk16(qkv, "qkv")
+    _chk16(out, "out")
+    rc = L.lib().lav_attn_fwd_f16(_p(qkv), qkv.stride(0), qkv.shape[0], q_off, k_off, v_off, head_dim, nheads, nprob,
+                                  L_tok, scale, _p(bias16), bias16.shape[-1] if bias16 is not None else 0,
+                                  _p(prob_class), prob_class.numel() if prob_class is not None else 1, _p(key_bias),
+                                  _p(out), out.stride(0), _p(lse), _stream())
+    L.check(rc, "lav_attn_fwd_f16")
+
+
+def attn_bwd(qkv, out, dout, lse, dq_acc, dqkv, *, q_off, k_off, v_off, head_dim, nheads, nprob, L_tok, scale,
+             bias16=None, prob_class=None, key_bias=None, ds16=None):
+    rc = L.lib().lav_attn_bwd_f16(_p(qkv), qkv.stride(0), qkv.shape[0], q_off, k_off, v_off, head_dim, nheads, nprob,
+                                  L_tok, scale, _p(bias16), bias16.shape[-1] if bias16 is not None else 0,
+                                  _p(prob_class), prob_class.numel() if prob_class is not None else 1,
+                                  _p(key_bias), key_bias.shape[-1] if key_bias is not None else 0,
+                                  _p(out), out.stride(0), _p(dout), dout.stride(0), _p(lse),
+                                  _p(dq_acc), dq_acc.stride(0), _p(dqkv), dqkv.stride(0),
+                                  _p(ds16), ds16.shape[-1] if ds16 is not None else 0, _stream())
+    L.check(rc, "lav_attn_bwd_f16")
+
+
+def relpos_bias_expand(table, rel_index, L_tok, labels, dense16):
+    """dense16: [ncls, nheads, NP, NP] fp16; labels: uint8 [ncls, NP] or None."""
+    ncls, nheads, NP, _ = dense16.shape
+    rc = L.lib().lav_relpos_bias_expand(_p(table), nheads, _p(rel_index), L_tok, _p(labels), ncls, _p(dense16), NP,
+                                        _stream())
+    L.check(rc, "lav_relpos_bias_expand")
+
+
+def relpos_bias_grad(ds16, rel_index, L_tok, dtable):
+    nprob, nheads, NP, _ = ds16.shape
+    rc = L.lib().lav_relpos_bias_grad(_p(ds16), nprob, nheads, NP, L_tok, _p(rel_index), _p(dtable), _stream())
+    L.check(rc, "lav_relpos_bias_grad")

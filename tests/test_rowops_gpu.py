@@ -1,0 +1,75 @@
+"""Row kernels (LayerNorm fwd/bwd with gather maps, casts, column sums) vs plain PyTorch fp32."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("rows,C,G", [(1000, 96, 1), (4096, 128, 1), (777, 768, 1), (980, 128, 4), (245, 512, 4),
+                                      (300, 1024, 1)])
+def test_layernorm_fwd_bwd(rows, C, G):
+    from lavender_b200 import ops
+    torch.manual_seed(0)
+    W = G * C
+    nsrc = rows * G
+    x = torch.randn(nsrc, C, device="cuda") * 2 + 0.5
+    gamma = 1 + 0.1 * torch.randn(W, device="cuda")
+    beta = 0.1 * torch.randn(W, device="cuda")
+    row_map = torch.randperm(nsrc, device="cuda").to(torch.int32)
+    y16 = torch.zeros(rows, W, device="cuda", dtype=torch.float16)
+    y32 = torch.zeros(rows, W, device="cuda")
+    mean = torch.zeros(rows, device="cuda")
+    rstd = torch.zeros(rows, device="cuda")
+    ops.layernorm_fwd(x, gamma, beta, 1e-5, rows=rows, C=C, G=G, row_map=row_map, out16=y16, out32=y32, mean=mean,
+                      rstd=rstd)
+    xg = x.clone().requires_grad_(True)
+    gref, bref = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    gathered = xg[row_map.long()].view(rows, W)
+    yref = F.layer_norm(gathered, (W,), gref, bref, 1e-5)
+    assert (y32 - yref).abs().max().item() < 2e-5
+    assert (y16.float() - yref).abs().max().item() < 5e-3
+
+    dy = torch.randn(rows, W, device="cuda")
+    add = torch.randn(nsrc, C, device="cuda")
+    yref.backward(dy)
+    for dyt, tol in ((dy, 2e-4), (dy.half(), 2e-2)):
+        dx32 = torch.zeros(nsrc, C, device="cuda")
+        dgamma = torch.zeros(W, device="cuda")
+        dbeta = torch.zeros(W, device="cuda")
+        dx16 = torch.zeros(rows, W, device="cuda", dtype=torch.float16) if G == 1 else None
+        ops.layernorm_bwd(dyt, x, gamma, mean, rstd, rows=rows, C=C, G=G, row_map=row_map, add32=add, dx32=dx32,
+                          dx16=dx16, dgamma=dgamma, dbeta=dbeta)
+        assert (dx32 - (xg.grad + add)).abs().max().item() < tol
+        assert (dgamma - gref.grad).abs().max().item() < tol * rows ** 0.5 * 4
+        assert (dbeta - bref.grad).abs().max().item() < tol * rows ** 0.5 * 4
+        if dx16 is not None:
+            assert (dx16.float() - (xg.grad + add)[row_map.long()]).abs().max().item() < 2e-2
+
+
+def test_layernorm_identity_no_map_eps12():
+    from lavender_b200 import ops
+    x = torch.randn(333, 768, device="cuda")
+    g, b = torch.randn(768, device="cuda"), torch.randn(768, device="cuda")
+    y = torch.zeros_like(x)
+    ops.layernorm_fwd(x, g, b, 1e-12, rows=333, C=768, out32=y)
+    assert (y - F.layer_norm(x, (768,), g, b, 1e-12)).abs().max().item() < 3e-5
+
+
+def test_scale_cast_and_colsum_and_flatcast():
+    from lavender_b200 import ops
+    rows, C = 980, 96
+    x = torch.randn(rows, C, device="cuda")
+    perm = torch.randperm(rows, device="cuda").to(torch.int32)
+    scale = torch.tensor([1.25, 0.0, 1.25, 1.25], device="cuda")
+    out = torch.zeros(rows, 104, device="cuda", dtype=torch.float16)
+    ops.scale_cast(x, out, rows=rows, C=C, row_map=perm, row_scale=scale, rows_per_scale=245, alpha=2.0)
+    ref = (x[perm.long()] * scale.repeat_interleave(245)[:, None] * 2.0).half()
+    assert torch.equal(out[:, :C], ref)
+    acc = torch.ones(C, device="cuda")
+    ops.colsum(out, acc, rows=rows, N=C, alpha=0.5)
+    assert (acc - (1 + 0.5 * ref.float().sum(0))).abs().max().item() < 1e-2
+    src = torch.randn(1_000_003, device="cuda")
+    dst = torch.zeros(1_000_003, device="cuda", dtype=torch.float16)
+    ops.cast_f16(src, dst)
+    assert torch.equal(dst, src.half())
