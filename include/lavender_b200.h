@@ -118,6 +118,10 @@ int lav_scale_cast_f16(const float* x, int64_t ldx, const int32_t* row_map, cons
  * agent.py:219) */
 int lav_cast_f32_to_f16(const float* src, void* dst, int64_t n, void* stream);
 
+/* out16 = dy16 * gelu_erf'(pre16), flat fp16 (backward of BertPredictionHeadTransform's GELU,
+ * main_pretrain_mlm.py:46-48; the other GELUs are fused into GEMM epilogues) */
+int lav_gelu_bwd_f16(const void* dy16, const void* pre16, void* out16, int64_t n, void* stream);
+
 /* out[c] += alpha * sum_r x16[r, c]  (bias gradients of every nn.Linear on the path) */
 int lav_colsum_f16(const void* x16, int64_t ld, int rows, int N, float* out, float alpha, void* stream);
 

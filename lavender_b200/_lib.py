@@ -48,6 +48,7 @@ SIGNATURES = {
     "lav_scale_cast_f16": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_float, c_void_p, c_int64, c_int,
                                    c_int, c_void_p]),
     "lav_cast_f32_to_f16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "lav_gelu_bwd_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "lav_colsum_f16": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_float, c_void_p]),
     "lav_attn_fwd_f16": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                                  c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),

@@ -202,13 +202,17 @@ scale_cast_kernel(const float* x, int64_t ldx, const int32_t* map, const float* 
   for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
     const int64_t sr = map ? map[r] : r;
     const float s = alpha * (scale ? scale[r / rows_per_scale] : 1.f);
-    const float4* src = reinterpret_cast<const float4*>(x + sr * ldx);
-    for (int i = lane; i < (C >> 2); i += 32) {
-      float4 v = src[i];
-      *reinterpret_cast<uint2*>(out + (int64_t)r * ldo + i * 4) =
-          make_uint2(pack_half2(v.x * s, v.y * s), pack_half2(v.z * s, v.w * s));
+    if ((ldx & 3) == 0) {
+      const float4* src = reinterpret_cast<const float4*>(x + sr * ldx);
+      for (int i = lane; i < (C >> 2); i += 32) {
+        float4 v = src[i];
+        *reinterpret_cast<uint2*>(out + (int64_t)r * ldo + i * 4) =
+            make_uint2(pack_half2(v.x * s, v.y * s), pack_half2(v.z * s, v.w * s));
+      }
+      for (int c = (C & ~3) + lane; c < C; c += 32) out[(int64_t)r * ldo + c] = __float2half_rn(x[sr * ldx + c] * s);
+    } else {  // unaligned rows (e.g. fp32 logit gradients with ld = 30522)
+      for (int c = lane; c < C; c += 32) out[(int64_t)r * ldo + c] = __float2half_rn(x[sr * ldx + c] * s);
     }
-    for (int c = (C & ~3) + lane; c < C; c += 32) out[(int64_t)r * ldo + c] = __float2half_rn(x[sr * ldx + c] * s);
   }
 }
 
@@ -239,6 +243,14 @@ colsum_f16_kernel(const __half* x, int64_t ld, int rows, int N, float* out, floa
 #pragma unroll
     for (int k = 1; k < 8; ++k) a += sm[k][tx];
     atomicAdd(out + col, a * alpha);
+  }
+}
+
+// out16 = dy16 * gelu_erf'(pre16)   (flat, n % 2 == 0)
+__global__ void __launch_bounds__(256) gelu_bwd_kernel(const __half2* dy, const __half2* pre, __half2* out, int64_t n2) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
+    float2 d = __half22float2(dy[i]), x = __half22float2(pre[i]);
+    out[i] = __floats2half2_rn(d.x * gelu_erf_grad(x.x), d.y * gelu_erf_grad(x.y));
   }
 }
 
@@ -297,7 +309,7 @@ extern "C" int lav_scale_cast_f16(const float* x, int64_t ldx, const int32_t* ro
                                   int rows_per_scale, float alpha, void* out16, int64_t ldo, int rows, int C,
                                   void* stream) {
   LAV_REQUIRE(x && out16, "lav_scale_cast_f16: null pointer");
-  LAV_REQUIRE((ldx % 4) == 0 && (ldo % 4) == 0, "lav_scale_cast_f16: ld must be %%4");
+  LAV_REQUIRE((ldo % 4) == 0, "lav_scale_cast_f16: output ld must be %%4");
   if (rows <= 0) return LAV_OK;
   scale_cast_kernel<<<row_grid(rows), kRowThreads, 0, (cudaStream_t)stream>>>(
       x, ldx, row_map, row_scale, rows_per_scale > 0 ? rows_per_scale : 1, alpha, (__half*)out16, ldo, rows, C);
@@ -324,6 +336,16 @@ extern "C" int lav_colsum_f16(const void* x16, int64_t ld, int rows, int N, floa
   const int rpb = slab_rows(rows, cb);
   dim3 grid(cb, (rows + rpb - 1) / rpb);
   colsum_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)x16, ld, rows, N, out, alpha, rpb);
+  LAV_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return LAV_OK;
+}
+
+extern "C" int lav_gelu_bwd_f16(const void* dy16, const void* pre16, void* out16, int64_t n, void* stream) {
+  LAV_REQUIRE(dy16 && pre16 && out16 && (n % 2) == 0, "lav_gelu_bwd_f16: bad arguments");
+  if (n <= 0) return LAV_OK;
+  int grid = (int)std::min<int64_t>((n / 2 + 255) / 256, (int64_t)sm_count() * 8);
+  gelu_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half2*)dy16, (const __half2*)pre16, (__half2*)out16, n / 2);
   LAV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return LAV_OK;

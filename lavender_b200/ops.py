@@ -138,3 +138,9 @@ def relpos_bias_grad(ds16, rel_index, L_tok, dtable):
     nprob, nheads, NP, _ = ds16.shape
     rc = L.lib().lav_relpos_bias_grad(_p(ds16), nprob, nheads, NP, L_tok, _p(rel_index), _p(dtable), _stream())
     L.check(rc, "lav_relpos_bias_grad")
+
+
+def gelu_bwd(dy16, pre16, out16):
+    assert dy16.is_contiguous() and pre16.is_contiguous() and out16.is_contiguous()
+    L.check(L.lib().lav_gelu_bwd_f16(_p(dy16), _p(pre16), _p(out16), dy16.numel(), _stream()), "lav_gelu_bwd_f16")
+    return out16
