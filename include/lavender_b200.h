@@ -158,6 +158,45 @@ int lav_relpos_bias_expand(const float* table, int nheads, const int32_t* rel_in
 int lav_relpos_bias_grad(const void* ds16, int nprob, int nheads, int NP, int L, const int32_t* rel_index,
                          float* dtable, void* stream);
 
+/* ---- token embeddings (HBM-bound row kernels) ------------------------------------------------------
+ * HF BertEmbeddings forward as reached through EncTxt.forward (model.py:125-142, txt_backbone_embed_only):
+ *   sum32[r] = word[ids[r]] + type[type_ids ? type_ids[r] : 0] + pos[pos_ids ? pos_ids[r] : r % Lt]
+ *   y32[r]   = LayerNorm(sum32[r]) (eps 1e-12), mean / rstd saved for lav_layernorm_bwd. */
+int lav_bert_embed_ln_fwd(const int64_t* ids, const int64_t* pos_ids, const int64_t* type_ids, int rows, int Lt, int C,
+                          int vocab, int max_pos, int n_types, const float* word, const float* pos, const float* type,
+                          const float* gamma, const float* beta, float eps, float* sum32, float* y32, float* mean,
+                          float* rstd, void* stream);
+/* d{word,pos,type}[index[r]] += dsum32[r]  (autograd of the three nn.Embedding lookups; fp32 atomics) */
+int lav_bert_embed_bwd(const float* dsum32, const int64_t* ids, const int64_t* pos_ids, const int64_t* type_ids,
+                       int rows, int Lt, int C, int vocab, int max_pos, int n_types, float* dword, float* dpos,
+                       float* dtype, void* stream);
+
+/* EncVideo.forward token assembly, model.py:69-85: row (b,t,s), s in [0, 1+hw):
+ *   sum32 = (s == 0 ? emb_cls : feat[(b*T+t)*hw + s-1]) + emb_pos[s] + (odr_swap[b*T+t] ? emb_odr : emb_len[t])
+ *   y32   = LayerNorm(sum32) (eps 1e-5).  odr_swap (uint8 [B*T], may be NULL) marks the frames whose emb_len is
+ *   replaced by emb_odr (model.py:72-81). */
+int lav_vid_embed_ln_fwd(const float* feat, int64_t ldf, const float* emb_cls, const float* emb_pos,
+                         const float* emb_len, const float* emb_odr, const uint8_t* odr_swap, int B, int T, int hw,
+                         int C, const float* gamma, const float* beta, float eps, float* sum32, float* y32,
+                         float* mean, float* rstd, void* stream);
+/* Backward of the assembly from dsum32 [B*T*(1+hw), C]: dfeat (fp16 and/or fp32, rows s >= 1) and
+ * demb_cls / demb_pos / demb_len / demb_odr (+=, any may be NULL). */
+int lav_vid_embed_bwd(const float* dsum32, int B, int T, int hw, int C, const uint8_t* odr_swap, void* dfeat16,
+                      int64_t lddf16, float* dfeat32, int64_t lddf32, float* demb_cls, float* demb_pos,
+                      float* demb_len, float* demb_odr, void* stream);
+
+/* ---- cross entropy over the vocabulary -------------------------------------------------------------
+ * nn.CrossEntropyLoss(ignore_index) of agent.py:73 on the MLM / VTM logits (main_pretrain_mlm.py:158-163).
+ * Forward: row_lse[r] = logsumexp(logits[r, :V]); loss_sum += sum over labelled rows of (lse - logit[label]);
+ * count += number of labelled rows (both fp32 device scalars, zeroed by the caller; loss = loss_sum / count). */
+int lav_xent_fwd(const float* logits, int64_t ld, const int64_t* labels, int rows, int V, int64_t ignore_index,
+                 float* row_lse, float* row_loss, float* loss_sum, float* count, void* stream);
+/* Backward: d[r,c] = (*gout / *count) * (softmax(logits[r])[c] - [c == label[r]]) on labelled rows, 0 elsewhere;
+ * written as fp32 (d32) and/or fp16 (d16, padding columns up to a multiple of 8 zeroed). */
+int lav_xent_bwd(const float* logits, int64_t ld, const int64_t* labels, int rows, int V, int64_t ignore_index,
+                 const float* row_lse, const float* gout, const float* count, float* d32, int64_t ldd32, void* d16,
+                 int64_t ldd16, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,6 +64,7 @@ class ParamArena:
         self._ver16 = None
         self._grad_views = {}
         self._clean = set()
+        self.on_swin_backward = None  # set by dist.GradSync: called when the video encoder's backward begins
 
     # ---- validity / shadow ------------------------------------------------------------------------
     def valid(self):
@@ -124,6 +125,16 @@ class ParamArena:
             elif p.grad.data_ptr() != gv.data_ptr():
                 gv.copy_(p.grad)
                 p.grad = gv
+
+    def finalize_grads(self):
+        """After backward: gradients that torch autograd produced for glue ops (e.g. `emb_task` indexing) are moved
+        into the arena so that the flat buffer holds every gradient (one all-reduce, one clip, one optimizer pass)."""
+        for p in self.params:
+            if p.grad is not None:
+                gv = self.g(p)
+                if p.grad.data_ptr() != gv.data_ptr():
+                    gv.copy_(p.grad)
+                    p.grad = gv
 
     def zero_grads(self, set_to_none=True):
         for p in self.params:

@@ -144,3 +144,59 @@ def gelu_bwd(dy16, pre16, out16):
     assert dy16.is_contiguous() and pre16.is_contiguous() and out16.is_contiguous()
     L.check(L.lib().lav_gelu_bwd_f16(_p(dy16), _p(pre16), _p(out16), dy16.numel(), _stream()), "lav_gelu_bwd_f16")
     return out16
+
+
+def bert_embed_ln_fwd(ids, pos_ids, type_ids, word, pos, typ, gamma, beta, eps, sum32, y32, mean, rstd, *, Lt):
+    """ids (int64, contiguous, `rows` elements); tables fp32 [*, C]."""
+    rows, C = ids.numel(), word.shape[1]
+    for t in (ids, pos_ids, type_ids):
+        assert t is None or (t.dtype == torch.int64 and t.is_contiguous() and t.numel() == rows)
+    rc = L.lib().lav_bert_embed_ln_fwd(_p(ids), _p(pos_ids), _p(type_ids), rows, Lt, C, word.shape[0], pos.shape[0],
+                                       typ.shape[0], _p(word), _p(pos), _p(typ), _p(gamma), _p(beta), eps, _p(sum32),
+                                       _p(y32), _p(mean), _p(rstd), _stream())
+    L.check(rc, "lav_bert_embed_ln_fwd")
+
+
+def bert_embed_bwd(dsum32, ids, pos_ids, type_ids, dword, dpos, dtyp, *, Lt):
+    rows, C = ids.numel(), dsum32.shape[-1]
+    assert dsum32.is_contiguous() and dsum32.dtype == torch.float32
+    rc = L.lib().lav_bert_embed_bwd(_p(dsum32), _p(ids), _p(pos_ids), _p(type_ids), rows, Lt, C, dword.shape[0],
+                                    dpos.shape[0], dtyp.shape[0], _p(dword), _p(dpos), _p(dtyp), _stream())
+    L.check(rc, "lav_bert_embed_bwd")
+
+
+def vid_embed_ln_fwd(feat, emb_cls, emb_pos, emb_len, emb_odr, odr_swap, gamma, beta, eps, sum32, y32, mean, rstd, *,
+                     B, T, hw):
+    C = feat.shape[-1]
+    assert feat.dtype == torch.float32 and feat.stride(-1) == 1 and feat.dim() == 2
+    rc = L.lib().lav_vid_embed_ln_fwd(_p(feat), feat.stride(0), _p(emb_cls), _p(emb_pos), _p(emb_len), _p(emb_odr),
+                                      _p(odr_swap), B, T, hw, C, _p(gamma), _p(beta), eps, _p(sum32), _p(y32), _p(mean),
+                                      _p(rstd), _stream())
+    L.check(rc, "lav_vid_embed_ln_fwd")
+
+
+def vid_embed_bwd(dsum32, odr_swap, *, B, T, hw, C, dfeat16=None, dfeat32=None, demb_cls=None, demb_pos=None,
+                  demb_len=None, demb_odr=None):
+    assert dsum32.is_contiguous() and dsum32.dtype == torch.float32
+    rc = L.lib().lav_vid_embed_bwd(_p(dsum32), B, T, hw, C, _p(odr_swap), _p(dfeat16),
+                                   dfeat16.stride(0) if dfeat16 is not None else 0, _p(dfeat32),
+                                   dfeat32.stride(0) if dfeat32 is not None else 0, _p(demb_cls), _p(demb_pos),
+                                   _p(demb_len), _p(demb_odr), _stream())
+    L.check(rc, "lav_vid_embed_bwd")
+
+
+def xent_fwd(logits, labels, ignore_index, row_lse, row_loss, loss_sum, count):
+    """logits fp32 [rows, V] (row stride >= V); labels int64 [rows]."""
+    rows, V = logits.shape
+    assert logits.dtype == torch.float32 and logits.stride(1) == 1 and labels.dtype == torch.int64
+    rc = L.lib().lav_xent_fwd(_p(logits), logits.stride(0), _p(labels), rows, V, ignore_index, _p(row_lse),
+                              _p(row_loss), _p(loss_sum), _p(count), _stream())
+    L.check(rc, "lav_xent_fwd")
+
+
+def xent_bwd(logits, labels, ignore_index, row_lse, gout, count, d32=None, d16=None):
+    rows, V = logits.shape
+    rc = L.lib().lav_xent_bwd(_p(logits), logits.stride(0), _p(labels), rows, V, ignore_index, _p(row_lse), _p(gout),
+                              _p(count), _p(d32), d32.stride(0) if d32 is not None else 0, _p(d16),
+                              d16.stride(0) if d16 is not None else 0, _stream())
+    L.check(rc, "lav_xent_bwd")

@@ -1,0 +1,84 @@
+"""Unified-MLM pre-training model: MLM + video-text-matching-as-MLM (main_pretrain_mlm.py:42-119).
+
+`LAVENDER_Pretrain_MLM` keeps the reference's constructor, attributes (`fc_mtm`, `emb_task`, `task_tok2id`,
+`vtm_batch`) and forward contract (dict batch in -> dict of logits / labels out) but builds the B*_O VTM pairs
+with index gathers instead of the reference's per-sample Python loop; the pair order, the numpy
+RNG call sequence (main_pretrain_mlm.py:90) and therefore the outputs are identical.
+The reference's own `LAVENDER_Pretrain_MLM` (the unchanged script) also runs on top of lavender_b200.model —
+see INTEGRATION.md.
+"""
+from collections import defaultdict
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .model import LAVENDER_Base, build_mlm_head
+
+
+class LAVENDER_Pretrain_MLM(LAVENDER_Base):
+    def __init__(self, args, tokzr=None):
+        super().__init__(args, tokzr)
+        self.patch_size = args.size_patch
+        self.fc_mtm, _ = build_mlm_head(args.tokenizer, args)
+        self.vtm_batch = min(args.size_batch, 4)
+        self.task_tok2id = {"vtm": 0, "mc": 1, "oe": 2, "cap": 3}
+        self.emb_task = nn.Parameter(0.02 * torch.randn(10, self.hidden_size))
+
+    @staticmethod
+    def draw_negatives(B, O):
+        """One np.random.permutation per clip, exactly as main_pretrain_mlm.py:90-91 consumes the numpy RNG."""
+        return [np.random.permutation([j for j in range(B) if j != i])[:max(O - 1, 0)] for i in range(B)]
+
+    def forward(self, batch):
+        batch = defaultdict(lambda: None, batch)
+        img, txt, mask = batch["img"], batch["txt"], batch["mask"]
+        B, T, _, H, W = img.shape
+        Lv = (1 + (H // self.patch_size) * (W // self.patch_size)) * T
+        O = min(B, self.vtm_batch)
+
+        feat_img, mask_img, feat_txt, mask_txt = self.go_feat(img, txt, mask, vt_mask=batch["vt_mask"])
+        out, _ = self.go_cross(feat_img, mask_img, feat_txt, mask_txt)
+        out_mtm = self.fc_mtm(out[:, Lv:])
+
+        # VTM: clip i paired with its own caption (label "true") then with O-1 other captions ("false")
+        negs = batch["vtm_negatives"] if batch["vtm_negatives"] is not None else self.draw_negatives(B, O)
+        vid_idx, txt_idx, label = [], [], []
+        for i in range(B):
+            vid_idx += [i] * O
+            txt_idx += [i] + [int(j) for j in negs[i][:O - 1]]
+            label += [self.true_token_id] + [self.false_token_id] * (O - 1)
+        dev = img.device
+        vi = torch.tensor(vid_idx, device=dev)
+        ti = torch.tensor(txt_idx, device=dev)
+        p_txt, p_mask, p_feat = self.prepro_txt_inputs(txt[ti], mask_txt[ti], feat_txt[ti], task_name="vtm",
+                                                       prompt=batch["vtm_prompt"])
+        ans_vtm = torch.full_like(p_txt, -1)
+        ans_vtm[:, -1] = torch.tensor(label, device=dev, dtype=ans_vtm.dtype)
+        out, _ = self.go_cross(feat_img[vi], mask_img[vi], p_feat, p_mask)
+        out_vtm = self.fc_mtm(out[:, Lv:])
+        return {"out_vtm": out_vtm, "out_mtm": out_mtm, "ans_vtm": ans_vtm, "ans_mtm": batch["ans_mtm"]}
+
+
+class FakeTokenizer:
+    """Stand-in for AutoTokenizer.from_pretrained('bert-base-uncased') when no vocabulary file is available
+    offline: the special-token ids are bert-base-uncased's; 'true' / 'false' are 2995 / 6270."""
+    cls_token, sep_token, pad_token, mask_token, unk_token = "[CLS]", "[SEP]", "[PAD]", "[MASK]", "[UNK]"
+    vocab = {"[PAD]": 0, "[UNK]": 100, "[CLS]": 101, "[SEP]": 102, "[MASK]": 103, "true": 2995, "false": 6270}
+
+    def convert_tokens_to_ids(self, toks):
+        return [self.vocab[t] for t in toks]
+
+
+def default_args(**kw):
+    """The hot-path-relevant keys of utils/args.py (SURVEY §5 'Config / flags') with the reference's defaults."""
+    from .config import Args
+    a = Args(vis_backbone_size="base", size_img=224, size_frame=5, size_txt=32, size_batch=8, size_patch=32,
+             max_size_frame=6, max_size_patch=14, vis_backbone_init="random", kinetics=400,
+             txt_backbone="bert-base-uncased", tokenizer="bert-base-uncased", fusion_encoder="bert-base-uncased",
+             fusion_encoder_rand_init=False, txt_backbone_embed_only=True, use_checkpoint=False,
+             enable_task_token=True, enable_prompt=False, deepspeed=False, max_grad_norm=1.0, lr=2e-5, decay=1e-3,
+             vis_backbone_lr_mul=1.0, max_iter=1000, p_mask=0.15, seed=0, logging_steps=100, distributed=False,
+             task="pretrain", path_output="./_snapshot")
+    a.update(kw)
+    return a

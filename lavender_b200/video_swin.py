@@ -329,6 +329,8 @@ class _SwinFn(torch.autograd.Function):
     def backward(ctx, gout):
         mod, saved = ctx.mod, ctx.saved
         ar = arena_of(mod)
+        if ar.on_swin_backward is not None:
+            ar.on_swin_backward()  # data parallel: BERT + head gradients are final -> reduce them under this backward
         ar.prepare_grads(list(mod.parameters()))
         dev = gout.device
         B, T, H, W = ctx.geom

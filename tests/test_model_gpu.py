@@ -1,0 +1,159 @@
+"""Module- and end-to-end parity of the native CUDA path against the CPU oracle (oracle/lavender_oracle.py, itself
+pinned against the unmodified reference by oracle/make_golden.py) and against the committed goldens.
+
+Tolerances: the device path uses fp16 tensor-core operands with fp32 accumulation / statistics / residual stream
+(the reference's own GPU path is fp16 autocast); the oracle is exact fp32.  Random-init logits have std ~0.55 and
+|max| ~3, so the absolute logit tolerance below is ~1e-3 of the dynamic range; `test_*_vs_rounded_oracle`
+additionally compares with the oracle run under the same operand rounding, which isolates kernel errors from
+precision effects.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+LOGIT_ATOL = 6e-3        # vs exact-fp32 oracle / reference goldens
+GRAD_REL = 3e-2          # per-parameter relative L2 error of gradients
+
+
+def _build(size, layers, B, task_token=True, seed=0):
+    import lavender_oracle as O
+    from lavender_b200.pretrain import LAVENDER_Pretrain_MLM, FakeTokenizer, default_args
+    cfg = O.ModelCfg(swin=O.SWIN[size], bert_layers=layers, enable_task_token=task_token, vtm_batch=min(B, 4))
+    sd = O.make_state_dict(cfg, seed)
+    args = default_args(vis_backbone_size=size, size_batch=B, bert_config={"num_hidden_layers": layers},
+                        enable_task_token=task_token)
+    torch.manual_seed(0)
+    m = LAVENDER_Pretrain_MLM(args, FakeTokenizer())
+    m.load_state_dict(sd, strict=True)
+    m.cuda().eval()
+    return m, cfg, sd
+
+
+def _rel(a, b):
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+def test_swin_tiny_forward_backward_vs_oracle():
+    import lavender_oracle as O
+    from lavender_b200.video_swin import SwinTransformer3D, SWIN_VARIANTS
+    cfg = O.SWIN["tiny"]
+    full = O.make_state_dict(O.ModelCfg(swin=cfg, bert_layers=1), seed=2)
+    sd = {k[len("enc_img.swin."):]: v for k, v in full.items() if k.startswith("enc_img.swin.")}
+    m = SwinTransformer3D(**SWIN_VARIANTS[("tiny", 224)])
+    m.load_state_dict(sd, strict=True)
+    m.cuda().train()
+    B = 2
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, 3, 5, 224, 224, generator=g)
+    nblk = sum(cfg.depths)
+    kp = 1.0 - torch.linspace(0, 0.2, nblk).view(-1, 1, 1)
+    keep = (torch.floor(kp + torch.rand(nblk, 2, B, generator=g)) / kp)  # DropPath factors (video_swin.py:46-54)
+    cot = torch.randn(B, 5, 7, 7, 768, generator=g)
+
+    sdg = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point else v) for k, v in sd.items()}
+    ref = O.swin_forward({"s." + k: v for k, v in sdg.items()}, "s.", x, cfg, keep)
+    (ref * cot).sum().backward()
+
+    out = m.forward_features(x.cuda(), keep=keep.cuda())
+    (out * cot.cuda() * 256.0).sum().backward()   # x256: keep fp16 activation gradients away from underflow
+    torch.cuda.synchronize()
+    err = (out.cpu() - ref.detach()).abs().max().item()
+    print("swin forward max abs err", err, "ref absmax", ref.abs().max().item())
+    assert err < 2e-2   # LayerNorm'ed features, |x| up to ~5
+    worst = 0.0
+    for n, p in m.named_parameters():
+        gr = sdg[n].grad
+        assert p.grad is not None, n
+        e = _rel(p.grad.cpu() / 256.0, gr)
+        worst = max(worst, e)
+        assert e < GRAD_REL, (n, e)
+    print("swin worst grad rel err", worst)
+
+
+@pytest.mark.parametrize("name,size,layers,B,task,seed", [("tiny_l2_b2", "tiny", 2, 2, True, 0),
+                                                          ("tiny_l1_b3_notask", "tiny", 1, 3, False, 3)])
+def test_pretrain_vs_reference_golden(name, size, layers, B, task, seed):
+    """Eval-mode forward + CE + backward on the seeded batch vs outputs of the UNMODIFIED reference."""
+    import lavender_oracle as O
+    from lavender_b200.bert import CrossEntropyLoss
+    gold = np.load(os.path.join(GOLD, name + ".npz"))
+    m, cfg, sd = _build(size, layers, B, task, seed)
+    batch = {k: v.cuda() for k, v in O.make_batch(B, seed=seed).items()}
+    np.random.seed(1 + seed)
+    out = m(batch)
+    assert torch.equal(out["ans_vtm"].cpu(), torch.from_numpy(gold["ans_vtm"]))
+    e1 = (out["out_mtm"].detach().cpu()[..., ::61] - torch.from_numpy(gold["out_mtm_s"])).abs().max().item()
+    e2 = (out["out_vtm"].detach().cpu()[..., ::61] - torch.from_numpy(gold["out_vtm_s"])).abs().max().item()
+    print(f"[{name}] logits max abs err: mtm {e1:.2e} vtm {e2:.2e} (ref absmax {gold['out_mtm_absmax']:.2f})")
+    assert e1 < LOGIT_ATOL and e2 < LOGIT_ATOL
+    ce = CrossEntropyLoss(ignore_index=-1)
+    l1 = ce(out["out_mtm"].flatten(0, 1), out["ans_mtm"].flatten())
+    l2 = ce(out["out_vtm"].flatten(0, 1), out["ans_vtm"].flatten())
+    assert abs(l1.item() - float(gold["ls_mtm"])) < 2e-3 and abs(l2.item() - float(gold["ls_vtm"])) < 2e-3
+    ((l1 + l2) * 1024.0).backward()
+    torch.cuda.synchronize()
+    worst = ("", 0.0)
+    for n, p in m.named_parameters():
+        gn = float(gold["gn/" + n])
+        g = p.grad.cpu() / 1024.0 if p.grad is not None else torch.zeros_like(p).cpu()
+        if gn < 1e-7:       # emb_odr, unused emb_task rows / key.bias (softmax shift invariance): ~0 in the reference
+            assert g.norm().item() < 1e-4, n
+            continue
+        s = O.sample_flat(g, 64)
+        rs = torch.from_numpy(gold["gs/" + n])
+        e_norm = abs(g.double().norm().item() - gn) / gn
+        e_s = ((s - rs).norm() / (rs.norm() + 1e-3 * gn)).item()
+        if max(e_norm, e_s) > worst[1]:
+            worst = (n, max(e_norm, e_s))
+        assert e_norm < GRAD_REL and e_s < 2 * GRAD_REL, (n, e_norm, e_s)
+    print(f"[{name}] worst grad err {worst}")
+
+
+def test_pretrain_vs_rounded_oracle():
+    """Same comparison against the oracle run with fp16-rounded contraction operands and stored activations: what
+    remains is accumulation order, so the tolerance is ~5x tighter."""
+    import lavender_oracle as O
+    m, cfg, sd = _build("tiny", 2, 2, True, 0)
+    cpu_batch = O.make_batch(2, seed=0)
+    batch = {k: v.cuda() for k, v in cpu_batch.items()}
+    np.random.seed(1)
+    out = m(batch)
+    O.set_operand_rounding(torch.float16, torch.float16)
+    try:
+        np.random.seed(1)
+        with torch.no_grad():
+            ref = O.pretrain_forward(sd, cpu_batch, cfg)
+    finally:
+        O.set_operand_rounding(None, None)
+    e1 = (out["out_mtm"].detach().cpu() - ref["out_mtm"]).abs().max().item()
+    e2 = (out["out_vtm"].detach().cpu() - ref["out_vtm"]).abs().max().item()
+    print(f"logits vs fp16-rounded oracle: mtm {e1:.2e} vtm {e2:.2e}")
+    assert e1 < 3e-3 and e2 < 3e-3
+
+
+def test_reference_style_loop_equals_batched_pairs():
+    """The reference builds the VTM pairs one by one (main_pretrain_mlm.py:74-106); the native model gathers them.
+    Driving go_feat / go_cross / prepro_txt_inputs / fc_mtm exactly like the reference loop must give the same logits."""
+    import lavender_oracle as O
+    m, cfg, sd = _build("tiny", 1, 3, True, 0)
+    batch = {k: v.cuda() for k, v in O.make_batch(3, seed=1).items()}
+    np.random.seed(7)
+    with torch.no_grad():
+        out = m(batch)
+        np.random.seed(7)
+        B, Lv, O_ = 3, 250, 3
+        fi, mi, ft, mt = m.go_feat(batch["img"], batch["txt"], batch["mask"])
+        pf, pm, pt_, pmt = [], [], [], []
+        for i in range(B):
+            neg = np.random.permutation([j for j in range(B) if j != i])
+            for j in [i] + [neg[k] for k in range(O_ - 1)]:
+                t, mm, f = m.prepro_txt_inputs(batch["txt"][j], mt[j], ft[j], task_name="vtm", prompt=None)
+                pf.append(fi[i][None]), pm.append(mi[i][None]), pt_.append(f[None]), pmt.append(mm[None])
+        o2, _ = m.go_cross(torch.cat(pf), torch.cat(pm), torch.cat(pt_), torch.cat(pmt))
+        o2 = m.fc_mtm(o2[:, Lv:])
+    assert torch.equal(out["out_vtm"], o2)
