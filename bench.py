@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""Headline benchmark: clips/s of one LAVENDER unified-MLM pre-training step (MLM + VTM-as-MLM forward, two
+cross-entropies, backward, gradient all-reduce at N > 1, clip, AdamW) on synthetic 5x224x224 clips + 32-token
+captions — BASELINE.json configs[1]: swin_base_patch244_window877 + 12-layer BERT-base, 8 clips per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (one rank per GPU, NCCL)
+
+Prints ONE JSON line (rank 0).  `value` = clips/s with the batch resident in HBM; `e2e` = the same step driven
+through the public Agent API with the batch in pinned host memory (H2D inside the timed region, the two losses
+read back every step like main_pretrain_mlm.py:167-168).  `roofline` is the dominant kernel family measured with
+CUDA events inside one extra instrumented step; `cpu_baseline` / `--impl reference` time the CPU oracle
+(oracle/lavender_oracle.py — the only place outside tests/ that executes it; it is the thing measured there, never
+part of the CUDA path) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "configs[1]: swin_base_patch244_window877 + 12-layer BERT-base fusion + MLM head, 8 clips/GPU, " \
+           "5x224x224 frames, 33 text tokens, MLM + VTM(4 pairs/clip) fwd+bwd+AdamW"
+METRIC = "clips/sec (5x224x224, seq=32) pretrain fwd+bwd"
+PER_GPU_BATCH = 8
+
+
+# ---------------------------------------------------------------------------------------------------------
+# algorithmic FLOPs (SURVEY §8d counting convention: 2*M*N*K of every contraction at unpadded sizes; bwd = 2x fwd)
+# ---------------------------------------------------------------------------------------------------------
+SWIN = {"tiny": (96, (2, 2, 6, 2)), "base": (128, (2, 2, 18, 2)), "large": (192, (2, 2, 18, 2))}
+
+
+def fwd_flops_per_clip(size="base", layers=12, T=5, H=224, W=224, Lt=33, B=8, hidden=768, ffn=3072, vocab=30522,
+                       task_token=True, win=(8, 7, 7)):
+    C, depths = SWIN[size]
+    h, w = H // 4, W // 4
+    fl = T * h * w * 2 * 96 * C
+    for s, d in enumerate(depths):
+        c = C * 2 ** s
+        tok = T * (h >> s) * (w >> s)
+        n = min(T, win[0]) * min(h >> s, win[1]) * min(w >> s, win[2])
+        fl += tok * d * (24 * c * c + 4 * n * c)
+        if s < 3:
+            fl += (tok // 4) * 16 * c * c
+    ntok = T * (H // 32) * (W // 32)
+    if 8 * C != hidden:
+        fl += ntok * 2 * 8 * C * hidden
+    Lv = T * (1 + (H // 32) * (W // 32))
+
+    def bert(L):
+        return layers * (8 * L * hidden ** 2 + 4 * L * L * hidden + 4 * L * hidden * ffn)
+
+    def head(lt):
+        return 2 * lt * hidden * (hidden + vocab)
+    O = min(B, 4)
+    lt2 = Lt + (1 if task_token else 0)
+    fl += bert(Lv + Lt) + head(Lt) + O * (bert(Lv + lt2) + head(lt2))
+    return float(fl)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def clocks_sampler(stop, samples, gpu_index):
+    q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    while not stop.is_set():
+        try:
+            r = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(gpu_index)],
+                               capture_output=True, text=True, timeout=5)
+            if r.returncode == 0 and r.stdout.strip():
+                samples.append([x.strip() for x in r.stdout.strip().split(",")])
+        except Exception:
+            pass
+        stop.wait(0.2)
+
+
+def summarize_clocks(samples):
+    if not samples:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    sm = sorted(int(s[0]) for s in samples if s[0].isdigit())
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower().startswith("active") for s in samples)]
+    return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(samples[0][1]) if samples[0][1].isdigit() else None,
+            "reasons": reasons, "samples": len(samples)}
+
+
+def make_host_batch(B, seed, pin):
+    import torch
+    g = torch.Generator().manual_seed(1000 + seed)
+    img = torch.randn(B, 5, 3, 224, 224, generator=g)
+    txt = torch.randint(1000, 30000, (B, 33), generator=g)
+    txt[:, 0], txt[:, -2], txt[:, -1] = 101, 102, 103
+    mask = torch.ones(B, 33, dtype=torch.long)
+    b = {"img": img, "txt": txt, "mask": mask}
+    if pin:
+        b = {k: v.pin_memory() for k, v in b.items()}
+    return b
+
+
+# ---------------------------------------------------------------------------------------------------------
+def run_native(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from lavender_b200 import _lib, ops
+    from lavender_b200 import dist as D
+    from lavender_b200.agent import Agent_Pretrain_MLM
+    from lavender_b200.pretrain import LAVENDER_Pretrain_MLM, FakeTokenizer, default_args
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the native path has no CPU fallback (use --impl reference)")
+    world, rank, local = D.get_world_size(), D.get_rank(), D.get_local_rank()
+    assert world == a.gpus or world == 1, f"--gpus {a.gpus} but WORLD_SIZE={world}"
+    args = default_args(vis_backbone_size="base", size_batch=PER_GPU_BATCH, seed=0, max_iter=100000)
+    torch.cuda.set_device(local)
+    D.dist_init(args, distributed=world > 1)
+    _lib.check(_lib.lib().lav_device_info(local, None, None, None), "lav_device_info")
+
+    torch.manual_seed(0)
+    model = LAVENDER_Pretrain_MLM(args, FakeTokenizer())
+    for cfg in (model.trsfr.config, model.enc_txt.emb_txt.config):
+        cfg.lav_eval_dropout = a.eval_dropout
+    model.cuda()
+    agent = Agent_Pretrain_MLM(args, model)
+    agent.prepare_dist_model()
+    nparams = sum(p.numel() for p in model.parameters())
+
+    B = PER_GPU_BATCH
+    host = make_host_batch(B, seed=rank, pin=True)
+    np.random.seed(1234 + rank)
+    torch.manual_seed(1234 + rank)
+
+    def masked_host():
+        b = {"img": host["img"], "txt": host["txt"].clone(), "mask": host["mask"]}
+        b.update(agent.masking(b["txt"], b["mask"], 0.15))
+        return b
+
+    dev_batch = agent.prepare_batch(masked_host())
+
+    def step_resident():
+        model.train()
+        out = agent.forward_step(dev_batch)
+        l1 = agent.loss_func(out["out_mtm"].flatten(0, 1), out["ans_mtm"].flatten())
+        l2 = agent.loss_func(out["out_vtm"].flatten(0, 1), out["ans_vtm"].flatten())
+        agent.backward_step(l1 + l2)
+        return l1, l2
+
+    def step_e2e():
+        return agent.step(agent.prepare_batch(masked_host()), True)   # H2D + fwd/bwd/opt + 2x .item()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = _lib.launch_count()
+        e0.record()
+        for _ in range(steps):
+            r = fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), _lib.launch_count() - n0, r
+
+    for _ in range(max(a.warmup, 3)):
+        step_resident()
+    stop, samples = threading.Event(), []
+    th = threading.Thread(target=clocks_sampler, args=(stop, samples, local), daemon=True)
+    if rank == 0:
+        th.start()
+    ms, launches, last = timed(step_resident, a.steps)
+    if a.quick:   # profiling runs (ncu): just the resident steps
+        if rank == 0:
+            print(json.dumps({"quick": True, "ms_per_step": ms / a.steps, "gpu_launches": int(launches)}), flush=True)
+        return
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, _, last_e2e = timed(step_e2e, a.steps)
+    stop.set()
+
+    # ---- one extra instrumented step: per-kernel-family device time (CUDA events around every C-ABI call)
+    fams = {}
+    if rank == 0:
+        ops.PROFILE = []
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        step_resident()
+        t1.record()
+        torch.cuda.synchronize()
+        for name, s, e, fl, _meta in ops.PROFILE:
+            f = fams.setdefault(name, {"ms": 0.0, "flops": 0.0, "launches": 0})
+            f["ms"] += s.elapsed_time(e)
+            f["flops"] += fl
+            f["launches"] += 1
+        step_ms_prof = t0.elapsed_time(t1)
+        ops.PROFILE = None
+    barrier()
+
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else \
+        "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+    clips = B * world * a.steps
+    fwd = fwd_flops_per_clip("base", 12, B=B)
+    step_flops = 3.0 * fwd * B
+    top = max((k for k in fams if fams[k]["flops"] > 0), key=lambda k: fams[k]["ms"])
+    tf = fams[top]["flops"] / (fams[top]["ms"] * 1e-3) / 1e12
+    kern_total = sum(f["ms"] for f in fams.values())
+    out = {
+        "metric": METRIC, "value": round(clips / (ms * 1e-3), 2), "unit": "clips/s", "n_gpus": world, "steps": a.steps,
+        "warmup": max(a.warmup, 3), "ms_per_step": round(ms / a.steps, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f16 operands, f32 accumulate/statistics/residual/master weights",
+        "data": "synthetic (seeded randn frames, random token ids, random-init weights)",
+        "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "params": nparams,
+                   "parallelism": f"dp{world}", "step": "fwd(MLM+VTM) + 2xCE + bwd + grad all-reduce + clip + AdamW",
+                   "l2": "working set (activations > 10 GB/step) far exceeds the 126 MB L2; no explicit flush",
+                   "drop_path": "active (rate linspace(0,0.2))",
+                   "bert_dropout": "identity" if a.eval_dropout else "active (p=0.1)",
+                   "algorithmic_gflop_per_clip_fwd_bwd": round(3 * fwd / 1e9, 1)},
+        "clocks": summarize_clocks(samples),
+        "e2e": {"value": round(clips / (ms_e2e * 1e-3), 2), "unit": "clips/s",
+                "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values()) + B * 33 * 8),
+                "d2h_bytes_per_step": 8, "ms_per_step": round(ms_e2e / a.steps, 3)},
+        "gpu_launches": int(launches),
+        "loss": {"mtm": round(float(last[0].detach()), 4), "vtm": round(float(last[1].detach()), 4)},
+        "roofline": {"bound": "tensor", "kernel": top, "achieved": round(tf, 1), "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": round(tf / peak_tf, 4), "traffic": None, "peak_source": peak_src,
+                     "launches_per_step": fams[top]["launches"], "ms_per_step": round(fams[top]["ms"], 3),
+                     "share_of_step": round(fams[top]["ms"] / max(step_ms_prof, 1e-9), 3)},
+        "step_roofline": {"achieved": round(step_flops / (ms / a.steps * 1e-3) / 1e12, 1), "peak": peak_tf,
+                          "unit": "TFLOP/s", "frac": round(step_flops / (ms / a.steps * 1e-3) / 1e12 / peak_tf, 4)},
+        "kernels": {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
+                        "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1) if v["flops"] else None}
+                    for k, v in sorted(fams.items(), key=lambda kv: -kv[1]["ms"])},
+        "instrumented_step_ms": round(step_ms_prof, 3), "kernel_ms_sum": round(kern_total, 3),
+    }
+    if not a.no_cpu_baseline and world == 1:
+        out["cpu_baseline"] = cpu_oracle_baseline(steps=1, warmup=0)
+    print(json.dumps(out), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def cpu_oracle_baseline(steps, warmup, B=4, budget_s=240.0):
+    """Times the CPU oracle (a port: the pure-Python reference cannot travel to the GPU box) on a bounded sample of
+    the same workload: swin_base + 12-layer BERT, B clips (B=4 keeps the per-clip work of configs[1]: 4 VTM pairs
+    per clip), fwd + CE + bwd, fp32, all host threads."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import lavender_oracle as O
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(cores)
+    cfg = O.ModelCfg(swin=O.SWIN["base"], bert_layers=12, vtm_batch=4)
+    sd = O.make_state_dict(cfg, 0)
+    sd = {k: (v.requires_grad_(True) if v.dtype.is_floating_point else v) for k, v in sd.items()}
+    sd["fc_mtm.predictions.decoder.bias"] = sd["fc_mtm.predictions.bias"]
+    batch = O.make_batch(B, seed=0)
+    nblk = sum(cfg.swin.depths)
+    kp = 1.0 - torch.linspace(0, 0.2, nblk).view(-1, 1, 1)
+    times = []
+    for it in range(warmup + steps):
+        keep = torch.floor(kp + torch.rand(nblk, 2, B)) / kp
+        t0 = time.perf_counter()
+        np.random.seed(it)
+        out = O.pretrain_forward(sd, batch, cfg, keep=keep)
+        loss, _, _ = O.pretrain_loss(out)
+        loss.backward()
+        for v in sd.values():
+            if v.dtype.is_floating_point:
+                v.grad = None
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+        budget_s -= dt
+        if it >= warmup and budget_s < dt:   # keep the whole run within a few minutes on slow hosts
+            break
+    tot = sum(times)
+    return {"value": round(B * len(times) / tot, 4), "unit": "clips/s", "cores": cores, "kind": "port",
+            "sample": f"{len(times)} step(s) of B={B} clips (configs[1] shapes, 4 VTM pairs/clip), fwd+CE+bwd fp32, "
+                      f"torch {torch.__version__} CPU, {cores} threads, {warmup} warm-up",
+            "s_per_step": round(tot / len(times), 2)}
+
+
+def len_steps(cb):
+    return int(cb["sample"].split(" step(s)")[0])
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, a.steps)
+    warm = min(a.warmup, 1)
+    cb = cpu_oracle_baseline(steps=steps, warmup=warm)
+    B = 4
+    fwd = fwd_flops_per_clip("base", 12, B=PER_GPU_BATCH)
+    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "clips/s", "n_gpus": a.gpus,
+           "steps": int(round(cb["value"] * cb["s_per_step"] * 0 + len_steps(cb))), "warmup": warm, "ms_per_step": round(cb["s_per_step"] * 1e3, 1), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (same generator as the CUDA arm)",
+           "config": {"workload": WORKLOAD, "sample_batch": B,
+                      "note": "the reference is pure Python/PyTorch and is not present on the GPU box; this arm times "
+                              "the CPU oracle that is pinned against it (tests/test_oracle_golden.py)",
+                      "algorithmic_gflop_per_clip_fwd_bwd": round(3 * fwd / 1e9, 1)},
+           "cpu_baseline": cb,
+           "e2e": {"value": cb["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="resident steps only (for ncu runs)")
+    ap.add_argument("--eval-dropout", action="store_true", default=True,
+                    help="identity BERT dropout (until the dropout kernels land)")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_native(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -10,6 +10,31 @@ from . import _lib as L
 
 F16 = torch.float16
 
+# Optional per-call timing (bench.py's roofline leg): when PROFILE is a list, every wrapper brackets its C-ABI call
+# with CUDA events on the launching stream and appends (family, start_event, end_event, algorithmic_flops).
+PROFILE = None
+PROFILE_META = False  # also record a shape tag per call (tools/profile_step.py)
+
+
+class _Timed:
+    __slots__ = ("name", "flops", "ev", "meta")
+
+    def __init__(self, name, flops=0.0, meta=None):
+        self.name, self.flops, self.ev, self.meta = name, flops, None, meta
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.ev = torch.cuda.Event(enable_timing=True)
+            self.ev.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None and self.ev is not None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record()
+            PROFILE.append((self.name, self.ev, end, self.flops, self.meta if PROFILE_META else None))
+        return False
+
 
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
@@ -51,8 +76,9 @@ def gemm(a, b, out, *, M, N, K, a_major=L.MAJOR_K, b_major=L.MAJOR_K, bias=None,
         e.row_scale, e.rows_per_scale = row_scale.data_ptr(), rows_per_scale
     e.alpha = alpha
     e.accumulate = L.ACCUMULATE if accumulate else L.STORE
-    rc = L.lib().lav_gemm_f16(_ptr(a), a.stride(0), a_major, _ptr(b), b.stride(0), b_major, M, N, K,
-                              ctypes.byref(e), split_k, _stream())
+    with _Timed("gemm", 2.0 * M * N * K, ("gemm", M, N, K, a_major, b_major, act, out.dtype == F16, accumulate)):
+        rc = L.lib().lav_gemm_f16(_ptr(a), a.stride(0), a_major, _ptr(b), b.stride(0), b_major, M, N, K,
+                                  ctypes.byref(e), split_k, _stream())
     L.check(rc, "lav_gemm_f16")
     return out
 
@@ -64,29 +90,32 @@ def _p(t):
 def layernorm_fwd(x, gamma, beta, eps, *, rows, C, G=1, row_map=None, out16=None, out32=None, mean=None, rstd=None):
     """out[r] = LN(concat_g x[row_map[r*G+g]]) (width G*C); x fp32 2-D."""
     assert x.dtype == torch.float32 and x.stride(-1) == 1
-    rc = L.lib().lav_layernorm_fwd(_p(x), x.stride(0), _p(row_map), G, C, _p(gamma), _p(beta), eps,
-                                   _p(out16), out16.stride(0) if out16 is not None else 0,
-                                   _p(out32), out32.stride(0) if out32 is not None else 0,
-                                   _p(mean), _p(rstd), rows, _stream())
+    with _Timed("layernorm_fwd"):
+        rc = L.lib().lav_layernorm_fwd(_p(x), x.stride(0), _p(row_map), G, C, _p(gamma), _p(beta), eps,
+                                       _p(out16), out16.stride(0) if out16 is not None else 0,
+                                       _p(out32), out32.stride(0) if out32 is not None else 0,
+                                       _p(mean), _p(rstd), rows, _stream())
     L.check(rc, "lav_layernorm_fwd")
 
 
 def layernorm_bwd(dy, x, gamma, mean, rstd, *, rows, C, G=1, row_map=None, add32=None, dx32=None, dx16=None,
                   dgamma=None, dbeta=None):
     assert dy.dtype in (F16, torch.float32) and x.dtype == torch.float32
-    rc = L.lib().lav_layernorm_bwd(_p(dy), dy.stride(0), int(dy.dtype == torch.float32), _p(x), x.stride(0),
-                                   _p(row_map), G, C, _p(gamma), _p(mean), _p(rstd),
-                                   _p(add32), add32.stride(0) if add32 is not None else 0,
-                                   _p(dx32), dx32.stride(0) if dx32 is not None else 0,
-                                   _p(dx16), dx16.stride(0) if dx16 is not None else 0,
-                                   _p(dgamma), _p(dbeta), rows, _stream())
+    with _Timed("layernorm_bwd"):
+        rc = L.lib().lav_layernorm_bwd(_p(dy), dy.stride(0), int(dy.dtype == torch.float32), _p(x), x.stride(0),
+                                       _p(row_map), G, C, _p(gamma), _p(mean), _p(rstd),
+                                       _p(add32), add32.stride(0) if add32 is not None else 0,
+                                       _p(dx32), dx32.stride(0) if dx32 is not None else 0,
+                                       _p(dx16), dx16.stride(0) if dx16 is not None else 0,
+                                       _p(dgamma), _p(dbeta), rows, _stream())
     L.check(rc, "lav_layernorm_bwd")
 
 
 def scale_cast(x, out16, *, rows, C, row_map=None, row_scale=None, rows_per_scale=1, alpha=1.0):
     assert x.dtype == torch.float32 and out16.dtype == F16
-    rc = L.lib().lav_scale_cast_f16(_p(x), x.stride(0), _p(row_map), _p(row_scale), rows_per_scale, alpha,
-                                    _p(out16), out16.stride(0), rows, C, _stream())
+    with _Timed("cast"):
+        rc = L.lib().lav_scale_cast_f16(_p(x), x.stride(0), _p(row_map), _p(row_scale), rows_per_scale, alpha,
+                                        _p(out16), out16.stride(0), rows, C, _stream())
     L.check(rc, "lav_scale_cast_f16")
     return out16
 
@@ -94,20 +123,24 @@ def scale_cast(x, out16, *, rows, C, row_map=None, row_scale=None, rows_per_scal
 def cast_f16(src, dst):
     assert src.dtype == torch.float32 and dst.dtype == F16 and src.numel() == dst.numel()
     assert src.is_contiguous() and dst.is_contiguous()
-    L.check(L.lib().lav_cast_f32_to_f16(_p(src), _p(dst), src.numel(), _stream()), "lav_cast_f32_to_f16")
+    with _Timed("cast"):
+        L.check(L.lib().lav_cast_f32_to_f16(_p(src), _p(dst), src.numel(), _stream()), "lav_cast_f32_to_f16")
     return dst
 
 
 def colsum(x16, out, *, rows, N, alpha=1.0):
     assert x16.dtype == F16 and out.dtype == torch.float32
-    L.check(L.lib().lav_colsum_f16(_p(x16), x16.stride(0), rows, N, _p(out), alpha, _stream()), "lav_colsum_f16")
+    with _Timed("colsum"):
+        L.check(L.lib().lav_colsum_f16(_p(x16), x16.stride(0), rows, N, _p(out), alpha, _stream()), "lav_colsum_f16")
 
 
 def attn_fwd(qkv, out, lse, *, q_off, k_off, v_off, head_dim, nheads, nprob, L_tok, scale, bias16=None,
              prob_class=None, key_bias=None):
     _chk16(qkv, "qkv")
     _chk16(out, "out")
-    rc = L.lib().lav_attn_fwd_f16(_p(qkv), qkv.stride(0), qkv.shape[0], q_off, k_off, v_off, head_dim, nheads, nprob,
+    fam = "win_attn_fwd" if head_dim == 32 else "bert_attn_fwd"
+    with _Timed(fam, 4.0 * L_tok * L_tok * head_dim * nheads * nprob):
+      rc = L.lib().lav_attn_fwd_f16(_p(qkv), qkv.stride(0), qkv.shape[0], q_off, k_off, v_off, head_dim, nheads, nprob,
                                   L_tok, scale, _p(bias16), bias16.shape[-1] if bias16 is not None else 0,
                                   _p(prob_class), prob_class.numel() if prob_class is not None else 1, _p(key_bias),
                                   _p(out), out.stride(0), _p(lse), _stream())
@@ -116,7 +149,9 @@ def attn_fwd(qkv, out, lse, *, q_off, k_off, v_off, head_dim, nheads, nprob, L_t
 
 def attn_bwd(qkv, out, dout, lse, dq_acc, dqkv, *, q_off, k_off, v_off, head_dim, nheads, nprob, L_tok, scale,
              bias16=None, prob_class=None, key_bias=None, ds16=None):
-    rc = L.lib().lav_attn_bwd_f16(_p(qkv), qkv.stride(0), qkv.shape[0], q_off, k_off, v_off, head_dim, nheads, nprob,
+    fam = "win_attn_bwd" if head_dim == 32 else "bert_attn_bwd"
+    with _Timed(fam, 8.0 * L_tok * L_tok * head_dim * nheads * nprob):
+      rc = L.lib().lav_attn_bwd_f16(_p(qkv), qkv.stride(0), qkv.shape[0], q_off, k_off, v_off, head_dim, nheads, nprob,
                                   L_tok, scale, _p(bias16), bias16.shape[-1] if bias16 is not None else 0,
                                   _p(prob_class), prob_class.numel() if prob_class is not None else 1,
                                   _p(key_bias), key_bias.shape[-1] if key_bias is not None else 0,
@@ -129,20 +164,23 @@ def attn_bwd(qkv, out, dout, lse, dq_acc, dqkv, *, q_off, k_off, v_off, head_dim
 def relpos_bias_expand(table, rel_index, L_tok, labels, dense16):
     """dense16: [ncls, nheads, NP, NP] fp16; labels: uint8 [ncls, NP] or None."""
     ncls, nheads, NP, _ = dense16.shape
-    rc = L.lib().lav_relpos_bias_expand(_p(table), nheads, _p(rel_index), L_tok, _p(labels), ncls, _p(dense16), NP,
-                                        _stream())
+    with _Timed("relpos_expand"):
+        rc = L.lib().lav_relpos_bias_expand(_p(table), nheads, _p(rel_index), L_tok, _p(labels), ncls, _p(dense16), NP,
+                                            _stream())
     L.check(rc, "lav_relpos_bias_expand")
 
 
 def relpos_bias_grad(ds16, rel_index, L_tok, dtable):
     nprob, nheads, NP, _ = ds16.shape
-    rc = L.lib().lav_relpos_bias_grad(_p(ds16), nprob, nheads, NP, L_tok, _p(rel_index), _p(dtable), _stream())
+    with _Timed("relpos_grad"):
+        rc = L.lib().lav_relpos_bias_grad(_p(ds16), nprob, nheads, NP, L_tok, _p(rel_index), _p(dtable), _stream())
     L.check(rc, "lav_relpos_bias_grad")
 
 
 def gelu_bwd(dy16, pre16, out16):
     assert dy16.is_contiguous() and pre16.is_contiguous() and out16.is_contiguous()
-    L.check(L.lib().lav_gelu_bwd_f16(_p(dy16), _p(pre16), _p(out16), dy16.numel(), _stream()), "lav_gelu_bwd_f16")
+    with _Timed("gelu_bwd"):
+        L.check(L.lib().lav_gelu_bwd_f16(_p(dy16), _p(pre16), _p(out16), dy16.numel(), _stream()), "lav_gelu_bwd_f16")
     return out16
 
 
@@ -151,17 +189,19 @@ def bert_embed_ln_fwd(ids, pos_ids, type_ids, word, pos, typ, gamma, beta, eps, 
     rows, C = ids.numel(), word.shape[1]
     for t in (ids, pos_ids, type_ids):
         assert t is None or (t.dtype == torch.int64 and t.is_contiguous() and t.numel() == rows)
-    rc = L.lib().lav_bert_embed_ln_fwd(_p(ids), _p(pos_ids), _p(type_ids), rows, Lt, C, word.shape[0], pos.shape[0],
-                                       typ.shape[0], _p(word), _p(pos), _p(typ), _p(gamma), _p(beta), eps, _p(sum32),
-                                       _p(y32), _p(mean), _p(rstd), _stream())
+    with _Timed("embed"):
+        rc = L.lib().lav_bert_embed_ln_fwd(_p(ids), _p(pos_ids), _p(type_ids), rows, Lt, C, word.shape[0], pos.shape[0],
+                                           typ.shape[0], _p(word), _p(pos), _p(typ), _p(gamma), _p(beta), eps, _p(sum32),
+                                           _p(y32), _p(mean), _p(rstd), _stream())
     L.check(rc, "lav_bert_embed_ln_fwd")
 
 
 def bert_embed_bwd(dsum32, ids, pos_ids, type_ids, dword, dpos, dtyp, *, Lt):
     rows, C = ids.numel(), dsum32.shape[-1]
     assert dsum32.is_contiguous() and dsum32.dtype == torch.float32
-    rc = L.lib().lav_bert_embed_bwd(_p(dsum32), _p(ids), _p(pos_ids), _p(type_ids), rows, Lt, C, dword.shape[0],
-                                    dpos.shape[0], dtyp.shape[0], _p(dword), _p(dpos), _p(dtyp), _stream())
+    with _Timed("embed"):
+        rc = L.lib().lav_bert_embed_bwd(_p(dsum32), _p(ids), _p(pos_ids), _p(type_ids), rows, Lt, C, dword.shape[0],
+                                        dpos.shape[0], dtyp.shape[0], _p(dword), _p(dpos), _p(dtyp), _stream())
     L.check(rc, "lav_bert_embed_bwd")
 
 
@@ -169,19 +209,21 @@ def vid_embed_ln_fwd(feat, emb_cls, emb_pos, emb_len, emb_odr, odr_swap, gamma, 
                      B, T, hw):
     C = feat.shape[-1]
     assert feat.dtype == torch.float32 and feat.stride(-1) == 1 and feat.dim() == 2
-    rc = L.lib().lav_vid_embed_ln_fwd(_p(feat), feat.stride(0), _p(emb_cls), _p(emb_pos), _p(emb_len), _p(emb_odr),
-                                      _p(odr_swap), B, T, hw, C, _p(gamma), _p(beta), eps, _p(sum32), _p(y32), _p(mean),
-                                      _p(rstd), _stream())
+    with _Timed("embed"):
+        rc = L.lib().lav_vid_embed_ln_fwd(_p(feat), feat.stride(0), _p(emb_cls), _p(emb_pos), _p(emb_len), _p(emb_odr),
+                                          _p(odr_swap), B, T, hw, C, _p(gamma), _p(beta), eps, _p(sum32), _p(y32), _p(mean),
+                                          _p(rstd), _stream())
     L.check(rc, "lav_vid_embed_ln_fwd")
 
 
 def vid_embed_bwd(dsum32, odr_swap, *, B, T, hw, C, dfeat16=None, dfeat32=None, demb_cls=None, demb_pos=None,
                   demb_len=None, demb_odr=None):
     assert dsum32.is_contiguous() and dsum32.dtype == torch.float32
-    rc = L.lib().lav_vid_embed_bwd(_p(dsum32), B, T, hw, C, _p(odr_swap), _p(dfeat16),
-                                   dfeat16.stride(0) if dfeat16 is not None else 0, _p(dfeat32),
-                                   dfeat32.stride(0) if dfeat32 is not None else 0, _p(demb_cls), _p(demb_pos),
-                                   _p(demb_len), _p(demb_odr), _stream())
+    with _Timed("embed"):
+        rc = L.lib().lav_vid_embed_bwd(_p(dsum32), B, T, hw, C, _p(odr_swap), _p(dfeat16),
+                                       dfeat16.stride(0) if dfeat16 is not None else 0, _p(dfeat32),
+                                       dfeat32.stride(0) if dfeat32 is not None else 0, _p(demb_cls), _p(demb_pos),
+                                       _p(demb_len), _p(demb_odr), _stream())
     L.check(rc, "lav_vid_embed_bwd")
 
 
@@ -189,14 +231,16 @@ def xent_fwd(logits, labels, ignore_index, row_lse, row_loss, loss_sum, count):
     """logits fp32 [rows, V] (row stride >= V); labels int64 [rows]."""
     rows, V = logits.shape
     assert logits.dtype == torch.float32 and logits.stride(1) == 1 and labels.dtype == torch.int64
-    rc = L.lib().lav_xent_fwd(_p(logits), logits.stride(0), _p(labels), rows, V, ignore_index, _p(row_lse),
-                              _p(row_loss), _p(loss_sum), _p(count), _stream())
+    with _Timed("xent"):
+        rc = L.lib().lav_xent_fwd(_p(logits), logits.stride(0), _p(labels), rows, V, ignore_index, _p(row_lse),
+                                  _p(row_loss), _p(loss_sum), _p(count), _stream())
     L.check(rc, "lav_xent_fwd")
 
 
 def xent_bwd(logits, labels, ignore_index, row_lse, gout, count, d32=None, d16=None):
     rows, V = logits.shape
-    rc = L.lib().lav_xent_bwd(_p(logits), logits.stride(0), _p(labels), rows, V, ignore_index, _p(row_lse), _p(gout),
-                              _p(count), _p(d32), d32.stride(0) if d32 is not None else 0, _p(d16),
-                              d16.stride(0) if d16 is not None else 0, _stream())
+    with _Timed("xent"):
+        rc = L.lib().lav_xent_bwd(_p(logits), logits.stride(0), _p(labels), rows, V, ignore_index, _p(row_lse), _p(gout),
+                                  _p(count), _p(d32), d32.stride(0) if d32 is not None else 0, _p(d16),
+                                  d16.stride(0) if d16 is not None else 0, _stream())
     L.check(rc, "lav_xent_bwd")
