@@ -14,11 +14,11 @@ CUDA events inside one extra instrumented step; `cpu_baseline` / `--impl referen
 part of the CUDA path) on the host cores.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -65,18 +65,42 @@ def fwd_flops_per_clip(size="base", layers=12, T=5, H=224, W=224, Lt=33, B=8, hi
 
 
 # ---------------------------------------------------------------------------------------------------------
-def clocks_sampler(stop, samples, gpu_index):
-    q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+class ClockSampler:
+    """One long-lived `nvidia-smi -lms 200` process (the profiling recipe's clocks line) writing CSV to a temp file;
+    polling from a Python thread would steal the GIL from a host-bound training loop."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-    while not stop.is_set():
+
+    def __init__(self, gpu_index):
+        import tempfile
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
         try:
-            r = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(gpu_index)],
-                               capture_output=True, text=True, timeout=5)
-            if r.returncode == 0 and r.stdout.strip():
-                samples.append([x.strip() for x in r.stdout.strip().split(",")])
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                          str(gpu_index), "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             pass
-        stop.wait(0.2)
+        self.t0 = self.t1 = None
+
+    def mark(self, which):
+        setattr(self, which, time.time())
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        self.f.flush()
+        self.f.seek(0)
+        rows = [[x.strip() for x in l.split(",")] for l in self.f.read().splitlines() if l.strip()]
+        self.f.close()
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return rows
 
 
 def summarize_clocks(samples):
@@ -116,7 +140,8 @@ def run_native(a):
         raise SystemExit("bench.py: no CUDA device - the native path has no CPU fallback (use --impl reference)")
     world, rank, local = D.get_world_size(), D.get_rank(), D.get_local_rank()
     assert world == a.gpus or world == 1, f"--gpus {a.gpus} but WORLD_SIZE={world}"
-    args = default_args(vis_backbone_size="base", size_batch=PER_GPU_BATCH, seed=0, max_iter=100000)
+    args = default_args(vis_backbone_size="base", size_batch=PER_GPU_BATCH, seed=0, max_iter=100000,
+                        cuda_graph=not a.no_graph)
     torch.cuda.set_device(local)
     D.dist_init(args, distributed=world > 1)
     _lib.check(_lib.lib().lav_device_info(local, None, None, None), "lav_device_info")
@@ -143,6 +168,19 @@ def run_native(a):
     dev_batch = agent.prepare_batch(masked_host())
 
     def step_resident():
+        if args.cuda_graph:     # one cudaGraphLaunch for forward + losses + backward, then the eager optimizer
+            model.train()
+            g = agent.graphs.get(dev_batch) if agent.graphs is not None else None
+            if g is None:
+                from lavender_b200.graph import GraphCache
+                agent.graphs = GraphCache(agent)
+                g = agent.graphs.get(dev_batch)
+            l1, l2 = g(dev_batch)
+            agent.backward_step(None, graphed=True)
+            return l1, l2
+        return step_eager()
+
+    def step_eager():
         model.train()
         out = agent.forward_step(dev_batch)
         l1 = agent.loss_func(out["out_mtm"].flatten(0, 1), out["ans_mtm"].flatten())
@@ -162,31 +200,32 @@ def run_native(a):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n0 = _lib.launch_count()
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         e0.record()
-        for _ in range(steps):
+        for i in range(steps):
             r = fn()
+            marks[i].record()
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item(), _lib.launch_count() - n0, r
+        per_step = [round(a_.elapsed_time(b_), 2) for a_, b_ in zip([e0] + marks[:-1], marks)]
+        gc.unfreeze()
+        return ms.item(), _lib.launch_count() - n0, r, per_step
 
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(max(a.warmup, 3)):
         step_resident()
-    stop, samples = threading.Event(), []
-    th = threading.Thread(target=clocks_sampler, args=(stop, samples, local), daemon=True)
-    if rank == 0:
-        th.start()
-    ms, launches, last = timed(step_resident, a.steps)
+    ms, launches, last, per_step = timed(step_resident, a.steps)
     if a.quick:   # profiling runs (ncu): just the resident steps
         if rank == 0:
             print(json.dumps({"quick": True, "ms_per_step": ms / a.steps, "gpu_launches": int(launches)}), flush=True)
         return
     for _ in range(2):
         step_e2e()
-    ms_e2e, _, last_e2e = timed(step_e2e, a.steps)
-    stop.set()
+    ms_e2e, _, last_e2e, per_step_e2e = timed(step_e2e, a.steps)
+    samples = sampler.stop() if sampler is not None else []
 
     # ---- one extra instrumented step: per-kernel-family device time (CUDA events around every C-ABI call)
     fams = {}
@@ -195,7 +234,8 @@ def run_native(a):
         t0 = torch.cuda.Event(enable_timing=True)
         t1 = torch.cuda.Event(enable_timing=True)
         t0.record()
-        step_resident()
+        step_eager()
+        agent.optzr.zero_grad(set_to_none=True)
         t1.record()
         torch.cuda.synchronize()
         for name, s, e, fl, _meta in ops.PROFILE:
@@ -234,11 +274,12 @@ def run_native(a):
                    "drop_path": "active (rate linspace(0,0.2))",
                    "bert_dropout": "identity" if a.eval_dropout else "active (p=0.1)",
                    "algorithmic_gflop_per_clip_fwd_bwd": round(3 * fwd / 1e9, 1)},
-        "clocks": summarize_clocks(samples),
+        "clocks": summarize_clocks(samples), "cuda_graph": bool(args.cuda_graph),
         "e2e": {"value": round(clips / (ms_e2e * 1e-3), 2), "unit": "clips/s",
                 "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values()) + B * 33 * 8),
                 "d2h_bytes_per_step": 8, "ms_per_step": round(ms_e2e / a.steps, 3)},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches) if not args.cuda_graph else
+        int(agent.graphs.get(dev_batch).native_launches * a.steps),
         "loss": {"mtm": round(float(last[0].detach()), 4), "vtm": round(float(last[1].detach()), 4)},
         "roofline": {"bound": "tensor", "kernel": top, "achieved": round(tf, 1), "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": round(tf / peak_tf, 4), "traffic": None, "peak_source": peak_src,
@@ -249,6 +290,7 @@ def run_native(a):
         "kernels": {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
                         "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1) if v["flops"] else None}
                     for k, v in sorted(fams.items(), key=lambda kv: -kv[1]["ms"])},
+        "per_step_ms": per_step, "per_step_ms_e2e": per_step_e2e,
         "instrumented_step_ms": round(step_ms_prof, 3), "kernel_ms_sum": round(kern_total, 3),
     }
     if not a.no_cpu_baseline and world == 1:
@@ -316,7 +358,7 @@ def run_reference(a):
     B = 4
     fwd = fwd_flops_per_clip("base", 12, B=PER_GPU_BATCH)
     out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "clips/s", "n_gpus": a.gpus,
-           "steps": int(round(cb["value"] * cb["s_per_step"] * 0 + len_steps(cb))), "warmup": warm, "ms_per_step": round(cb["s_per_step"] * 1e3, 1), "higher_is_better": True,
+           "steps": len_steps(cb), "warmup": warm, "ms_per_step": round(cb["s_per_step"] * 1e3, 1), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (same generator as the CUDA arm)",
            "config": {"workload": WORKLOAD, "sample_batch": B,
                       "note": "the reference is pure Python/PyTorch and is not present on the GPU box; this arm times "
@@ -334,6 +376,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--quick", action="store_true", help="resident steps only (for ncu runs)")
     ap.add_argument("--eval-dropout", action="store_true", default=True,
                     help="identity BERT dropout (until the dropout kernels land)")

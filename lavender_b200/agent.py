@@ -84,6 +84,7 @@ class Agent_Base:
         self.scaler = torch.amp.GradScaler("cuda", enabled=torch.cuda.is_available())
         self.log = None
         self.grad_sync = None
+        self.graphs = None  # graph.GraphCache when args.cuda_graph
         self.tokzr = getattr(model, "tokzr", None)
         if self.tokzr is None:
             raise ValueError("Agent_Base needs model.tokzr (no tokenizer files are fetched offline)")
@@ -157,8 +158,11 @@ class Agent_Base:
             return self.model(*batch)
         raise TypeError(f"batch is either dict or tuple, {type(batch)}")
 
-    def backward_step(self, loss):
-        self.scaler.scale(loss).backward()
+    def backward_step(self, loss, graphed=False):
+        """agent.py:235-250.  graphed=True: the scaled backward already ran inside a CUDA-graph replay (graph.py),
+        which also zeroes the gradient arena at its start, so neither backward nor zero_grad happens here."""
+        if not graphed:
+            self.scaler.scale(loss).backward()
         if self.grad_sync is not None:
             self.grad_sync.finish()
         elif hasattr(self.model, "arena"):
@@ -169,7 +173,8 @@ class Agent_Base:
         self.scaler.step(self.optzr)
         self.scaler.update()
         self.lr_scheduler.step()
-        self.optzr.zero_grad()
+        if not graphed:
+            self.optzr.zero_grad()
         self.global_step += 1
 
     def prepare_dist_model(self):
@@ -197,6 +202,13 @@ class Agent_Pretrain_MLM(Agent_Base):
 
     def step(self, batch, is_train=True):
         self.model.train(is_train)
+        if is_train and getattr(self.args, "cuda_graph", False) and batch.get("vtm_prompt") is None:
+            if self.graphs is None:
+                from .graph import GraphCache
+                self.graphs = GraphCache(self)
+            ls_mtm, ls_vtm = self.graphs.get(batch)(batch)
+            self.backward_step(None, graphed=True)
+            return {"mtm": ls_mtm.item(), "vtm": ls_vtm.item()}
         with torch.set_grad_enabled(is_train):
             out = self.forward_step(batch)
             out_mtm, out_vtm, ans_mtm, ans_vtm = out["out_mtm"], out["out_vtm"], out["ans_mtm"], out["ans_vtm"]

@@ -15,17 +15,20 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 fp16 = one 128-byte swizzle atom
 constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = 128 + kEpiWarps * 32;
+constexpr int kEpiStride = 36;  // floats per staged accumulator row: 16-byte aligned, conflict-free for 128-bit access
 
 template <int BN>
 struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = 196608 / STAGE_BYTES;  // 4 / 6 / 8 for BN = 256 / 128 / 64
+  static constexpr int EPI_BYTES = kEpiWarps * kEpiStride * 32 * 4;  // per-warp 32x32 fp32 transpose buffers
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual 1 KB alignment
+  static constexpr int STAGES_MAX = (232448 - 1024 - BAR_BYTES - EPI_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_MAX > 6 ? 6 : STAGES_MAX;  // 3 / 5 / 6 for BN = 256 / 128 / 64
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
   static constexpr int TMEM_COLS = 2 * BN;                                    // 2 accumulator stages
-  static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of 2");
+  static constexpr int TMEM_ALLOC = TMEM_COLS <= 128 ? 128 : TMEM_COLS <= 256 ? 256 : 512;  // power of 2
 };
 
 struct GemmParams {
@@ -48,122 +51,140 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int item) 
   return t;
 }
 
-// One 32-column chunk of one accumulator row: bias / activation / residual / store.
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&acc)[32], int row, int col0) {
+// ---------------------------------------------------------------------------------------------------------
+// Epilogue.  tcgen05.ld gives each thread one accumulator ROW (32 consecutive columns of a 32x32 chunk).  The
+// per-element math (alpha, bias, GELU, DropPath row scale) runs in that layout; every global access goes through
+// a per-warp shared-memory transpose so that 8 lanes cover the 32 columns of one row and a warp instruction
+// touches 4 rows x 128 contiguous bytes (fp32) / 64 bytes (fp16) instead of 32 different 128-byte lines.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add_v4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+__device__ __forceinline__ void stage_rows(float* stg, int lane, const float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(stg + lane * kEpiStride + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+
+enum { ST_F32 = 0, ST_F32_RMW = 1, ST_F32_RED = 2, ST_F16 = 3 };
+
+// staged chunk -> out (+ residual, through the row map).  (rr, cg) = lane's row-in-group / 4-column group.
+template <int MODE>
+__device__ __forceinline__ void store_phase(const GemmParams& p, const float* stg, int row_base, int col, int rr, int cg) {
   const LavGemmEpilogue& e = p.epi;
-  const int ncols = min(32, p.N - col0);
-  float v[32];
+  const int nv = p.N - col;
+  if (nv <= 0) return;
+  const bool vec_o = nv >= 4 && (e.ldo & 3) == 0;
+  const bool vec_r = nv >= 4 && (e.ldres & 3) == 0;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * e.alpha;
-  if (e.bias) {
-    if (ncols == 32) {
-      const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 b = __ldg(b4 + j);
-        v[4 * j] += b.x, v[4 * j + 1] += b.y, v[4 * j + 2] += b.z, v[4 * j + 3] += b.w;
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + rr;
+    const int row = row_base + r;
+    if (row >= p.M) continue;
+    float4 a = *reinterpret_cast<const float4*>(stg + r * kEpiStride + 4 * cg);
+    const int orow = e.row_map ? __ldg(e.row_map + row) : row;
+    if (e.residual) {
+      const float* rs = e.residual + (size_t)orow * e.ldres + col;
+      if (vec_r) {
+        const float4 x = *reinterpret_cast<const float4*>(rs);
+        a.x += x.x, a.y += x.y, a.z += x.z, a.w += x.w;
+      } else {
+        a.x += rs[0];
+        if (nv > 1) a.y += rs[1];
+        if (nv > 2) a.z += rs[2];
+        if (nv > 3) a.w += rs[3];
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncols) v[j] += __ldg(e.bias + col0 + j);
     }
-  }
-  if (e.act == LAV_ACT_GELU) {
-    if (e.aux) {
-      __half* a = reinterpret_cast<__half*>(e.aux) + (size_t)row * e.ldaux + col0;
-      if (ncols == 32 && (e.ldaux & 7) == 0) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 u;
-          u.x = pack_half2(v[8 * j], v[8 * j + 1]), u.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
-          u.z = pack_half2(v[8 * j + 4], v[8 * j + 5]), u.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
-          reinterpret_cast<uint4*>(a)[j] = u;
-        }
+    const float v[4] = {a.x, a.y, a.z, a.w};
+    if (MODE == ST_F16) {
+      __half* o = reinterpret_cast<__half*>(e.out) + (size_t)orow * e.ldo + col;
+      if (vec_o) {
+        *reinterpret_cast<uint2*>(o) = make_uint2(pack_half2(a.x, a.y), pack_half2(a.z, a.w));
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < ncols) a[j] = __float2half_rn(v[j]);
+        for (int j = 0; j < 4; ++j)
+          if (j < nv) o[j] = __float2half_rn(v[j]);
       }
-    }
+    } else {
+      float* o = reinterpret_cast<float*>(e.out) + (size_t)orow * e.ldo + col;
+      if (MODE == ST_F32_RED) {
+        if (vec_o) red_add_v4(o, a);
+        else {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-  } else if (e.act == LAV_ACT_GELU_BWD) {
-    const __half* a = reinterpret_cast<const __half*>(e.aux) + (size_t)row * e.ldaux + col0;
-    if (ncols == 32 && (e.ldaux & 7) == 0) {
+          for (int j = 0; j < 4; ++j)
+            if (j < nv) atomicAdd(o + j, v[j]);
+        }
+      } else if (MODE == ST_F32_RMW) {
+        if (vec_o) {
+          const float4 x = *reinterpret_cast<float4*>(o);
+          *reinterpret_cast<float4*>(o) = make_float4(x.x + a.x, x.y + a.y, x.z + a.z, x.w + a.w);
+        } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 u = reinterpret_cast<const uint4*>(a)[j];
-        const __half2* h = reinterpret_cast<const __half2*>(&u);
+          for (int j = 0; j < 4; ++j)
+            if (j < nv) o[j] += v[j];
+        }
+      } else {
+        if (vec_o) *reinterpret_cast<float4*>(o) = a;
+        else {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float2 f = __half22float2(h[q]);
-          v[8 * j + 2 * q] *= gelu_erf_grad(f.x);
-          v[8 * j + 2 * q + 1] *= gelu_erf_grad(f.y);
+          for (int j = 0; j < 4; ++j)
+            if (j < nv) o[j] = v[j];
         }
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncols) v[j] *= gelu_erf_grad(__half2float(a[j]));
     }
   }
-  if (e.row_scale) {
-    const float s = __ldg(e.row_scale + row / e.rows_per_scale);
+}
+
+// staged chunk -> aux (fp16 [row][col], identity rows): the GELU pre-activation
+__device__ __forceinline__ void store_aux_phase(const GemmParams& p, const float* stg, int row_base, int col, int rr, int cg) {
+  const LavGemmEpilogue& e = p.epi;
+  const int nv = p.N - col;
+  if (nv <= 0) return;
+  const bool vec = nv >= 4 && (e.ldaux & 3) == 0;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] *= s;
-  }
-  const int orow = e.row_map ? __ldg(e.row_map + row) : row;
-  if (e.residual) {
-    const float* r = e.residual + (size_t)orow * e.ldres + col0;
-    if (ncols == 32 && (e.ldres & 3) == 0) {
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + rr;
+    const int row = row_base + r;
+    if (row >= p.M) continue;
+    const float4 a = *reinterpret_cast<const float4*>(stg + r * kEpiStride + 4 * cg);
+    __half* o = reinterpret_cast<__half*>(e.aux) + (size_t)row * e.ldaux + col;
+    if (vec) *reinterpret_cast<uint2*>(o) = make_uint2(pack_half2(a.x, a.y), pack_half2(a.z, a.w));
+    else {
+      const float v[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 x = reinterpret_cast<const float4*>(r)[j];
-        v[4 * j] += x.x, v[4 * j + 1] += x.y, v[4 * j + 2] += x.z, v[4 * j + 3] += x.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncols) v[j] += r[j];
+      for (int j = 0; j < 4; ++j)
+        if (j < nv) o[j] = __float2half_rn(v[j]);
     }
   }
-  if (e.out_dtype == LAV_OUT_F16) {
-    __half* o = reinterpret_cast<__half*>(e.out) + (size_t)orow * e.ldo + col0;
-    if (ncols == 32 && (e.ldo & 7) == 0) {
+}
+
+// aux (fp16 [row][col]) -> staged chunk as fp32, coalesced
+__device__ __forceinline__ void load_aux_phase(const GemmParams& p, float* stg, int row_base, int col, int rr, int cg) {
+  const LavGemmEpilogue& e = p.epi;
+  const int nv = p.N - col;
+  const bool vec = nv >= 4 && (e.ldaux & 3) == 0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 u;
-        u.x = pack_half2(v[8 * j], v[8 * j + 1]), u.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
-        u.z = pack_half2(v[8 * j + 4], v[8 * j + 5]), u.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
-        reinterpret_cast<uint4*>(o)[j] = u;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncols) o[j] = __float2half_rn(v[j]);
-    }
-  } else {
-    float* o = reinterpret_cast<float*>(e.out) + (size_t)orow * e.ldo + col0;
-    if (e.accumulate == LAV_ACCUMULATE) {
-      if (p.splits > 1) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < ncols) atomicAdd(o + j, v[j]);
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + rr;
+    const int row = row_base + r;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < p.M && nv > 0) {
+      const __half* x = reinterpret_cast<const __half*>(e.aux) + (size_t)row * e.ldaux + col;
+      if (vec) {
+        uint2 u = *reinterpret_cast<const uint2*>(x);
+        const float2 f0 = __half22float2(*reinterpret_cast<__half2*>(&u.x));
+        const float2 f1 = __half22float2(*reinterpret_cast<__half2*>(&u.y));
+        a = make_float4(f0.x, f0.y, f1.x, f1.y);
       } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < ncols) o[j] += v[j];
+        a.x = __half2float(x[0]);
+        if (nv > 1) a.y = __half2float(x[1]);
+        if (nv > 2) a.z = __half2float(x[2]);
+        if (nv > 3) a.w = __half2float(x[3]);
       }
-    } else if (ncols == 32 && (e.ldo & 3) == 0) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncols) o[j] = v[j];
     }
+    *reinterpret_cast<float4*>(stg + r * kEpiStride + 4 * cg) = a;
   }
 }
 
@@ -174,7 +195,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  float* epi_stage = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + Cfg::STAGES;
   uint64_t* tmem_full = bars + 2 * Cfg::STAGES;
@@ -199,7 +221,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  if (warp == 2) tmem_alloc<Cfg::TMEM_ALLOC>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -277,31 +299,89 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ------------------------------------------------ epilogue: warpgroup g drains accumulator stage g
     const int wg = (warp - 4) >> 2;
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    float* stg = epi_stage + (warp - 4) * (kEpiStride * 32);
+    const int rr = lane >> 3, cg = lane & 7;  // this lane's row-within-group / 4-column group in the store phase
+    const LavGemmEpilogue& e = p.epi;
+    const int store_mode = e.out_dtype == LAV_OUT_F16 ? ST_F16
+                           : e.accumulate != LAV_ACCUMULATE ? ST_F32 : (p.splits > 1 ? ST_F32_RED : ST_F32_RMW);
     int iter = 0;
     for (int item = blockIdx.x; item < total; item += gridDim.x, ++iter) {
       if ((iter & 1) != wg) continue;
       const TileCoord t = decode_tile(p, item);
       mbar_wait(tmem_full + wg, (iter >> 1) & 1, 4);
       tc_fence_after();
-      const int row = t.m_blk * BM + q * 32 + lane;
+      const int row_base = t.m_blk * BM + q * 32;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + wg * BN;
+      const int nchunks = min(BN / 32, (p.N - t.n_blk * BN + 31) / 32);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < nchunks; ++c) {
         const int col0 = t.n_blk * BN + c * 32;
-        if (col0 >= p.N) break;
+        const int col = col0 + 4 * cg;  // this lane's columns in the transposed (store) phases
         uint32_t acc[32];
         tmem_ld_32x32(taddr + c * 32, acc);
         tmem_ld_wait();
-        if (row < p.M) epilogue_chunk(p, acc, row, col0);
+        if (c == nchunks - 1) {  // accumulator fully read: hand the TMEM stage back to the MMA warp early
+          tc_fence_before();
+          mbar_arrive(tmem_empty + wg);
+        }
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * e.alpha;
+        if (e.bias) {
+          if (col0 + 32 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col0) + j);
+              v[4 * j] += b.x, v[4 * j + 1] += b.y, v[4 * j + 2] += b.z, v[4 * j + 3] += b.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) v[j] += __ldg(e.bias + col0 + j);
+          }
+        }
+        if (e.act == LAV_ACT_GELU) {
+          if (e.aux) {
+            stage_rows(stg, lane, v);
+            __syncwarp();
+            store_aux_phase(p, stg, row_base, col, rr, cg);
+            __syncwarp();
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        } else if (e.act == LAV_ACT_GELU_BWD) {
+          load_aux_phase(p, stg, row_base, col, rr, cg);
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 x = *reinterpret_cast<const float4*>(stg + lane * kEpiStride + 4 * j);
+            v[4 * j] *= gelu_erf_grad(x.x), v[4 * j + 1] *= gelu_erf_grad(x.y);
+            v[4 * j + 2] *= gelu_erf_grad(x.z), v[4 * j + 3] *= gelu_erf_grad(x.w);
+          }
+          __syncwarp();
+        }
+        if (e.row_scale) {
+          const int row = min(row_base + lane, p.M - 1);
+          const float sc = __ldg(e.row_scale + row / e.rows_per_scale);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= sc;
+        }
+        stage_rows(stg, lane, v);
+        __syncwarp();
+        switch (store_mode) {
+          case ST_F16: store_phase<ST_F16>(p, stg, row_base, col, rr, cg); break;
+          case ST_F32_RED: store_phase<ST_F32_RED>(p, stg, row_base, col, rr, cg); break;
+          case ST_F32_RMW: store_phase<ST_F32_RMW>(p, stg, row_base, col, rr, cg); break;
+          default: store_phase<ST_F32>(p, stg, row_base, col, rr, cg); break;
+        }
+        __syncwarp();
       }
-      tc_fence_before();
-      mbar_arrive(tmem_empty + wg);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  if (warp == 2) tmem_dealloc<Cfg::TMEM_ALLOC>(tmem_base);
 }
 
 template <int BN, int AMAJ, int BMAJ>
@@ -360,17 +440,27 @@ extern "C" int lav_gemm_f16(const void* A, int64_t lda, int a_major, const void*
   p.m_blocks = (M + BM - 1) / BM;
   p.k_blocks = (K + BK - 1) / BK;
   p.epi = *epi;
-  // tile width: 256 when N is large, 64 for narrow outputs (less padding waste / more CTAs)
-  int bn = 128;
-  if (N <= 64) bn = 64;
-  else if (N >= 512 && (N % 256 == 0 || N > 2048)) bn = 256;
-  const int n_blocks = (N + bn - 1) / bn;
-  int splits = split_k;
-  if (splits <= 0) {  // auto: fill the machine when the output has few tiles but the contraction is long
-    const int tiles = p.m_blocks * n_blocks;
-    splits = 1;
-    if (epi->accumulate == LAV_ACCUMULATE && epi->act == LAV_ACT_NONE && tiles < 2 * sm_count())
-      splits = std::max(1, std::min((2 * sm_count() + tiles - 1) / tiles, p.k_blocks / 4));
+  // Tile width BN in {64,128,192,256} and split-K factor chosen by a small cost model (SM clocks):
+  //   per k-block  max(MMA issue 2*BN, operand feed (BM+BN)*BK*2 bytes at ~110 B/clk/SM), times the number of
+  //   waves over the SMs, plus one exposed epilogue (atomics cost more).
+  const int nsm = sm_count();
+  const bool may_split = split_k != 1 && epi->accumulate == LAV_ACCUMULATE && epi->act == LAV_ACT_NONE;
+  int bn = 128, splits = 1;
+  double best = 1e30;
+  const int cands[4] = {256, 192, 128, 64};
+  for (int ci = 0; ci < 4; ++ci) {
+    const int c = cands[ci];
+    if (c > 64 && c >= 2 * ((N + 63) / 64 * 64)) continue;  // far wider than the problem
+    const int tiles = p.m_blocks * ((N + c - 1) / c);
+    const double kb_clk = std::max(2.0 * c, (BM + c) * BK * 2 / 110.0);
+    const int smax = may_split ? (split_k > 1 ? split_k : std::max(1, std::min(p.k_blocks / 4, 64))) : 1;
+    for (int sp = (split_k > 1 ? split_k : 1); sp <= smax; ++sp) {
+      const int kbs = (p.k_blocks + sp - 1) / sp;
+      const int items = tiles * ((p.k_blocks + kbs - 1) / kbs);
+      const int waves = (items + nsm - 1) / nsm;
+      const double cost = waves * (kbs * kb_clk + 300.0) + c * (sp > 1 ? 10.0 : 6.0);
+      if (cost < best) best = cost, bn = c, splits = sp;
+    }
   }
   splits = std::max(1, std::min(splits, p.k_blocks));
   LAV_REQUIRE(splits == 1 || epi->accumulate == LAV_ACCUMULATE, "lav_gemm_f16: split-K needs LAV_ACCUMULATE");
@@ -379,6 +469,7 @@ extern "C" int lav_gemm_f16(const void* A, int64_t lda, int a_major, const void*
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   switch (bn) {
     case 64: return dispatch_major<64>(A, lda, a_major, B, ldb, b_major, p, s);
+    case 192: return dispatch_major<192>(A, lda, a_major, B, ldb, b_major, p, s);
     case 256: return dispatch_major<256>(A, lda, a_major, B, ldb, b_major, p, s);
     default: return dispatch_major<128>(A, lda, a_major, B, ldb, b_major, p, s);
   }

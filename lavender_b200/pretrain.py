@@ -30,6 +30,18 @@ class LAVENDER_Pretrain_MLM(LAVENDER_Base):
         """One np.random.permutation per clip, exactly as main_pretrain_mlm.py:90-91 consumes the numpy RNG."""
         return [np.random.permutation([j for j in range(B) if j != i])[:max(O - 1, 0)] for i in range(B)]
 
+    def build_vtm_pairs(self, B, O, negs=None, device=None):
+        """(video index, text index, label token) of the B*O pairs, in the reference's order."""
+        if negs is None:
+            negs = self.draw_negatives(B, O)
+        vid_idx, txt_idx, label = [], [], []
+        for i in range(B):
+            vid_idx += [i] * O
+            txt_idx += [i] + [int(j) for j in negs[i][:O - 1]]
+            label += [self.true_token_id] + [self.false_token_id] * (O - 1)
+        return (torch.tensor(vid_idx, device=device), torch.tensor(txt_idx, device=device),
+                torch.tensor(label, device=device))
+
     def forward(self, batch):
         batch = defaultdict(lambda: None, batch)
         img, txt, mask = batch["img"], batch["txt"], batch["mask"]
@@ -42,19 +54,15 @@ class LAVENDER_Pretrain_MLM(LAVENDER_Base):
         out_mtm = self.fc_mtm(out[:, Lv:])
 
         # VTM: clip i paired with its own caption (label "true") then with O-1 other captions ("false")
-        negs = batch["vtm_negatives"] if batch["vtm_negatives"] is not None else self.draw_negatives(B, O)
-        vid_idx, txt_idx, label = [], [], []
-        for i in range(B):
-            vid_idx += [i] * O
-            txt_idx += [i] + [int(j) for j in negs[i][:O - 1]]
-            label += [self.true_token_id] + [self.false_token_id] * (O - 1)
         dev = img.device
-        vi = torch.tensor(vid_idx, device=dev)
-        ti = torch.tensor(txt_idx, device=dev)
+        if batch["vtm_vid_idx"] is not None:     # pre-built on the device (CUDA-graph replay: see graph.py)
+            vi, ti, lab = batch["vtm_vid_idx"], batch["vtm_txt_idx"], batch["vtm_labels"]
+        else:
+            vi, ti, lab = self.build_vtm_pairs(B, O, batch["vtm_negatives"], dev)
         p_txt, p_mask, p_feat = self.prepro_txt_inputs(txt[ti], mask_txt[ti], feat_txt[ti], task_name="vtm",
                                                        prompt=batch["vtm_prompt"])
         ans_vtm = torch.full_like(p_txt, -1)
-        ans_vtm[:, -1] = torch.tensor(label, device=dev, dtype=ans_vtm.dtype)
+        ans_vtm[:, -1] = lab.to(ans_vtm.dtype)
         out, _ = self.go_cross(feat_img[vi], mask_img[vi], p_feat, p_mask)
         out_vtm = self.fc_mtm(out[:, Lv:])
         return {"out_vtm": out_vtm, "out_mtm": out_mtm, "ans_vtm": ans_vtm, "ans_mtm": batch["ans_mtm"]}

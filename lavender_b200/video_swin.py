@@ -248,8 +248,11 @@ class SwinTransformer3D(nn.Module):
 
     def sample_drop_path(self, B, device):
         """Per-sample DropPath factors floor(keep_prob + U)/keep_prob (video_swin.py:46-54), [n_blocks, 2, B]."""
-        rates = torch.tensor([blk.drop_path_rate for layer in self.layers for blk in layer.blocks], device=device)
-        kp = (1.0 - rates).view(-1, 1, 1)
+        c = self.__dict__.get("_lav_keep_prob")
+        if c is None or c.device != device:   # cached: no host->device copy per step (CUDA-graph capturable)
+            rates = torch.tensor([blk.drop_path_rate for layer in self.layers for blk in layer.blocks])
+            c = self.__dict__["_lav_keep_prob"] = (1.0 - rates).view(-1, 1, 1).to(device)
+        kp, rates = c, c
         u = torch.rand(rates.numel(), 2, B, device=device)
         return (torch.floor(kp + u) / kp).contiguous()
 
