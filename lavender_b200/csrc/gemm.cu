@@ -70,36 +70,27 @@ __device__ __forceinline__ void stage_rows(float* stg, int lane, const float (&v
 
 enum { ST_F32 = 0, ST_F32_RMW = 1, ST_F32_RED = 2, ST_F16 = 3 };
 
-// staged chunk -> out (+ residual, through the row map).  (rr, cg) = lane's row-in-group / 4-column group.
+// staged chunk -> out (+ prefetched residual, at the pre-resolved output rows).  (rr, cg) = lane's row-in-group /
+// 4-column group; orow[it] < 0 marks rows beyond M.
 template <int MODE>
-__device__ __forceinline__ void store_phase(const GemmParams& p, const float* stg, int row_base, int col, int rr, int cg) {
+__device__ __forceinline__ void store_phase(const GemmParams& p, const float* stg, const int (&orow)[8],
+                                            const uint4 (&res)[8], bool use_res, int col, int rr, int cg) {
   const LavGemmEpilogue& e = p.epi;
   const int nv = p.N - col;
   if (nv <= 0) return;
   const bool vec_o = nv >= 4 && (e.ldo & 3) == 0;
-  const bool vec_r = nv >= 4 && (e.ldres & 3) == 0;
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int r = it * 4 + rr;
-    const int row = row_base + r;
-    if (row >= p.M) continue;
+    if (orow[it] < 0) continue;
     float4 a = *reinterpret_cast<const float4*>(stg + r * kEpiStride + 4 * cg);
-    const int orow = e.row_map ? __ldg(e.row_map + row) : row;
-    if (e.residual) {
-      const float* rs = e.residual + (size_t)orow * e.ldres + col;
-      if (vec_r) {
-        const float4 x = *reinterpret_cast<const float4*>(rs);
-        a.x += x.x, a.y += x.y, a.z += x.z, a.w += x.w;
-      } else {
-        a.x += rs[0];
-        if (nv > 1) a.y += rs[1];
-        if (nv > 2) a.z += rs[2];
-        if (nv > 3) a.w += rs[3];
-      }
+    if (use_res) {
+      a.x += __uint_as_float(res[it].x), a.y += __uint_as_float(res[it].y);
+      a.z += __uint_as_float(res[it].z), a.w += __uint_as_float(res[it].w);
     }
     const float v[4] = {a.x, a.y, a.z, a.w};
     if (MODE == ST_F16) {
-      __half* o = reinterpret_cast<__half*>(e.out) + (size_t)orow * e.ldo + col;
+      __half* o = reinterpret_cast<__half*>(e.out) + (size_t)orow[it] * e.ldo + col;
       if (vec_o) {
         *reinterpret_cast<uint2*>(o) = make_uint2(pack_half2(a.x, a.y), pack_half2(a.z, a.w));
       } else {
@@ -108,7 +99,7 @@ __device__ __forceinline__ void store_phase(const GemmParams& p, const float* st
           if (j < nv) o[j] = __float2half_rn(v[j]);
       }
     } else {
-      float* o = reinterpret_cast<float*>(e.out) + (size_t)orow * e.ldo + col;
+      float* o = reinterpret_cast<float*>(e.out) + (size_t)orow[it] * e.ldo + col;
       if (MODE == ST_F32_RED) {
         if (vec_o) red_add_v4(o, a);
         else {
@@ -160,31 +151,138 @@ __device__ __forceinline__ void store_aux_phase(const GemmParams& p, const float
   }
 }
 
-// aux (fp16 [row][col]) -> staged chunk as fp32, coalesced
-__device__ __forceinline__ void load_aux_phase(const GemmParams& p, float* stg, int row_base, int col, int rr, int cg) {
+// Body of the 8 epilogue warps (two warpgroups, one per TMEM accumulator stage), specialised at compile time on the
+// activation, on whether a global input is prefetched (PRE: residual rows) and on the store mode: the epilogue is
+// instruction-issue bound for the short-K GEMMs of the Swin stages, so unused paths must not cost instructions.
+template <int BN, int ACT, int PRE, int STORE>
+__device__ __forceinline__ void epilogue_warps(const GemmParams& p, float* epi_stage, uint64_t* tmem_full,
+                                               uint64_t* tmem_empty, uint32_t tmem_base, int warp, int lane, int total) {
+  const int wg = (warp - 4) >> 2;
+  const int q = warp & 3;  // TMEM lane quarter this warp may access
+  float* stg = epi_stage + (warp - 4) * (kEpiStride * 32);
+  const int rr = lane >> 3, cg = lane & 7;  // this lane's row-within-group / 4-column group in the store phase
   const LavGemmEpilogue& e = p.epi;
-  const int nv = p.N - col;
-  const bool vec = nv >= 4 && (e.ldaux & 3) == 0;
+  constexpr bool use_res = PRE == 1;
+  constexpr bool use_auxin = ACT == LAV_ACT_GELU_BWD;
+  constexpr bool use_pre = use_res || use_auxin;
+  int iter = 0;
+  for (int item = blockIdx.x; item < total; item += gridDim.x, ++iter) {
+    if ((iter & 1) != wg) continue;
+    const TileCoord t = decode_tile(p, item);
+    const int row_base = t.m_blk * BM + q * 32;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + wg * BN;
+    const int nchunks = min(BN / 32, (p.N - t.n_blk * BN + 31) / 32);
+    // output rows of this lane's 8 store-phase rows (row map resolved once per tile)
+    int orow[8];
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int r = it * 4 + rr;
-    const int row = row_base + r;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row < p.M && nv > 0) {
-      const __half* x = reinterpret_cast<const __half*>(e.aux) + (size_t)row * e.ldaux + col;
-      if (vec) {
-        uint2 u = *reinterpret_cast<const uint2*>(x);
-        const float2 f0 = __half22float2(*reinterpret_cast<__half2*>(&u.x));
-        const float2 f1 = __half22float2(*reinterpret_cast<__half2*>(&u.y));
-        a = make_float4(f0.x, f0.y, f1.x, f1.y);
-      } else {
-        a.x = __half2float(x[0]);
-        if (nv > 1) a.y = __half2float(x[1]);
-        if (nv > 2) a.z = __half2float(x[2]);
-        if (nv > 3) a.w = __half2float(x[3]);
+    for (int it = 0; it < 8; ++it) {
+      const int row = row_base + it * 4 + rr;
+      orow[it] = row < p.M ? (e.row_map ? __ldg(e.row_map + row) : row) : -1;
+    }
+    // Prefetch of the chunk's global INPUT (residual rows, or the GELU pre-activation for GELU_BWD) into registers,
+    // one chunk ahead: chunk 0 is requested before the accumulator is ready, so the latency hides under the MMAs.
+    auto prefetch = [&](uint4(&dst)[8], int c) {
+      const int col = t.n_blk * BN + c * 32 + 4 * cg;
+      const int nv = p.N - col;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        dst[it] = make_uint4(0u, 0u, 0u, 0u);
+        if (orow[it] < 0 || nv <= 0) continue;
+        if (use_res) {
+          const float* rs = e.residual + (size_t)orow[it] * e.ldres + col;
+          if (nv >= 4 && (e.ldres & 3) == 0) dst[it] = *reinterpret_cast<const uint4*>(rs);
+          else {
+            dst[it].x = __float_as_uint(rs[0]);
+            if (nv > 1) dst[it].y = __float_as_uint(rs[1]);
+            if (nv > 2) dst[it].z = __float_as_uint(rs[2]);
+            if (nv > 3) dst[it].w = __float_as_uint(rs[3]);
+          }
+        } else if (use_auxin) {
+          const __half* x = reinterpret_cast<const __half*>(e.aux) + (size_t)(row_base + it * 4 + rr) * e.ldaux + col;
+          if (nv >= 4 && (e.ldaux & 3) == 0) {
+            const uint2 u = *reinterpret_cast<const uint2*>(x);
+            dst[it].x = u.x, dst[it].y = u.y;
+          } else {
+            const __half z = __float2half_rn(0.f);
+            __half2 h0 = __halves2half2(x[0], nv > 1 ? x[1] : z), h1 = __halves2half2(nv > 2 ? x[2] : z, nv > 3 ? x[3] : z);
+            dst[it].x = *reinterpret_cast<uint32_t*>(&h0), dst[it].y = *reinterpret_cast<uint32_t*>(&h1);
+          }
+        }
+      }
+    };
+    uint4 cur[8], nxt[8];
+    if (use_pre) prefetch(cur, 0);
+    mbar_wait(tmem_full + wg, (iter >> 1) & 1, 4);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < nchunks; ++c) {
+      const int col0 = t.n_blk * BN + c * 32;
+      const int col = col0 + 4 * cg;  // this lane's columns in the transposed (store) phases
+      uint32_t acc[32];
+      tmem_ld_32x32(taddr + c * 32, acc);
+      if (use_pre && c + 1 < nchunks) prefetch(nxt, c + 1);
+      tmem_ld_wait();
+      if (c == nchunks - 1) {  // accumulator fully read: hand the TMEM stage back to the MMA warp early
+        tc_fence_before();
+        mbar_arrive(tmem_empty + wg);
+      }
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * e.alpha;
+      if (e.bias) {
+        if (col0 + 32 <= p.N) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col0) + j);
+            v[4 * j] += b.x, v[4 * j + 1] += b.y, v[4 * j + 2] += b.z, v[4 * j + 3] += b.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) v[j] += __ldg(e.bias + col0 + j);
+        }
+      }
+      if (ACT == LAV_ACT_GELU) {
+        if (e.aux) {
+          stage_rows(stg, lane, v);
+          __syncwarp();
+          store_aux_phase(p, stg, row_base, col, rr, cg);
+          __syncwarp();
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+      } else if (use_auxin) {
+        // pre-activation: (store-layout registers) -> smem -> (row-layout registers)
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&cur[it].x));
+          const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&cur[it].y));
+          *reinterpret_cast<float4*>(stg + (it * 4 + rr) * kEpiStride + 4 * cg) = make_float4(f0.x, f0.y, f1.x, f1.y);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 x = *reinterpret_cast<const float4*>(stg + lane * kEpiStride + 4 * j);
+          v[4 * j] *= gelu_erf_grad(x.x), v[4 * j + 1] *= gelu_erf_grad(x.y);
+          v[4 * j + 2] *= gelu_erf_grad(x.z), v[4 * j + 3] *= gelu_erf_grad(x.w);
+        }
+        __syncwarp();
+      }
+      if (e.row_scale) {
+        const int row = min(row_base + lane, p.M - 1);
+        const float sc = __ldg(e.row_scale + row / e.rows_per_scale);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= sc;
+      }
+      stage_rows(stg, lane, v);
+      __syncwarp();
+      store_phase<STORE>(p, stg, orow, cur, use_res, col, rr, cg);
+      __syncwarp();
+      if (use_pre) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) cur[it] = nxt[it];
       }
     }
-    *reinterpret_cast<float4*>(stg + r * kEpiStride + 4 * cg) = a;
   }
 }
 
@@ -297,86 +395,29 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else if (warp >= 4) {
     // ------------------------------------------------ epilogue: warpgroup g drains accumulator stage g
-    const int wg = (warp - 4) >> 2;
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    float* stg = epi_stage + (warp - 4) * (kEpiStride * 32);
-    const int rr = lane >> 3, cg = lane & 7;  // this lane's row-within-group / 4-column group in the store phase
     const LavGemmEpilogue& e = p.epi;
-    const int store_mode = e.out_dtype == LAV_OUT_F16 ? ST_F16
-                           : e.accumulate != LAV_ACCUMULATE ? ST_F32 : (p.splits > 1 ? ST_F32_RED : ST_F32_RMW);
-    int iter = 0;
-    for (int item = blockIdx.x; item < total; item += gridDim.x, ++iter) {
-      if ((iter & 1) != wg) continue;
-      const TileCoord t = decode_tile(p, item);
-      mbar_wait(tmem_full + wg, (iter >> 1) & 1, 4);
-      tc_fence_after();
-      const int row_base = t.m_blk * BM + q * 32;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + wg * BN;
-      const int nchunks = min(BN / 32, (p.N - t.n_blk * BN + 31) / 32);
-#pragma unroll 1
-      for (int c = 0; c < nchunks; ++c) {
-        const int col0 = t.n_blk * BN + c * 32;
-        const int col = col0 + 4 * cg;  // this lane's columns in the transposed (store) phases
-        uint32_t acc[32];
-        tmem_ld_32x32(taddr + c * 32, acc);
-        tmem_ld_wait();
-        if (c == nchunks - 1) {  // accumulator fully read: hand the TMEM stage back to the MMA warp early
-          tc_fence_before();
-          mbar_arrive(tmem_empty + wg);
-        }
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * e.alpha;
-        if (e.bias) {
-          if (col0 + 32 <= p.N) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col0) + j);
-              v[4 * j] += b.x, v[4 * j + 1] += b.y, v[4 * j + 2] += b.z, v[4 * j + 3] += b.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) v[j] += __ldg(e.bias + col0 + j);
-          }
-        }
-        if (e.act == LAV_ACT_GELU) {
-          if (e.aux) {
-            stage_rows(stg, lane, v);
-            __syncwarp();
-            store_aux_phase(p, stg, row_base, col, rr, cg);
-            __syncwarp();
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-        } else if (e.act == LAV_ACT_GELU_BWD) {
-          load_aux_phase(p, stg, row_base, col, rr, cg);
-          __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 x = *reinterpret_cast<const float4*>(stg + lane * kEpiStride + 4 * j);
-            v[4 * j] *= gelu_erf_grad(x.x), v[4 * j + 1] *= gelu_erf_grad(x.y);
-            v[4 * j + 2] *= gelu_erf_grad(x.z), v[4 * j + 3] *= gelu_erf_grad(x.w);
-          }
-          __syncwarp();
-        }
-        if (e.row_scale) {
-          const int row = min(row_base + lane, p.M - 1);
-          const float sc = __ldg(e.row_scale + row / e.rows_per_scale);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= sc;
-        }
-        stage_rows(stg, lane, v);
-        __syncwarp();
-        switch (store_mode) {
-          case ST_F16: store_phase<ST_F16>(p, stg, row_base, col, rr, cg); break;
-          case ST_F32_RED: store_phase<ST_F32_RED>(p, stg, row_base, col, rr, cg); break;
-          case ST_F32_RMW: store_phase<ST_F32_RMW>(p, stg, row_base, col, rr, cg); break;
-          default: store_phase<ST_F32>(p, stg, row_base, col, rr, cg); break;
-        }
-        __syncwarp();
-      }
+    const int st = e.out_dtype == LAV_OUT_F16 ? ST_F16
+                   : e.accumulate != LAV_ACCUMULATE ? ST_F32 : (p.splits > 1 ? ST_F32_RED : ST_F32_RMW);
+    const int pre = e.residual != nullptr ? 1 : 0;
+#define LAV_EPI(A, P, S) epilogue_warps<BN, A, P, S>(p, epi_stage, tmem_full, tmem_empty, tmem_base, warp, lane, total)
+    if (e.act == LAV_ACT_GELU) {
+      if (st == ST_F16 && !pre) LAV_EPI(LAV_ACT_GELU, 0, ST_F16);
+      else LAV_EPI(LAV_ACT_GELU, 0, ST_F32);               // host restricts GELU to {f16, f32 store} without residual
+    } else if (e.act == LAV_ACT_GELU_BWD) {
+      if (st == ST_F16) LAV_EPI(LAV_ACT_GELU_BWD, 0, ST_F16);
+      else LAV_EPI(LAV_ACT_GELU_BWD, 0, ST_F32);
+    } else if (!pre) {
+      if (st == ST_F16) LAV_EPI(LAV_ACT_NONE, 0, ST_F16);
+      else if (st == ST_F32) LAV_EPI(LAV_ACT_NONE, 0, ST_F32);
+      else if (st == ST_F32_RED) LAV_EPI(LAV_ACT_NONE, 0, ST_F32_RED);
+      else LAV_EPI(LAV_ACT_NONE, 0, ST_F32_RMW);
+    } else {
+      if (st == ST_F16) LAV_EPI(LAV_ACT_NONE, 1, ST_F16);
+      else if (st == ST_F32) LAV_EPI(LAV_ACT_NONE, 1, ST_F32);
+      else if (st == ST_F32_RED) LAV_EPI(LAV_ACT_NONE, 1, ST_F32_RED);
+      else LAV_EPI(LAV_ACT_NONE, 1, ST_F32_RMW);
     }
+#undef LAV_EPI
   }
 
   tc_fence_before();
@@ -420,7 +461,7 @@ static int dispatch_major(const void* A, int64_t lda, int a_major, const void* B
   if (a_major == LAV_MAJOR_K && b_major == LAV_MAJOR_K) return launch_gemm<BN, 0, 0>(A, lda, B, ldb, p, s);
   if (a_major == LAV_MAJOR_K && b_major == LAV_MAJOR_MN) return launch_gemm<BN, 0, 1>(A, lda, B, ldb, p, s);
   if (a_major == LAV_MAJOR_MN && b_major == LAV_MAJOR_MN) return launch_gemm<BN, 1, 1>(A, lda, B, ldb, p, s);
-  return launch_gemm<BN, 1, 0>(A, lda, B, ldb, p, s);
+  return set_error(LAV_E_INVALID, "lav_gemm_f16: (A MN-major, B K-major) is not instantiated (no caller on the hot path)");
 }
 
 }  // namespace lav
@@ -435,6 +476,8 @@ extern "C" int lav_gemm_f16(const void* A, int64_t lda, int a_major, const void*
               "lav_gemm_f16: accumulation needs an fp32 output");
   LAV_REQUIRE(!(epi->act != LAV_ACT_NONE && split_k > 1), "lav_gemm_f16: activation with split-K");
   LAV_REQUIRE(!(epi->act == LAV_ACT_GELU_BWD && !epi->aux), "lav_gemm_f16: GELU_BWD needs aux");
+  LAV_REQUIRE(!(epi->act != LAV_ACT_NONE && epi->residual), "lav_gemm_f16: activations cannot be combined with a residual");
+  LAV_REQUIRE(!(epi->act != LAV_ACT_NONE && epi->accumulate == LAV_ACCUMULATE), "lav_gemm_f16: activations cannot accumulate");
   GemmParams p;
   p.M = M, p.N = N, p.K = K;
   p.m_blocks = (M + BM - 1) / BM;

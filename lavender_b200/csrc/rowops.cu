@@ -162,33 +162,41 @@ __global__ void __launch_bounds__(kRowThreads) ln_bwd_kernel(const LnBwdParams p
   }
 }
 
-// dgamma[c] += sum_r dy[r,c]*xhat[r,c] ; dbeta[c] += sum_r dy[r,c].  Block = 32 columns x 8 row lanes.
+// dgamma[c] += sum_r dy[r,c]*xhat[r,c] ; dbeta[c] += sum_r dy[r,c].
+// Block = 8 warps; a warp covers 128 consecutive columns (one float4 / 4 halfs per lane) of one row at a time and
+// walks the rows of its slab with stride 8; partial sums meet in shared memory, one atomic per column per block.
 __global__ void __launch_bounds__(256) ln_bwd_params_kernel(const LnBwdParams p, int rows_per_block) {
-  __shared__ float sg[8][33], sb[8][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  __shared__ float sg[8][128], sb[8][128];
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
   const int W = p.G * p.C;
-  const int col = blockIdx.x * 32 + tx;
+  const int col = blockIdx.x * 128 + lane * 4;  // C % 4 == 0, so a quad never straddles two gathered source rows
   const int g = col / p.C, cc = col - g * p.C;
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(p.rows, r0 + rows_per_block);
-  float ag = 0.f, ab = 0.f;
+  float ag[4] = {0.f, 0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f};
   if (col < W) {
-    for (int r = r0 + ty; r < r1; r += 8) {
+    for (int r = r0 + wy; r < r1; r += 8) {
       const int64_t sr = p.map ? p.map[(int64_t)r * p.G + g] : (int64_t)r * p.G + g;
-      const float xv = p.x[sr * p.ldx + cc];
-      const float d = p.dy_f32 ? reinterpret_cast<const float*>(p.dy)[(int64_t)r * p.lddy + col]
-                               : __half2float(reinterpret_cast<const __half*>(p.dy)[(int64_t)r * p.lddy + col]);
-      ag += d * (xv - p.mean[r]) * p.rstd[r];
-      ab += d;
+      const float4 xv = *reinterpret_cast<const float4*>(p.x + sr * p.ldx + cc);
+      const float4 d = load_dy4(p, r, col);
+      const float mean = p.mean[r], rstd = p.rstd[r];
+      ag[0] += d.x * (xv.x - mean) * rstd, ag[1] += d.y * (xv.y - mean) * rstd;
+      ag[2] += d.z * (xv.z - mean) * rstd, ag[3] += d.w * (xv.w - mean) * rstd;
+      ab[0] += d.x, ab[1] += d.y, ab[2] += d.z, ab[3] += d.w;
     }
   }
-  sg[ty][tx] = ag, sb[ty][tx] = ab;
-  __syncthreads();
-  if (ty == 0 && col < W) {
 #pragma unroll
-    for (int k = 1; k < 8; ++k) ag += sg[k][tx], ab += sb[k][tx];
-    atomicAdd(p.dgamma + col, ag);
-    atomicAdd(p.dbeta + col, ab);
+  for (int j = 0; j < 4; ++j) sg[wy][lane * 4 + j] = ag[j], sb[wy][lane * 4 + j] = ab[j];
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    if (c < W) {
+      float tg = 0.f, tb = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tg += sg[k][threadIdx.x], tb += sb[k][threadIdx.x];
+      atomicAdd(p.dgamma + c, tg);
+      atomicAdd(p.dbeta + c, tb);
+    }
   }
 }
 
@@ -227,22 +235,35 @@ __global__ void __launch_bounds__(256) cast_flat_kernel(const float* __restrict_
     dst[i] = __float2half_rn(src[i]);
 }
 
-// out[c] += sum_r x16[r, c]   (bias gradients).  Block = 32 columns x 8 row lanes over a slab of rows.
+// out[c] += alpha * sum_r x16[r, c]   (bias gradients).  Block = 8 warps; a warp covers 256 consecutive columns of
+// one row (one 16-byte load per lane) and walks its slab of rows with stride 8.  Needs ld % 8 == 0.
 __global__ void __launch_bounds__(256)
 colsum_f16_kernel(const __half* x, int64_t ld, int rows, int N, float* out, float alpha, int rows_per_block) {
-  __shared__ float sm[8][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int col = blockIdx.x * 32 + tx;
+  __shared__ float sm[8][256];
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + lane * 8;
   const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
-  float a = 0.f;
-  if (col < N)
-    for (int r = r0 + ty; r < r1; r += 8) a += __half2float(x[(int64_t)r * ld + col]);
-  sm[ty][tx] = a;
-  __syncthreads();
-  if (ty == 0 && col < N) {
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col + 8 <= ld && col < N) {
+    for (int r = r0 + wy; r < r1; r += 8) {
+      const uint4 u = *reinterpret_cast<const uint4*>(x + (int64_t)r * ld + col);
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
-    for (int k = 1; k < 8; ++k) a += sm[k][tx];
-    atomicAdd(out + col, a * alpha);
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = __half22float2(h[q]);
+        a[2 * q] += f.x, a[2 * q + 1] += f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sm[wy][lane * 8 + j] = a[j];
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sm[k][threadIdx.x];
+    atomicAdd(out + c, t * alpha);
   }
 }
 
@@ -255,9 +276,9 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const __half2* dy, const 
 }
 
 static int slab_rows(int rows, int col_blocks) {
-  // enough row slabs to fill the machine a few times, at least 64 rows each
-  int want = std::max(1, (4 * sm_count()) / std::max(1, col_blocks));
-  int rpb = std::max(64, (rows + want - 1) / want);
+  // enough row slabs to fill the machine a few times, at least 32 rows each
+  int want = std::max(1, (6 * sm_count()) / std::max(1, col_blocks));
+  int rpb = std::max(32, (rows + want - 1) / want);
   return (rpb + 7) / 8 * 8;
 }
 
@@ -292,7 +313,7 @@ extern "C" int lav_layernorm_bwd(const void* dy, int64_t lddy, int dy_is_f32, co
                 dx32, lddx32, (__half*)dx16, lddx16, dgamma, dbeta, rows};
   cudaStream_t s = (cudaStream_t)stream;
   if (dgamma) {  // must read x before an in-place dx32 overwrite of the same rows
-    const int cb = (G * C + 31) / 32;
+    const int cb = (G * C + 127) / 128;
     const int rpb = slab_rows(rows, cb);
     dim3 grid(cb, (rows + rpb - 1) / rpb);
     ln_bwd_params_kernel<<<grid, 256, 0, s>>>(p, rpb);
@@ -331,8 +352,9 @@ extern "C" int lav_cast_f32_to_f16(const float* src, void* dst, int64_t n, void*
 
 extern "C" int lav_colsum_f16(const void* x16, int64_t ld, int rows, int N, float* out, float alpha, void* stream) {
   LAV_REQUIRE(x16 && out, "lav_colsum_f16: null pointer");
+  LAV_REQUIRE((ld % 8) == 0 && ((uintptr_t)x16 % 16) == 0, "lav_colsum_f16: need ld %% 8 == 0 and a 16-byte aligned base");
   if (rows <= 0 || N <= 0) return LAV_OK;
-  const int cb = (N + 31) / 32;
+  const int cb = (N + 255) / 256;
   const int rpb = slab_rows(rows, cb);
   dim3 grid(cb, (rows + rpb - 1) / rpb);
   colsum_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)x16, ld, rows, N, out, alpha, rpb);

@@ -160,11 +160,31 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 
 // ---------------------------------------------------------------- small math helpers
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// Exact-erf GELU (nn.GELU() / HF "gelu") through the normal CDF Phi(x) = 0.5 (1 + erf(x / sqrt 2)), with erf from
+// Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, i.e. fp32 rounding level): one MUFU.RCP, one MUFU.EX2 and ~10 FMA-pipe
+// instructions instead of erff()'s ~30 -- the GEMM epilogues that apply it are instruction-issue bound.
+//   q(x) = 0.5 * (a1 t + ... + a5 t^5) * exp(-x^2 / 2),  t = 1 / (1 + p |x| / sqrt 2);   Phi = x >= 0 ? 1 - q : q
+__device__ __forceinline__ void normal_cdf_pdf(float x, float& cdf, float& pdf) {
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.2316418882f, ax, 1.0f));   // rcp.approx; p / sqrt(2)
+  const float e = exp2f(x * x * -0.7213475204f);              // exp(-x^2/2)
+  float poly = fmaf(t, 0.5307027145f, -0.7265760135f);        // 0.5 * a5, 0.5 * a4
+  poly = fmaf(t, poly, 0.7107068705f);                        // 0.5 * a3
+  poly = fmaf(t, poly, -0.1422483680f);                       // 0.5 * a2
+  poly = fmaf(t, poly, 0.1274147960f);                        // 0.5 * a1
+  const float q = poly * t * e;
+  cdf = x >= 0.f ? 1.0f - q : q;
+  pdf = 0.3989422804f * e;
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  float c, d;
+  normal_cdf_pdf(x, c, d);
+  return x * c;
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float c, d;
+  normal_cdf_pdf(x, c, d);
+  return fmaf(x, d, c);
 }
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);

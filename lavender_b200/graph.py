@@ -59,6 +59,7 @@ class GraphedPretrainStep:
         n0 = _lib.launch_count()
         self.graph = torch.cuda.CUDAGraph()
         agent.optzr.zero_grad(set_to_none=True)   # first prepare_grads inside the capture records one arena memset
+        ar._ver16 = None                           # ... and the first refresh16 records the fp32 -> fp16 weight cast
         with torch.cuda.graph(self.graph):
             self.l_mtm, self.l_vtm = self._fwd_bwd()
         self.native_launches = _lib.launch_count() - n0   # kernels of the C-ABI library inside one replay

@@ -26,35 +26,42 @@ def _setup(graph):
     return m, ag, batch
 
 
-def test_graph_replay_matches_eager_over_three_steps():
+def test_graph_replay_matches_eager():
+    from lavender_b200.graph import GraphCache
     m1, a1, b1 = _setup(False)
     m2, a2, b2 = _setup(True)
-    for it in range(3):
-        np.random.seed(10 + it)
-        r1 = a1.step(dict(b1), True)
-        if it == 0:                      # capture consumes the numpy RNG once for the example pairs
-            a2.step(dict(b2), True)      # (captures, then replays with its own draw) -> restart both models below
-            break
-    # restart so both see identical RNG streams from step 0 on, with the graph already captured
-    m1, a1, b1 = _setup(False)
-    import lavender_oracle as O
-    cfg = O.ModelCfg(swin=O.SWIN["tiny"], bert_layers=1)
-    m2.load_state_dict(O.make_state_dict(cfg, 0), strict=True)
-    a2.optzr = a2.build_optimizer()
-    from lavender_b200.agent import WarmupLinearLR
-    a2.lr_scheduler = WarmupLinearLR(a2.optzr, a2.args.max_iter)
-    a2.scaler = torch.amp.GradScaler("cuda")
-    a1.scaler = torch.amp.GradScaler("cuda")
+    a2.graphs = GraphCache(a2)
+    g = a2.graphs.get(b2)            # capture now (warm-up + capture leave the weights untouched)
+    assert g.native_launches > 100
+    for (n, p), (_, q) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert torch.equal(p, q), n
+    # 1) gradients of one forward/backward: eager autograd vs one replay
+    np.random.seed(3)
+    m1.train()
+    out = a1.forward_step(dict(b1))
+    ls = a1.loss_func(out["out_mtm"].flatten(0, 1), out["ans_mtm"].flatten()) + \
+        a1.loss_func(out["out_vtm"].flatten(0, 1), out["ans_vtm"].flatten())
+    a1.scaler.scale(ls).backward()
+    m1.arena().finalize_grads()
+    np.random.seed(3)
+    l_mtm, l_vtm = g(b2)
+    torch.cuda.synchronize()
+    assert abs((l_mtm + l_vtm).item() - ls.item()) < 1e-4
+    worst = 0.0
+    for (n, p), (_, q) in zip(m1.named_parameters(), m2.named_parameters()):
+        if p.grad is None:
+            assert q.grad is None or float(q.grad.abs().max()) == 0.0, n
+            continue
+        e = ((p.grad - q.grad).norm() / (p.grad.norm() + 1e-3 * 65536)).item()   # grads carry the 65536 loss scale
+        worst = max(worst, e)
+        assert e < 1e-3, (n, e)
+    print("worst relative gradient difference eager vs graph:", worst)
+    a1.optzr.zero_grad()
+    # 2) three optimizer steps: same loss trajectory
     for it in range(3):
         np.random.seed(10 + it)
         r1 = a1.step(dict(b1), True)
         np.random.seed(10 + it)
         r2 = a2.step(dict(b2), True)
-        assert abs(r1["mtm"] - r2["mtm"]) < 2e-3 and abs(r1["vtm"] - r2["vtm"]) < 2e-3, (it, r1, r2)
-    worst = 0.0
-    for (n, p), (_, q) in zip(m1.named_parameters(), m2.named_parameters()):
-        d = (p - q).abs().max().item()
-        worst = max(worst, d)
-        assert d < 5e-3, (n, d)      # three AdamW steps at lr 1e-3: any wrong gradient sign moves a weight by ~3e-3
-    print("max weight difference eager vs graph after 3 steps:", worst)
-    assert a2.graphs is not None and len(a2.graphs.graphs) == 1
+        assert abs(r1["mtm"] - r2["mtm"]) < 5e-3 and abs(r1["vtm"] - r2["vtm"]) < 5e-3, (it, r1, r2)
+    assert len(a2.graphs.graphs) == 1

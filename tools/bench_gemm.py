@@ -41,17 +41,25 @@ def main():
         ("swin_s2_fc1_dgrad", 7840, 512, 2048, "dgrad"), ("swin_s2_fc1_wgrad", 2048, 512, 7840, "wgrad"),
         ("swin_s0_qkv_wgrad", 384, 128, 125440, "wgrad"), ("bert_ffn1_wgrad", 3072, 768, 9056, "wgrad"),
     ]
+    shapes += [("swin_s2_fc2_dgrad_gelu", 7840, 2048, 512, "dgrad_gelu"), ("swin_s2_proj_res", 7840, 512, 512, "res")]
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]
+    if only:
+        shapes = [s_ for s_ in shapes if s_[0] in only]
     for tag, M, N, K, mode in shapes:
         if mode == "wgrad":
             a = torch.randn(K, M, device="cuda").half()
             b = torch.randn(K, N, device="cuda").half()
             out = torch.zeros(M, N, device="cuda")
             fn = lambda: ops.gemm(a, b, out, M=M, N=N, K=K, a_major=1, b_major=1, accumulate=True)
-        elif mode == "dgrad":
+        elif mode in ("dgrad", "dgrad_gelu"):
             a = torch.randn(M, K, device="cuda").half()
             b = torch.randn(K, N, device="cuda").half()
             out = torch.zeros(M, N, device="cuda").half()
-            fn = lambda: ops.gemm(a, b, out, M=M, N=N, K=K, b_major=1)
+            if mode == "dgrad":
+                fn = lambda: ops.gemm(a, b, out, M=M, N=N, K=K, b_major=1)
+            else:
+                aux = torch.randn(M, N, device="cuda").half()
+                fn = lambda: ops.gemm(a, b, out, M=M, N=N, K=K, b_major=1, act=L.ACT_GELU_BWD, aux=aux)
         else:
             a = torch.randn(M, K, device="cuda").half()
             b = torch.randn(N, K, device="cuda").half()
@@ -75,7 +83,7 @@ def main():
         # torch (cuBLAS) for comparison on the plain product
         if mode == "wgrad":
             ms_t = timeit(lambda: torch.matmul(a.t(), b), flush=flush)
-        elif mode == "dgrad":
+        elif mode in ("dgrad", "dgrad_gelu"):
             ms_t = timeit(lambda: torch.matmul(a, b), flush=flush)
         else:
             ms_t = timeit(lambda: torch.matmul(a, b.t()), flush=flush)
