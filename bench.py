@@ -269,7 +269,8 @@ def run_native(a):
         "vs_baseline": None, "dtype": "f16 operands, f32 accumulate/statistics/residual/master weights",
         "data": "synthetic (seeded randn frames, random token ids, random-init weights)",
         "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "params": nparams,
-                   "parallelism": f"dp{world}", "step": "fwd(MLM+VTM) + 2xCE + bwd + grad all-reduce + clip + AdamW",
+                   "parallelism": f"dp{world}", "step": "fwd(MLM+VTM) + 2xCE + bwd + grad all-reduce + clip + AdamW"
+                   + (" (fused flat-arena kernels)" if agent.fused else " (torch foreach)"),
                    "l2": "working set (activations > 10 GB/step) far exceeds the 126 MB L2; no explicit flush",
                    "drop_path": "active (rate linspace(0,0.2))",
                    "bert_dropout": "identity" if a.eval_dropout else "active (p=0.1)",

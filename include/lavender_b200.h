@@ -197,6 +197,21 @@ int lav_xent_bwd(const float* logits, int64_t ld, const int64_t* labels, int row
                  const float* row_lse, const float* gout, const float* count, float* d32, int64_t ldd32, void* d16,
                  int64_t ldd16, void* stream);
 
+/* ---- fused optimizer step on the flat arena ----------------------------------------
+ * Device-side restatement of Agent_Base.backward_step (agent.py:240-250): GradScaler.unscale_ with the inf check,
+ * clip_grad_norm_(max_grad_norm), AdamW (agent.py:137-139: betas (0.9, 0.98), decoupled weight decay, per-group lr /
+ * weight decay from the name rules of agent.py:98-119) and GradScaler.update, without a host round trip.
+ * `state` is a caller-owned fp32[16] device array: [0] loss scale, [1] growth tracker, [2] optimizer step count,
+ * [3] sum of squares and [4] non-finite count of the (scaled) gradient — both accumulated by lav_grad_stats and
+ * cleared by lav_adamw_step —, [5] unscaled gradient norm (out), [6] found_inf (out), [7..9] internal. */
+int lav_grad_stats(const float* grad, int64_t n, float* state, void* stream);
+/* group_of_block[i] = parameter group (0..ngroups-1) of elements [8i, 8i+8), 255 = no gradient (skipped);
+ * group_lr / group_wd are fp32 device arrays indexed by group.  The update is skipped when found_inf. */
+int lav_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                   const uint8_t* group_of_block, const float* group_lr, const float* group_wd, float beta1, float beta2,
+                   float eps, float max_grad_norm, float* state, float growth_factor, float backoff_factor,
+                   int growth_interval, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

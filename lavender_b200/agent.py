@@ -79,9 +79,16 @@ class Agent_Base:
     def __init__(self, args, model):
         self.args, self.model = args, model
         self.loss_func = CrossEntropyLoss(ignore_index=-1)
+        # fused flat-arena optimizer (optim.py) unless args.fused_optimizer is False or the model has no arena
+        self.fused = bool(getattr(args, "fused_optimizer", True)) and hasattr(model, "arena") and \
+            next(model.parameters()).is_cuda
+        if self.fused:
+            from .optim import DeviceGradScaler
+            self.scaler = DeviceGradScaler(next(model.parameters()).device)
+        else:
+            self.scaler = torch.amp.GradScaler("cuda", enabled=torch.cuda.is_available())
         self.optzr = self.build_optimizer()
         self.lr_scheduler = WarmupLinearLR(self.optzr, args.max_iter)
-        self.scaler = torch.amp.GradScaler("cuda", enabled=torch.cuda.is_available())
         self.log = None
         self.grad_sync = None
         self.graphs = None  # graph.GraphCache when args.cuda_graph
@@ -107,6 +114,10 @@ class Agent_Base:
                 {"params": groups[(True, False)], "weight_decay": wd},
                 {"params": groups[(False, True)], "weight_decay": 0.0, "lr": lr * mul},
                 {"params": groups[(False, False)], "weight_decay": 0.0}]
+        if getattr(self, "fused", False):
+            from .optim import FlatAdamW
+            return FlatAdamW(spec, self.model.arena(), self.scaler, lr=lr, betas=(0.9, 0.98), weight_decay=wd,
+                             max_grad_norm=self.args.max_grad_norm)
         return torch.optim.AdamW(spec, lr=lr, betas=(0.9, 0.98), weight_decay=wd)
 
     # ---- metrics / checkpoints -------------------------------------------------------------------------
@@ -167,7 +178,7 @@ class Agent_Base:
             self.grad_sync.finish()
         elif hasattr(self.model, "arena"):
             self.model.arena().finalize_grads()
-        if self.args.max_grad_norm > 0:
+        if self.args.max_grad_norm > 0 and not self.fused:     # the fused optimizer clips inside its own kernels
             self.scaler.unscale_(self.optzr)
             torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.args.max_grad_norm)
         self.scaler.step(self.optzr)

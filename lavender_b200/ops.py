@@ -244,3 +244,21 @@ def xent_bwd(logits, labels, ignore_index, row_lse, gout, count, d32=None, d16=N
                                   _p(count), _p(d32), d32.stride(0) if d32 is not None else 0, _p(d16),
                                   d16.stride(0) if d16 is not None else 0, _stream())
     L.check(rc, "lav_xent_bwd")
+
+
+def grad_stats(grad, state):
+    assert grad.dtype == torch.float32 and grad.is_contiguous() and state.dtype == torch.float32
+    with _Timed("optimizer"):
+        rc = L.lib().lav_grad_stats(_p(grad), grad.numel(), _p(state), _stream())
+    L.check(rc, "lav_grad_stats")
+
+
+def adamw_step(param, grad, exp_avg, exp_avg_sq, group_of_block, group_lr, group_wd, state, *, beta1, beta2, eps,
+               max_grad_norm, growth_factor=2.0, backoff_factor=0.5, growth_interval=2000):
+    n = param.numel()
+    assert grad.numel() == n and exp_avg.numel() == n and exp_avg_sq.numel() == n and group_of_block.numel() * 8 == n
+    with _Timed("optimizer"):
+        rc = L.lib().lav_adamw_step(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), n, _p(group_of_block), _p(group_lr),
+                                    _p(group_wd), beta1, beta2, eps, max_grad_norm, _p(state), growth_factor,
+                                    backoff_factor, growth_interval, _stream())
+    L.check(rc, "lav_adamw_step")
