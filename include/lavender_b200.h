@@ -42,6 +42,28 @@ int64_t lav_launch_count(void);
 /* queries device 0..n: fills sm_count; returns LAV_E_NO_DEVICE when no sm_100 device is present */
 int lav_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
 
+/* ---- dropout ---------------------------------------------------------------------------------------
+ * HF BERT's nn.Dropout sites (hidden_dropout_prob / attention_probs_dropout_prob = 0.1, active in train() mode as
+ * Agent_Pretrain_MLM.step runs it, main_pretrain_mlm.py:147) are folded into the kernels that produce the dropped
+ * tensor.  A mask bit is a pure function of (rng[0] = seed, rng[1] = step, site, row, column[, head]) — Philox-4x32-7,
+ * 16 random bits per element — so backward kernels regenerate it and nothing mask-shaped is stored.  `rng` is a
+ * DEVICE pointer (two uint64), read when the kernel runs: a CUDA-graph replay sees the step counter the host (or a
+ * captured increment) wrote before it.  p == 0 or a NULL struct disables the site.  Kept elements are scaled by
+ * 1 / (1 - round(p * 65536) / 65536). */
+typedef struct LavDropout {
+  const uint64_t* rng;     /* device: [seed, step]                                                        */
+  uint32_t site;           /* distinct per dropout call site (and per call of the same module in a step)  */
+  float p;                 /* drop probability                                                            */
+} LavDropout;
+
+/* out[r, c] = x[r, c] * keep(r, c) / (1 - p)  on fp32 [rows, C] (C % 8 == 0; in place allowed).  BertEmbeddings.dropout
+ * forward, and its backward on the incoming gradient. */
+int lav_dropout_f32(const float* x, int64_t ldx, float* out, int64_t ldo, int rows, int C, const LavDropout* drop,
+                    void* stream);
+/* Test helper: keep[r, c] (uint8 0/1) of the elementwise sites (head < 0: index (r, c)) or of the attention
+ * probabilities of head `head` (index (query row r, key column c, head)). */
+int lav_dropout_mask(uint8_t* keep, int rows, int C, int head, const LavDropout* drop, void* stream);
+
 /* ---- GEMM (tcgen05 + TMA) -------------------------------------------------------------------------
  * D[M,N] = epilogue( alpha * sum_k A(m,k) * B(n,k) )
  * Replaces every nn.Linear / Conv3d-as-GEMM call on the path: video_swin.py:74,77 (Mlp), :147,168
@@ -84,6 +106,8 @@ typedef struct LavGemmEpilogue {
   float alpha;
   int32_t accumulate;      /* LAV_STORE / LAV_ACCUMULATE                                                  */
   int32_t reserved;
+  LavDropout drop;         /* dropout of (value + bias) before row_scale / residual (BertSelfOutput / BertOutput
+                              .dropout, element index = (GEMM row, column)); drop.p == 0 disables           */
 } LavGemmEpilogue;
 
 int lav_gemm_f16(const void* A, int64_t lda, int a_major, const void* B, int64_t ldb, int b_major, int M, int N,
@@ -107,7 +131,11 @@ int lav_layernorm_fwd(const float* x, int64_t ldx, const int32_t* row_map, int G
 int lav_layernorm_bwd(const void* dy, int64_t lddy, int dy_is_f32, const float* x, int64_t ldx,
                       const int32_t* row_map, int G, int C, const float* gamma, const float* mean,
                       const float* rstd, const float* add32, int64_t ldadd, float* dx32, int64_t lddx32,
-                      void* dx16, int64_t lddx16, float* dgamma, float* dbeta, int rows, void* stream);
+                      void* dx16, int64_t lddx16, float* dgamma, float* dbeta, int rows, const LavDropout* drop16,
+                      void* stream);
+/* drop16 (may be NULL): dx16 is additionally multiplied by the dropout mask of site drop16 at (r, column) — the
+ * gradient entering a dense layer whose output was dropped in the forward epilogue — while dx32 stays unmasked
+ * (the residual path). */
 
 /* out16[r, 0:C] = fp16( alpha * row_scale[r / rows_per_scale] * x[row_map[r], 0:C] )
  * (gradient gather for window-major GEMM operands; DropPath scale of video_swin.py:46-54 in backward). */
@@ -137,7 +165,9 @@ int lav_colsum_f16(const void* x16, int64_t ld, int rows, int N, float* out, flo
 int lav_attn_fwd_f16(const void* qkv, int64_t ld, int64_t rows_total, int q_off, int k_off, int v_off, int head_dim,
                      int nheads, int nprob, int L, float scale, const void* bias16, int NPb,
                      const int32_t* prob_class, int class_period, const float* key_bias, void* out16, int64_t ldo,
-                     float* lse, void* stream);
+                     float* lse, const LavDropout* drop, void* stream);
+/* drop (may be NULL): dropout of the attention probabilities (HF BertSelfAttention.dropout), element index
+ * (global query row, key column, head); lse is that of the un-dropped softmax. */
 
 /* Backward of the above.  dq_acc: fp32 [rows_total, nheads*head_dim], zeroed by the caller (dQ is reduced
  * over key chunks with atomics); dK and dV are written as fp16 into dqkv16 at k_off / v_off.  When ds16 is
@@ -147,7 +177,8 @@ int lav_attn_bwd_f16(const void* qkv, int64_t ld, int64_t rows_total, int q_off,
                      int nheads, int nprob, int L, float scale, const void* bias16, int NPb,
                      const int32_t* prob_class, int class_period, const float* key_bias, int NPk,
                      const void* out16, int64_t ldo, const void* dout16, int64_t lddo, const float* lse,
-                     float* dq_acc, int64_t lddq, void* dqkv16, int64_t lddqkv, void* ds16, int NPs, void* stream);
+                     float* dq_acc, int64_t lddq, void* dqkv16, int64_t lddqkv, void* ds16, int NPs,
+                     const LavDropout* drop, void* stream);
 
 /* dense16[cls][h][i][j] = table[rel_index[i*L+j]][h] + (labels[cls][i] != labels[cls][j] ? -100 : 0), -inf for
  * j >= L (video_swin.py:153-160 and compute_mask :290-305); labels may be NULL (unshifted block, ncls = 1). */

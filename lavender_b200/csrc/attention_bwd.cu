@@ -7,6 +7,7 @@
 // dQ_t is reduced over the key chunks with fp32 atomics into `dq_acc`; dK/dV are written once as fp16.
 // For the Swin relative-position bias the per-window dS is also written out (fp16) and reduced over windows by
 // relpos_bias_grad_kernel (autograd's index_put of video_swin.py:153 in the reference).
+#include "rng.cuh"
 #include "runtime.h"
 #include "sm100.cuh"
 
@@ -27,6 +28,7 @@ struct AttnBwdParams {
   float* dq_acc; int64_t lddq;              // fp32 [rows_total, nheads*HD], pre-zeroed
   __half* dqkv; int64_t lddqkv;             // dK / dV written at k_off / v_off
   __half* ds_out; int NPs;                  // optional [nprob][nheads][NPs][NPs]
+  DropParams drop;                          // attention-probability dropout of the forward (regenerated here)
 };
 
 template <int HD>
@@ -140,6 +142,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const float* kb = p.key_bias ? p.key_bias + (size_t)prob * p.NPk + c * 128 : nullptr;
     uint8_t* prow = smem + Cfg::OFF_P + i * 128;
     uint8_t* dsrow = smem + Cfg::OFF_DS + i * 128;
+    DropKey dkey{};
+    if (p.drop.on) dkey = drop_key(p.drop);
 
     for (int t = 0; t < nqt; ++t) {
       const int qi = t * 128 + i;
@@ -192,11 +196,27 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 32; ++j) pv[j] += __ldg(kb + j0 + j) * 1.4426950408889634f;
         }
+        if (!p.drop.on) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float pe = valid ? exp2f(pv[j]) : 0.f;
-          pv[j] = pe;
-          dsv[j] = pe * (__uint_as_float(dp[j]) - delta);
+          for (int j = 0; j < 32; ++j) {
+            const float pe = valid ? exp2f(pv[j]) : 0.f;
+            pv[j] = pe;
+            dsv[j] = pe * (__uint_as_float(dp[j]) - delta);
+          }
+        } else {  // O = (keep * P / (1-p)) V: dV uses the dropped P, dP = keep * dP_drop / (1-p), dS = P (dP - delta)
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            const uint32_t m = drop_keep8(dkey, p.drop.thresh, (uint32_t)(row0 + qi), (uint32_t)(((c * 128 + j0) >> 3) + j8),
+                                          (uint32_t)h);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int j = 8 * j8 + q;
+              const float pe = valid ? exp2f(pv[j]) : 0.f;
+              const float kc = ((m >> q) & 1u) ? p.drop.inv_keep : 0.f;
+              pv[j] = pe * kc;
+              dsv[j] = pe * (kc * __uint_as_float(dp[j]) - delta);
+            }
+          }
         }
         uint8_t* pa = prow + (j0 >> 6) * 16384;
         uint8_t* da = dsrow + (j0 >> 6) * 16384;
@@ -324,7 +344,7 @@ extern "C" int lav_attn_bwd_f16(const void* qkv, int64_t ld, int64_t rows_total,
                                 const int32_t* prob_class, int class_period, const float* key_bias, int NPk,
                                 const void* out16, int64_t ldo, const void* dout16, int64_t lddo, const float* lse,
                                 float* dq_acc, int64_t lddq, void* dqkv16, int64_t lddqkv, void* ds16, int NPs,
-                                void* stream) {
+                                const LavDropout* drop, void* stream) {
   LAV_REQUIRE(qkv && out16 && dout16 && lse && dq_acc && dqkv16, "lav_attn_bwd_f16: null pointer");
   LAV_REQUIRE(nprob > 0 && nheads > 0 && L > 0, "lav_attn_bwd_f16: empty problem");
   LAV_REQUIRE((ldo % 8) == 0 && (lddo % 8) == 0 && (lddqkv % 8) == 0 && (q_off % 8) == 0 && (k_off % 8) == 0 &&
@@ -340,6 +360,7 @@ extern "C" int lav_attn_bwd_f16(const void* qkv, int64_t ld, int64_t rows_total,
   p.key_bias = key_bias, p.NPk = NPk, p.out = (const __half*)out16, p.ldo = ldo, p.dout = (const __half*)dout16;
   p.lddo = lddo, p.lse = lse, p.rows_total = rows_total, p.dq_acc = dq_acc, p.lddq = lddq;
   p.dqkv = (__half*)dqkv16, p.lddqkv = lddqkv, p.ds_out = (__half*)ds16, p.NPs = NPs;
+  p.drop = make_drop(drop);
   cudaStream_t s = (cudaStream_t)stream;
   return head_dim == 32 ? launch_attn_bwd<32>(qkv, ld, p, nkc, s) : launch_attn_bwd<64>(qkv, ld, p, nkc, s);
 }

@@ -8,6 +8,7 @@
 //   * relative-position bias + shift mask (+ -inf on the padded key columns) come pre-expanded as a dense fp16
 //     [class][head][NP][NP] tensor (lav_relpos_bias_expand); BERT passes an additive per-key fp32 row instead.
 // Nothing of size [B_, nh, N, N] ever reaches HBM.
+#include "rng.cuh"
 #include "runtime.h"
 #include "sm100.cuh"
 
@@ -24,6 +25,7 @@ struct AttnFwdParams {
   const float* key_bias;                   // [nprob][NKC*128] additive (0 / -inf) or null
   __half* out; int64_t ldo;
   float* lse; int64_t rows_total;
+  DropParams drop;                         // attention-probability dropout (BERT, train mode)
 };
 
 template <int HD, int NKC>
@@ -116,6 +118,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
       brow = p.bias16 + (((size_t)cls * p.nheads + h) * p.NPb + min(qi, p.NPb - 1)) * p.NPb;
     }
     const float* kb = p.key_bias ? p.key_bias + (size_t)prob * NP : nullptr;
+    DropKey dkey{};
+    if (p.drop.on) dkey = drop_key(p.drop);
 
     auto biased = [&](const uint32_t(&s)[32], int j0, float(&v)[32]) {
 #pragma unroll
@@ -169,6 +173,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
       for (int j = 0; j < 32; ++j) {
         v[j] = exp2f(v[j] * 1.4426950408889634f - mlog);
         l += v[j];
+      }
+      if (p.drop.on) {  // P -> keep * P / (1 - p); the normaliser l stays that of the un-dropped softmax
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t m = drop_keep8(dkey, p.drop.thresh, (uint32_t)(row0 + qi), (uint32_t)((j0 >> 3) + j), (uint32_t)h);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[8 * j + q] = ((m >> q) & 1u) ? v[8 * j + q] * p.drop.inv_keep : 0.f;
+        }
       }
       // P (fp16) -> smem, K-major 128B-swizzle atoms of [128 rows x 64 keys]
       uint8_t* atom = prow + (j0 >> 6) * 16384;
@@ -259,7 +271,7 @@ using namespace lav;
 extern "C" int lav_attn_fwd_f16(const void* qkv, int64_t ld, int64_t rows_total, int q_off, int k_off, int v_off,
                                 int head_dim, int nheads, int nprob, int L, float scale, const void* bias16, int NPb,
                                 const int32_t* prob_class, int class_period, const float* key_bias, void* out16,
-                                int64_t ldo, float* lse, void* stream) {
+                                int64_t ldo, float* lse, const LavDropout* drop, void* stream) {
   LAV_REQUIRE(qkv && out16, "lav_attn_fwd_f16: null pointer");
   LAV_REQUIRE(nprob > 0 && nheads > 0 && L > 0, "lav_attn_fwd_f16: empty problem");
   LAV_REQUIRE((ldo % 8) == 0 && (q_off % 8) == 0 && (k_off % 8) == 0 && (v_off % 8) == 0,
@@ -269,6 +281,7 @@ extern "C" int lav_attn_fwd_f16(const void* qkv, int64_t ld, int64_t rows_total,
   p.q_off = q_off, p.k_off = k_off, p.v_off = v_off, p.scale = scale;
   p.bias16 = (const __half*)bias16, p.NPb = NPb, p.prob_class = prob_class, p.period = class_period > 0 ? class_period : 1;
   p.key_bias = key_bias, p.out = (__half*)out16, p.ldo = ldo, p.lse = lse, p.rows_total = rows_total;
+  p.drop = make_drop(drop);
   cudaStream_t s = (cudaStream_t)stream;
   if (head_dim == 32 && L <= 256) {
     LAV_REQUIRE(!bias16 || NPb == 256, "lav_attn_fwd_f16: dense bias must be [*, *, 256, 256] for L <= 256");

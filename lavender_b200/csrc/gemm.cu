@@ -5,7 +5,9 @@
 // Both operands may be K-major or MN-major (UMMA descriptor bit), which gives forward (K,K), dgrad (K,MN)
 // and wgrad (MN,MN; split-K with fp32 atomics) from one kernel without transposed copies.
 #include <algorithm>
+#include <cstdlib>
 
+#include "rng.cuh"
 #include "runtime.h"
 #include "sm100.cuh"
 
@@ -17,15 +19,33 @@ constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = 128 + kEpiWarps * 32;
 constexpr int kEpiStride = 36;  // floats per staged accumulator row: 16-byte aligned, conflict-free for 128-bit access
 
-template <int BN>
+// Persistent work streams: one CTA per SM, or one CTA pair per TPC.  The pair path (LAV_GEMM_PAIR=1) is correct and
+// wins on large square problems (8192^3: 1342 vs 1150 TFLOP/s) but not on the hot path's shapes, whose cost is the
+// epilogue and the per-launch prologue rather than the operand feed (profiles/r1d_gemm_sweep.md), so it is opt-in.
+static int work_streams(int ncta) { return ncta == 2 ? std::max(1, sm_count() / 2) : sm_count(); }
+static bool pair_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LAV_GEMM_PAIR");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+// NCTA = 2: a CTA pair (cluster of two on one TPC) owns a 256 x BN tile and issues cta_group::2 MMAs; each CTA stages
+// its own 128 rows of A and its own BN/2 rows of B, so the L2 -> smem traffic and the smem footprint per FLOP halve
+// for B and the ring is deep enough (5 x 32 KB at BN = 256) to cover the TMA latency.
+template <int BN, int NCTA>
 struct GemmCfg {
+  static constexpr int BNL = BN / NCTA;  // rows of B staged by one CTA
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = BNL * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_BYTES = kEpiWarps * kEpiStride * 32 * 4;  // per-warp 32x32 fp32 transpose buffers
   static constexpr int BAR_BYTES = 256;
   static constexpr int STAGES_MAX = (232448 - 1024 - BAR_BYTES - EPI_BYTES) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_MAX > 6 ? 6 : STAGES_MAX;  // 3 / 5 / 6 for BN = 256 / 128 / 64
+  static constexpr int STAGES_CAP = NCTA == 2 ? 8 : 6;
+  static constexpr int STAGES = STAGES_MAX > STAGES_CAP ? STAGES_CAP : STAGES_MAX;  // 1-CTA: 3 / 5 / 6 for BN = 256 / 128 / 64
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
   static constexpr int TMEM_COLS = 2 * BN;                                    // 2 accumulator stages
   static constexpr int TMEM_ALLOC = TMEM_COLS <= 128 ? 128 : TMEM_COLS <= 256 ? 256 : 512;  // power of 2
@@ -33,7 +53,9 @@ struct GemmCfg {
 
 struct GemmParams {
   int M, N, K;
-  int m_blocks, n_blocks, k_blocks, splits, kb_per_split;
+  int m_blocks, n_blocks, k_blocks, splits, kb_per_split;  // m_blocks counts tiles of BM * NCTA rows
+  DropParams drop;  // resolved from epi.drop
+  int debug;  // LAV_GEMM_DEBUG (profiling only): bit 0 = epilogue drains without math / stores, bit 1 = no MMA issue
   LavGemmEpilogue epi;
 };
 
@@ -154,9 +176,10 @@ __device__ __forceinline__ void store_aux_phase(const GemmParams& p, const float
 // Body of the 8 epilogue warps (two warpgroups, one per TMEM accumulator stage), specialised at compile time on the
 // activation, on whether a global input is prefetched (PRE: residual rows) and on the store mode: the epilogue is
 // instruction-issue bound for the short-K GEMMs of the Swin stages, so unused paths must not cost instructions.
-template <int BN, int ACT, int PRE, int STORE>
+template <int BN, int NCTA, int ACT, int PRE, int STORE, bool DROP = false>
 __device__ __forceinline__ void epilogue_warps(const GemmParams& p, float* epi_stage, uint64_t* tmem_full,
-                                               uint64_t* tmem_empty, uint32_t tmem_base, int warp, int lane, int total) {
+                                               uint64_t* tmem_empty, uint32_t tmem_base, int warp, int lane, int total,
+                                               int stream_id, int nstreams, int rank) {
   const int wg = (warp - 4) >> 2;
   const int q = warp & 3;  // TMEM lane quarter this warp may access
   float* stg = epi_stage + (warp - 4) * (kEpiStride * 32);
@@ -165,11 +188,13 @@ __device__ __forceinline__ void epilogue_warps(const GemmParams& p, float* epi_s
   constexpr bool use_res = PRE == 1;
   constexpr bool use_auxin = ACT == LAV_ACT_GELU_BWD;
   constexpr bool use_pre = use_res || use_auxin;
+  DropKey dkey{};
+  if (DROP) dkey = drop_key(p.drop);
   int iter = 0;
-  for (int item = blockIdx.x; item < total; item += gridDim.x, ++iter) {
+  for (int item = stream_id; item < total; item += nstreams, ++iter) {
     if ((iter & 1) != wg) continue;
     const TileCoord t = decode_tile(p, item);
-    const int row_base = t.m_blk * BM + q * 32;
+    const int row_base = (t.m_blk * NCTA + rank) * BM + q * 32;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + wg * BN;
     const int nchunks = min(BN / 32, (p.N - t.n_blk * BN + 31) / 32);
     // output rows of this lane's 8 store-phase rows (row map resolved once per tile)
@@ -214,6 +239,12 @@ __device__ __forceinline__ void epilogue_warps(const GemmParams& p, float* epi_s
     if (use_pre) prefetch(cur, 0);
     mbar_wait(tmem_full + wg, (iter >> 1) & 1, 4);
     tc_fence_after();
+    if (p.debug & 1) {
+      tc_fence_before();
+      if (NCTA == 2) mbar_arrive_cluster(tmem_empty + wg, 0);
+      else mbar_arrive(tmem_empty + wg);
+      continue;
+    }
 #pragma unroll 1
     for (int c = 0; c < nchunks; ++c) {
       const int col0 = t.n_blk * BN + c * 32;
@@ -224,7 +255,8 @@ __device__ __forceinline__ void epilogue_warps(const GemmParams& p, float* epi_s
       tmem_ld_wait();
       if (c == nchunks - 1) {  // accumulator fully read: hand the TMEM stage back to the MMA warp early
         tc_fence_before();
-        mbar_arrive(tmem_empty + wg);
+        if (NCTA == 2) mbar_arrive_cluster(tmem_empty + wg, 0);  // the leader's MMA warp waits for both CTAs
+        else mbar_arrive(tmem_empty + wg);
       }
       float v[32];
 #pragma unroll
@@ -268,6 +300,14 @@ __device__ __forceinline__ void epilogue_warps(const GemmParams& p, float* epi_s
         }
         __syncwarp();
       }
+      if (DROP) {  // BertSelfOutput / BertOutput .dropout on (dense + bias), element index (GEMM row, column)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t m = drop_keep8(dkey, p.drop.thresh, (uint32_t)(row_base + lane), (uint32_t)((col0 >> 3) + j), 0u);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[8 * j + q] = ((m >> q) & 1u) ? v[8 * j + q] * p.drop.inv_keep : 0.f;
+        }
+      }
       if (e.row_scale) {
         const int row = min(row_base + lane, p.M - 1);
         const float sc = __ldg(e.row_scale + row / e.rows_per_scale);
@@ -286,12 +326,14 @@ __device__ __forceinline__ void epilogue_warps(const GemmParams& p, float* epi_s
   }
 }
 
-template <int BN, int AMAJ, int BMAJ>
+template <int BN, int AMAJ, int BMAJ, int NCTA>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, NCTA>;
+  constexpr int BNL = Cfg::BNL;
   extern __shared__ uint8_t smem_raw[];
+  // (the dynamic smem window starts at the same offset in both CTAs of a pair, so the aligned offsets match too)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* epi_stage = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
@@ -303,6 +345,9 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int rank = NCTA == 2 ? (int)cluster_ctarank() : 0;          // 0 = leader (issues the MMAs)
+  const int stream_id = NCTA == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;  // persistent work stream of this CTA (pair)
+  const int nstreams = NCTA == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -315,52 +360,61 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tmem_full + s, 1);
-      mbar_init(tmem_empty + s, 128);
+      mbar_init(tmem_empty + s, 128 * NCTA);
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<Cfg::TMEM_ALLOC>(tmem_slot);
+  if (warp == 2) {
+    if (NCTA == 2) tmem_alloc_pair<Cfg::TMEM_ALLOC>(tmem_slot);
+    else tmem_alloc<Cfg::TMEM_ALLOC>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all();  // the peer's barriers must be initialised before any remote arrive / TMA signal
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int total = p.m_blocks * p.n_blocks * p.splits;
 
   if (warp == 0) {
-    // ------------------------------------------------ TMA producer (one lane)
+    // ------------------------------------------------ TMA producer (one lane; in a pair, both CTAs run one)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < total; item += gridDim.x) {
+      for (int item = stream_id; item < total; item += nstreams) {
         const TileCoord t = decode_tile(p, item);
+        const int m0 = (t.m_blk * NCTA + rank) * BM;
+        const int n0 = t.n_blk * BN + rank * BNL;
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
           mbar_wait(empty + stage, phase ^ 1, 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
-          mbar_arrive_expect_tx(full + stage, Cfg::STAGE_BYTES);
+          // the bytes of BOTH CTAs complete on the leader's barrier (the leader's MMA warp is the only consumer)
+          if (rank == 0) mbar_arrive_expect_tx(full + stage, Cfg::STAGE_BYTES * NCTA);
+          auto load = [&](void* dst, const CUtensorMap* m, int c0, int c1) {
+            if (NCTA == 2) tma_load_2d_pair(dst, m, full + stage, c0, c1);
+            else tma_load_2d(dst, m, full + stage, c0, c1);
+          };
           if (AMAJ == LAV_MAJOR_K) {
-            tma_load_2d(sa, &tmA, full + stage, kb * BK, t.m_blk * BM);
+            load(sa, &tmA, kb * BK, m0);
           } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j)
-              tma_load_2d(sa + j * (BK * 128), &tmA, full + stage, t.m_blk * BM + j * 64, kb * BK);
+            for (int j = 0; j < BM / 64; ++j) load(sa + j * (BK * 128), &tmA, m0 + j * 64, kb * BK);
           }
           if (BMAJ == LAV_MAJOR_K) {
-            tma_load_2d(sb, &tmB, full + stage, kb * BK, t.n_blk * BN);
+            load(sb, &tmB, kb * BK, n0);
           } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(sb + j * (BK * 128), &tmB, full + stage, t.n_blk * BN + j * 64, kb * BK);
+            for (int j = 0; j < BNL / 64; ++j) load(sb + j * (BK * 128), &tmB, n0 + j * 64, kb * BK);
           }
           if (++stage == Cfg::STAGES) stage = 0, phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer (one lane)
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(BM, BN, AMAJ, BMAJ);
+    // ------------------------------------------------ MMA issuer (one lane of the leader CTA)
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BM * NCTA, BN, AMAJ, BMAJ);
       // K-major: 8-row atoms are 1024 B apart (SBO); MN-major: 64-element atoms are BK*128 B apart (LBO),
       // 8-k-row groups 1024 B apart (SBO).
       constexpr uint32_t a_lbo = (AMAJ == LAV_MAJOR_K) ? 0 : BK * 128;
@@ -370,7 +424,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
-      for (int item = blockIdx.x; item < total; item += gridDim.x, ++iter) {
+      for (int item = stream_id; item < total; item += nstreams, ++iter) {
         const TileCoord t = decode_tile(p, item);
         const int as = iter & 1;
         mbar_wait(tmem_empty + as, ((iter >> 1) & 1) ^ 1, 2);
@@ -383,12 +437,19 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint32_t sb = sa + Cfg::A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
+            if (p.debug & 2) break;
             const uint64_t ad = make_smem_desc(sa + k * a_kstep, a_lbo, 1024, SWZ_128B);
             const uint64_t bd = make_smem_desc(sb + k * b_kstep, b_lbo, 1024, SWZ_128B);
-            umma_f16_ss(d_tmem, ad, bd, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
+            if (NCTA == 2) umma_f16_ss_pair(d_tmem, ad, bd, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
+            else umma_f16_ss(d_tmem, ad, bd, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(empty + stage);  // frees the smem slot once these MMAs have read it
-          if (kb == t.kb1 - 1) umma_commit(tmem_full + as);
+          // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
+          if (NCTA == 2) umma_commit_pair(empty + stage);
+          else umma_commit(empty + stage);
+          if (kb == t.kb1 - 1) {
+            if (NCTA == 2) umma_commit_pair(tmem_full + as);
+            else umma_commit(tmem_full + as);
+          }
           if (++stage == Cfg::STAGES) stage = 0, phase ^= 1;
         }
       }
@@ -399,7 +460,9 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int st = e.out_dtype == LAV_OUT_F16 ? ST_F16
                    : e.accumulate != LAV_ACCUMULATE ? ST_F32 : (p.splits > 1 ? ST_F32_RED : ST_F32_RMW);
     const int pre = e.residual != nullptr ? 1 : 0;
-#define LAV_EPI(A, P, S) epilogue_warps<BN, A, P, S>(p, epi_stage, tmem_full, tmem_empty, tmem_base, warp, lane, total)
+#define LAV_EPI(A, P, S)                                                                                       \
+  epilogue_warps<BN, NCTA, A, P, S>(p, epi_stage, tmem_full, tmem_empty, tmem_base, warp, lane, total, stream_id, \
+                                    nstreams, rank)
     if (e.act == LAV_ACT_GELU) {
       if (st == ST_F16 && !pre) LAV_EPI(LAV_ACT_GELU, 0, ST_F16);
       else LAV_EPI(LAV_ACT_GELU, 0, ST_F32);               // host restricts GELU to {f16, f32 store} without residual
@@ -411,6 +474,9 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       else if (st == ST_F32) LAV_EPI(LAV_ACT_NONE, 0, ST_F32);
       else if (st == ST_F32_RED) LAV_EPI(LAV_ACT_NONE, 0, ST_F32_RED);
       else LAV_EPI(LAV_ACT_NONE, 0, ST_F32_RMW);
+    } else if (p.drop.on) {  // host restricts dropout to (no activation, residual, fp32 store)
+      epilogue_warps<BN, NCTA, LAV_ACT_NONE, 1, ST_F32, true>(p, epi_stage, tmem_full, tmem_empty, tmem_base, warp, lane,
+                                                              total, stream_id, nstreams, rank);
     } else {
       if (st == ST_F16) LAV_EPI(LAV_ACT_NONE, 1, ST_F16);
       else if (st == ST_F32) LAV_EPI(LAV_ACT_NONE, 1, ST_F32);
@@ -421,13 +487,17 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc<Cfg::TMEM_ALLOC>(tmem_base);
+  if (NCTA == 2) cluster_sync_all();  // neither CTA may exit (or free TMEM) while the peer can still signal it
+  else __syncthreads();
+  if (warp == 2) {
+    if (NCTA == 2) tmem_dealloc_pair<Cfg::TMEM_ALLOC>(tmem_base);
+    else tmem_dealloc<Cfg::TMEM_ALLOC>(tmem_base);
+  }
 }
 
-template <int BN, int AMAJ, int BMAJ>
+template <int BN, int AMAJ, int BMAJ, int NCTA>
 static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, NCTA>;
   CUtensorMap tmA, tmB;
   int rc;
   if (AMAJ == LAV_MAJOR_K)
@@ -436,31 +506,40 @@ static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, G
     rc = encode_tmap_2d_f16(&tmA, A, p.K, p.M, lda, BK, 64, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   if (BMAJ == LAV_MAJOR_K)
-    rc = encode_tmap_2d_f16(&tmB, B, p.N, p.K, ldb, BN, BK, CU_TENSOR_MAP_SWIZZLE_128B);
+    rc = encode_tmap_2d_f16(&tmB, B, p.N, p.K, ldb, Cfg::BNL, BK, CU_TENSOR_MAP_SWIZZLE_128B);
   else
     rc = encode_tmap_2d_f16(&tmB, B, p.K, p.N, ldb, BK, 64, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   p.n_blocks = (p.N + BN - 1) / BN;
-  auto kern = gemm_f16_kernel<BN, AMAJ, BMAJ>;
+  auto kern = gemm_f16_kernel<BN, AMAJ, BMAJ, NCTA>;
   static bool attr_set = false;
   if (!attr_set) {
     LAV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int total = p.m_blocks * p.n_blocks * p.splits;
-  const int grid = std::min(total, sm_count());
-  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
-  LAV_CHECK_CUDA(cudaGetLastError());
+  const int streams = std::min(total, work_streams(NCTA));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(streams * NCTA);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NCTA, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = NCTA == 2 ? 1 : 0;
+  LAV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
   count_launch();
   return LAV_OK;
 }
 
-template <int BN>
+template <int BN, int NCTA>
 static int dispatch_major(const void* A, int64_t lda, int a_major, const void* B, int64_t ldb, int b_major,
                           GemmParams& p, cudaStream_t s) {
-  if (a_major == LAV_MAJOR_K && b_major == LAV_MAJOR_K) return launch_gemm<BN, 0, 0>(A, lda, B, ldb, p, s);
-  if (a_major == LAV_MAJOR_K && b_major == LAV_MAJOR_MN) return launch_gemm<BN, 0, 1>(A, lda, B, ldb, p, s);
-  if (a_major == LAV_MAJOR_MN && b_major == LAV_MAJOR_MN) return launch_gemm<BN, 1, 1>(A, lda, B, ldb, p, s);
+  if (a_major == LAV_MAJOR_K && b_major == LAV_MAJOR_K) return launch_gemm<BN, 0, 0, NCTA>(A, lda, B, ldb, p, s);
+  if (a_major == LAV_MAJOR_K && b_major == LAV_MAJOR_MN) return launch_gemm<BN, 0, 1, NCTA>(A, lda, B, ldb, p, s);
+  if (a_major == LAV_MAJOR_MN && b_major == LAV_MAJOR_MN) return launch_gemm<BN, 1, 1, NCTA>(A, lda, B, ldb, p, s);
   return set_error(LAV_E_INVALID, "lav_gemm_f16: (A MN-major, B K-major) is not instantiated (no caller on the hot path)");
 }
 
@@ -480,27 +559,42 @@ extern "C" int lav_gemm_f16(const void* A, int64_t lda, int a_major, const void*
   LAV_REQUIRE(!(epi->act != LAV_ACT_NONE && epi->accumulate == LAV_ACCUMULATE), "lav_gemm_f16: activations cannot accumulate");
   GemmParams p;
   p.M = M, p.N = N, p.K = K;
-  p.m_blocks = (M + BM - 1) / BM;
   p.k_blocks = (K + BK - 1) / BK;
   p.epi = *epi;
-  // Tile width BN in {64,128,192,256} and split-K factor chosen by a small cost model (SM clocks):
-  //   per k-block  max(MMA issue 2*BN, operand feed (BM+BN)*BK*2 bytes at ~110 B/clk/SM), times the number of
-  //   waves over the SMs, plus one exposed epilogue (atomics cost more).
-  const int nsm = sm_count();
+  p.drop = make_drop(&epi->drop);
+  LAV_REQUIRE(!p.drop.on || (epi->act == LAV_ACT_NONE && epi->residual && epi->out_dtype == LAV_OUT_F32 &&
+                             epi->accumulate != LAV_ACCUMULATE),
+              "lav_gemm_f16: epilogue dropout needs (no activation, residual, fp32 store)");
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("LAV_GEMM_DEBUG");
+      dbg = e ? atoi(e) : 0;
+    }
+    p.debug = dbg;
+  }
+  // CTA pairs (256-row tiles, cta_group::2) whenever the problem has more than one 128-row block.
+  const int ncta = (pair_enabled() && M > BM) ? 2 : 1;
+  p.m_blocks = (M + BM * ncta - 1) / (BM * ncta);
+  // Tile width BN and split-K factor chosen by a small cost model (SM clocks):
+  //   per k-block  max(MMA issue 2*BN, operand feed (BM + BN/ncta)*BK*2 bytes at ~110 B/clk/SM), times the number of
+  //   waves over the work streams, plus one exposed epilogue (atomics cost more).
+  const int nstr = work_streams(ncta);
   const bool may_split = split_k != 1 && epi->accumulate == LAV_ACCUMULATE && epi->act == LAV_ACT_NONE;
   int bn = 128, splits = 1;
   double best = 1e30;
   const int cands[4] = {256, 192, 128, 64};
   for (int ci = 0; ci < 4; ++ci) {
     const int c = cands[ci];
-    if (c > 64 && c >= 2 * ((N + 63) / 64 * 64)) continue;  // far wider than the problem
+    if (ncta == 2 && c != 256 && c != 128) continue;        // pair tiles: B halves must be whole 64-row atoms
+    if (c > 64 && c >= 2 * ((N + 63) / 64 * 64) && !(ncta == 2 && c == 128)) continue;  // far wider than the problem
     const int tiles = p.m_blocks * ((N + c - 1) / c);
-    const double kb_clk = std::max(2.0 * c, (BM + c) * BK * 2 / 110.0);
+    const double kb_clk = std::max(2.0 * c, (BM + c / ncta) * BK * 2 / 110.0);
     const int smax = may_split ? (split_k > 1 ? split_k : std::max(1, std::min(p.k_blocks / 4, 64))) : 1;
     for (int sp = (split_k > 1 ? split_k : 1); sp <= smax; ++sp) {
       const int kbs = (p.k_blocks + sp - 1) / sp;
       const int items = tiles * ((p.k_blocks + kbs - 1) / kbs);
-      const int waves = (items + nsm - 1) / nsm;
+      const int waves = (items + nstr - 1) / nstr;
       const double cost = waves * (kbs * kb_clk + 300.0) + c * (sp > 1 ? 10.0 : 6.0);
       if (cost < best) best = cost, bn = c, splits = sp;
     }
@@ -510,10 +604,14 @@ extern "C" int lav_gemm_f16(const void* A, int64_t lda, int a_major, const void*
   p.kb_per_split = (p.k_blocks + splits - 1) / splits;
   p.splits = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (ncta == 2) {
+    if (bn == 256) return dispatch_major<256, 2>(A, lda, a_major, B, ldb, b_major, p, s);
+    return dispatch_major<128, 2>(A, lda, a_major, B, ldb, b_major, p, s);
+  }
   switch (bn) {
-    case 64: return dispatch_major<64>(A, lda, a_major, B, ldb, b_major, p, s);
-    case 192: return dispatch_major<192>(A, lda, a_major, B, ldb, b_major, p, s);
-    case 256: return dispatch_major<256>(A, lda, a_major, B, ldb, b_major, p, s);
-    default: return dispatch_major<128>(A, lda, a_major, B, ldb, b_major, p, s);
+    case 64: return dispatch_major<64, 1>(A, lda, a_major, B, ldb, b_major, p, s);
+    case 192: return dispatch_major<192, 1>(A, lda, a_major, B, ldb, b_major, p, s);
+    case 256: return dispatch_major<256, 1>(A, lda, a_major, B, ldb, b_major, p, s);
+    default: return dispatch_major<128, 1>(A, lda, a_major, B, ldb, b_major, p, s);
   }
 }

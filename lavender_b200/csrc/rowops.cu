@@ -1,6 +1,7 @@
 // HBM-bound row kernels of the hot path: LayerNorm forward/backward (with the window-partition / cyclic-shift /
 // patch-merging gather folded into the row map), fp32->fp16 casts, column sums (bias gradients).
 // One warp per row, 128-bit accesses, fp32 statistics.
+#include "rng.cuh"
 #include "runtime.h"
 #include "sm100.cuh"
 
@@ -101,6 +102,7 @@ struct LnBwdParams {
   __half* dx16; int64_t lddx16;
   float* dgamma; float* dbeta;
   int rows;
+  DropParams drop;  // mask applied to dx16 only
 };
 
 __device__ __forceinline__ float4 load_dy4(const LnBwdParams& p, int r, int col) {
@@ -116,6 +118,8 @@ __global__ void __launch_bounds__(kRowThreads) ln_bwd_kernel(const LnBwdParams p
   const int wpb = kRowThreads / 32;
   const int W = p.G * p.C;
   const int c4 = p.C >> 2;
+  DropKey dkey{};
+  if (p.drop.on) dkey = drop_key(p.drop);
   for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < p.rows; r += gridDim.x * wpb) {
     int64_t srow[4];
 #pragma unroll
@@ -155,9 +159,15 @@ __global__ void __launch_bounds__(kRowThreads) ln_bwd_kernel(const LnBwdParams p
             o.x += a.x, o.y += a.y, o.z += a.z, o.w += a.w;
           }
           if (p.dx32) *reinterpret_cast<float4*>(p.dx32 + srow[g] * p.lddx32 + i * 4) = o;
-          if (p.dx16)
+          if (p.dx16) {
+            if (p.drop.on) {  // gradient entering a dense layer whose output was dropped at (r, col) in the forward
+              const uint32_t m = drop_keep8(dkey, p.drop.thresh, (uint32_t)r, (uint32_t)(col >> 3), 0u) >> (col & 7);
+              o.x = (m & 1u) ? o.x * p.drop.inv_keep : 0.f, o.y = (m & 2u) ? o.y * p.drop.inv_keep : 0.f;
+              o.z = (m & 4u) ? o.z * p.drop.inv_keep : 0.f, o.w = (m & 8u) ? o.w * p.drop.inv_keep : 0.f;
+            }
             *reinterpret_cast<uint2*>(p.dx16 + (int64_t)r * p.lddx16 + col) =
                 make_uint2(pack_half2(o.x, o.y), pack_half2(o.z, o.w));
+          }
         }
   }
 }
@@ -275,6 +285,38 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const __half2* dy, const 
   }
 }
 
+// out = x * keep / (1 - p), fp32 [rows, C], one thread per 8 consecutive columns (one Philox call)
+__global__ void __launch_bounds__(256)
+dropout_f32_kernel(const float* x, int64_t ldx, float* out, int64_t ldo, int rows, int C8, const DropParams d) {
+  const DropKey key = drop_key(d);
+  const int64_t n = (int64_t)rows * C8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / C8), b = (int)(i - (int64_t)r * C8);
+    const uint32_t m = drop_keep8(key, d.thresh, (uint32_t)r, (uint32_t)b, 0u);
+    const float4* src = reinterpret_cast<const float4*>(x + (int64_t)r * ldx + b * 8);
+    float4* dst = reinterpret_cast<float4*>(out + (int64_t)r * ldo + b * 8);
+    float4 v0 = src[0], v1 = src[1];
+    v0.x = (m & 1u) ? v0.x * d.inv_keep : 0.f, v0.y = (m & 2u) ? v0.y * d.inv_keep : 0.f;
+    v0.z = (m & 4u) ? v0.z * d.inv_keep : 0.f, v0.w = (m & 8u) ? v0.w * d.inv_keep : 0.f;
+    v1.x = (m & 16u) ? v1.x * d.inv_keep : 0.f, v1.y = (m & 32u) ? v1.y * d.inv_keep : 0.f;
+    v1.z = (m & 64u) ? v1.z * d.inv_keep : 0.f, v1.w = (m & 128u) ? v1.w * d.inv_keep : 0.f;
+    dst[0] = v0, dst[1] = v1;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+dropout_mask_kernel(uint8_t* keep, int rows, int C, int head, const DropParams d) {
+  const DropKey key = drop_key(d);
+  const int C8 = (C + 7) / 8;
+  const int64_t n = (int64_t)rows * C8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / C8), b = (int)(i - (int64_t)r * C8);
+    const uint32_t m = drop_keep8(key, d.thresh, (uint32_t)r, (uint32_t)b, head < 0 ? 0u : (uint32_t)head);
+    for (int q = 0; q < 8; ++q)
+      if (b * 8 + q < C) keep[(int64_t)r * C + b * 8 + q] = (m >> q) & 1u;
+  }
+}
+
 static int slab_rows(int rows, int col_blocks) {
   // enough row slabs to fill the machine a few times, at least 32 rows each
   int want = std::max(1, (6 * sm_count()) / std::max(1, col_blocks));
@@ -303,14 +345,16 @@ extern "C" int lav_layernorm_fwd(const float* x, int64_t ldx, const int32_t* row
 extern "C" int lav_layernorm_bwd(const void* dy, int64_t lddy, int dy_is_f32, const float* x, int64_t ldx,
                                  const int32_t* row_map, int G, int C, const float* gamma, const float* mean,
                                  const float* rstd, const float* add32, int64_t ldadd, float* dx32, int64_t lddx32,
-                                 void* dx16, int64_t lddx16, float* dgamma, float* dbeta, int rows, void* stream) {
+                                 void* dx16, int64_t lddx16, float* dgamma, float* dbeta, int rows, const LavDropout* drop16,
+                      void* stream) {
   LAV_REQUIRE(dy && x && gamma && mean && rstd && (dx32 || dx16), "lav_layernorm_bwd: null pointer");
   LAV_REQUIRE(G >= 1 && G <= 4 && C > 0 && (C % 4) == 0 && (ldx % 4) == 0 && (lddy % 4) == 0,
               "lav_layernorm_bwd: need C%%4==0, 1<=G<=4, ld%%4==0");
   LAV_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "lav_layernorm_bwd: dgamma/dbeta must come together");
   if (rows <= 0) return LAV_OK;
   LnBwdParams p{dy, lddy, dy_is_f32, x, ldx, row_map, G, C, gamma, mean, rstd, add32, ldadd,
-                dx32, lddx32, (__half*)dx16, lddx16, dgamma, dbeta, rows};
+                dx32, lddx32, (__half*)dx16, lddx16, dgamma, dbeta, rows, make_drop(drop16)};
+  LAV_REQUIRE(!p.drop.on || (dx16 && G == 1), "lav_layernorm_bwd: drop16 needs dx16 and G == 1");
   cudaStream_t s = (cudaStream_t)stream;
   if (dgamma) {  // must read x before an in-place dx32 overwrite of the same rows
     const int cb = (G * C + 127) / 128;
@@ -368,6 +412,35 @@ extern "C" int lav_gelu_bwd_f16(const void* dy16, const void* pre16, void* out16
   if (n <= 0) return LAV_OK;
   int grid = (int)std::min<int64_t>((n / 2 + 255) / 256, (int64_t)sm_count() * 8);
   gelu_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half2*)dy16, (const __half2*)pre16, (__half2*)out16, n / 2);
+  LAV_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return LAV_OK;
+}
+
+extern "C" int lav_dropout_f32(const float* x, int64_t ldx, float* out, int64_t ldo, int rows, int C,
+                               const LavDropout* drop, void* stream) {
+  LAV_REQUIRE(x && out && drop && drop->rng, "lav_dropout_f32: null pointer");
+  LAV_REQUIRE((C % 8) == 0 && (ldx % 4) == 0 && (ldo % 4) == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)out % 16) == 0,
+              "lav_dropout_f32: need C %% 8 == 0 and 16-byte aligned rows");
+  if (rows <= 0 || C <= 0) return LAV_OK;
+  DropParams d = make_drop(drop);
+  if (!d.on) d.on = 1, d.rng = drop->rng, d.site = drop->site, d.thresh = 0, d.inv_keep = 1.f;  // p == 0: copy
+  const int64_t n = (int64_t)rows * (C / 8);
+  const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 8);
+  dropout_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, out, ldo, rows, C / 8, d);
+  LAV_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return LAV_OK;
+}
+
+extern "C" int lav_dropout_mask(uint8_t* keep, int rows, int C, int head, const LavDropout* drop, void* stream) {
+  LAV_REQUIRE(keep && drop && drop->rng, "lav_dropout_mask: null pointer");
+  if (rows <= 0 || C <= 0) return LAV_OK;
+  DropParams d = make_drop(drop);
+  if (!d.on) d.on = 1, d.rng = drop->rng, d.site = drop->site, d.thresh = 0, d.inv_keep = 1.f;
+  const int64_t n = (int64_t)rows * ((C + 7) / 8);
+  const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 8);
+  dropout_mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(keep, rows, C, head, d);
   LAV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return LAV_OK;

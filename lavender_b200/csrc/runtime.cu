@@ -74,7 +74,7 @@ int encode_tmap_2d_f16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_
 
 extern "C" {
 
-int lav_abi_version(void) { return 1; }
+int lav_abi_version(void) { return 2; }
 const char* lav_last_error(void) { return lav::g_err; }
 int64_t lav_launch_count(void) { return lav::g_launches.load(); }
 

@@ -22,7 +22,8 @@ def _tol(K):
 
 
 @pytest.mark.parametrize("M,N,K", [(256, 128, 64), (128, 64, 256), (1000, 384, 128), (1960, 768, 1024),
-                                   (4096, 512, 96), (130, 72, 200), (2264, 2304, 768), (777, 256, 3072)])
+                                   (4096, 512, 96), (130, 72, 200), (2264, 2304, 768), (777, 256, 3072),
+                                   (7840, 2048, 512), (20000, 640, 192), (257, 130, 64)])
 def test_forward_plain(M, N, K):
     from lavender_b200 import ops
     a, b = _mk((M, K), 1), _mk((N, K), 2)
@@ -96,7 +97,8 @@ def test_residual_rowmap_rowscale():
     assert (out.double() - ref).abs().max().item() < 1e-3
 
 
-@pytest.mark.parametrize("M,N,K", [(512, 256, 128), (1000, 384, 128), (1352, 768, 30528), (300, 96, 384)])
+@pytest.mark.parametrize("M,N,K", [(512, 256, 128), (1000, 384, 128), (1352, 768, 30528), (300, 96, 384),
+                                   (7840, 512, 2048), (31000, 128, 512)])
 def test_dgrad_mn_major_b(M, N, K):
     """dX[M,N] = dY[M,K] @ W[K,N] with W stored [K(out features), N(in features)] row-major (MN-major B)."""
     from lavender_b200 import ops, _lib as L
@@ -108,7 +110,8 @@ def test_dgrad_mn_major_b(M, N, K):
 
 
 @pytest.mark.parametrize("T,N,K,split", [(1024, 256, 128, 1), (1960, 384, 128, 0), (125440 // 8, 384, 128, 0),
-                                         (1352, 768, 3072, 0), (1000, 96, 288, 4), (1352, 30522, 768, 0)])
+                                         (1352, 768, 3072, 0), (1000, 96, 288, 4), (1352, 30522, 768, 0),
+                                         (7840, 2048, 512, 0), (9088, 768, 3072, 0), (7840, 512, 512, 0)])
 def test_wgrad_mn_mn_accumulate(T, N, K, split):
     """dW[N,K] += dY[T,N]^T @ X[T,K]: both operands token-major (MN-major), fp32 accumulate, split-K atomics."""
     from lavender_b200 import ops, _lib as L

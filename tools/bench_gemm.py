@@ -42,6 +42,11 @@ def main():
         ("swin_s0_qkv_wgrad", 384, 128, 125440, "wgrad"), ("bert_ffn1_wgrad", 3072, 768, 9056, "wgrad"),
     ]
     shapes += [("swin_s2_fc2_dgrad_gelu", 7840, 2048, 512, "dgrad_gelu"), ("swin_s2_proj_res", 7840, 512, 512, "res")]
+    if "--sweep" in sys.argv:
+        shapes = [(f"k{K}", 7840, 2048, K, "fwd") for K in (64, 256, 512, 1024, 2048, 4096)]
+        shapes += [(f"m{M}", M, 2048, 512, "fwd") for M in (128, 1024, 18944, 37888)]
+        shapes += [("swin_s2_fc1_gelu", 7840, 2048, 512, "gelu"), ("swin_s2_fc2_res", 7840, 512, 2048, "res"),
+                   ("swin_s0_fc1_gelu", 125440, 512, 128, "gelu"), ("swin_s2_fc1_wgrad", 2048, 512, 7840, "wgrad")]
     only = [a for a in sys.argv[1:] if not a.startswith("-")]
     if only:
         shapes = [s_ for s_ in shapes if s_[0] in only]
@@ -81,7 +86,9 @@ def main():
         ms = timeit(fn, flush=flush)
         tf = 2.0 * M * N * K / ms / 1e9
         # torch (cuBLAS) for comparison on the plain product
-        if mode == "wgrad":
+        if "--no-cublas" in sys.argv:
+            ms_t = float("nan")
+        elif mode == "wgrad":
             ms_t = timeit(lambda: torch.matmul(a.t(), b), flush=flush)
         elif mode in ("dgrad", "dgrad_gelu"):
             ms_t = timeit(lambda: torch.matmul(a, b), flush=flush)
