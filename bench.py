@@ -379,8 +379,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--quick", action="store_true", help="resident steps only (for ncu runs)")
-    ap.add_argument("--eval-dropout", action="store_true", default=True,
-                    help="identity BERT dropout (until the dropout kernels land)")
+    ap.add_argument("--eval-dropout", action="store_true",
+                    help="identity BERT dropout (default: active p=0.1 dropout as in the reference's train() step)")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

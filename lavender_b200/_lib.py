@@ -15,12 +15,17 @@ class LavError(RuntimeError):
     pass
 
 
+class Dropout(ctypes.Structure):
+    """LavDropout: device rng pointer ([seed, step] uint64), call-site id, drop probability."""
+    _fields_ = [("rng", c_void_p), ("site", ctypes.c_uint32), ("p", c_float)]
+
+
 class GemmEpilogue(ctypes.Structure):
     _fields_ = [
         ("out", c_void_p), ("ldo", c_int64), ("out_dtype", ctypes.c_int32), ("act", ctypes.c_int32),
         ("bias", c_void_p), ("aux", c_void_p), ("ldaux", c_int64), ("residual", c_void_p), ("ldres", c_int64),
         ("row_map", c_void_p), ("row_scale", c_void_p), ("rows_per_scale", ctypes.c_int32), ("alpha", c_float),
-        ("accumulate", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("accumulate", ctypes.c_int32), ("reserved", ctypes.c_int32), ("drop", Dropout),
     ]
 
 
@@ -44,17 +49,21 @@ SIGNATURES = {
                                   c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p]),
     "lav_layernorm_bwd": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
-                                  c_void_p, c_void_p, c_int, c_void_p]),
+                                  c_void_p, c_void_p, c_int, ctypes.POINTER(Dropout), c_void_p]),
+    "lav_dropout_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, ctypes.POINTER(Dropout), c_void_p]),
+    "lav_dropout_mask": (c_int, [c_void_p, c_int, c_int, c_int, ctypes.POINTER(Dropout), c_void_p]),
     "lav_scale_cast_f16": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_float, c_void_p, c_int64, c_int,
                                    c_int, c_void_p]),
     "lav_cast_f32_to_f16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "lav_gelu_bwd_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "lav_colsum_f16": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_float, c_void_p]),
     "lav_attn_fwd_f16": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
-                                 c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+                                 c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p,
+                                 ctypes.POINTER(Dropout), c_void_p]),
     "lav_attn_bwd_f16": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                                  c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64, c_void_p,
-                                 c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_void_p]),
+                                 c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int,
+                                 ctypes.POINTER(Dropout), c_void_p]),
     "lav_relpos_bias_expand": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "lav_relpos_bias_grad": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "lav_bert_embed_ln_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,

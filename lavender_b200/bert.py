@@ -10,9 +10,11 @@ Arithmetic (verified against transformers 5.5 by the oracle goldens): post-LN la
 with LN eps 1e-12.  The residual stream, LN / softmax statistics and every accumulator are fp32; GEMM and
 attention operands are fp16 (the reference's GPU path is fp16 autocast, agent.py:219).
 
-Dropout (hidden 0.1, attention-probability 0.1) is applied only in train() mode and only when the config's
-probabilities are non-zero; see `BertConfig.lav_dropout` — the native kernels currently run the eval arithmetic
-(identity dropout) and raise if asked for a non-zero rate, they never silently fall back to torch.
+Dropout (hidden 0.1 after the embeddings / BertSelfOutput.dense / BertOutput.dense, attention-probability 0.1) is
+applied in train() mode exactly where HF applies it, inside the producing kernels (GEMM epilogue, attention
+softmax, embedding row kernel) from counter-based masks that the backward kernels regenerate (dropout.py,
+csrc/rng.cuh).  `config.lav_eval_dropout = True` forces identity dropout in train() mode (the configuration the
+bit-level parity tests against the reference goldens use, since a torch RNG stream cannot be reproduced).
 """
 import math
 
@@ -22,6 +24,7 @@ import torch.nn as nn
 from . import ops
 from . import _lib as L
 from .arena import arena_of
+from .dropout import rng_for
 from .functional import (F16, F32, empty16, empty32, linear_dgrad, linear_fwd, linear_wgrad, require_cuda)
 
 NEG_INF = float("-inf")
@@ -103,11 +106,11 @@ class BertLayer(nn.Module):
         self.output = BertOutput(c)
 
 
-def _check_dropout(mod, p, what):
+def _drop_p(mod, p):
+    """Effective drop probability of a site of `mod` (0 in eval() mode or under config.lav_eval_dropout)."""
     if mod.training and p > 0.0 and not getattr(mod.config, "lav_eval_dropout", False):
-        raise NotImplementedError(
-            f"{what}: dropout p={p} in train() mode is not implemented in the native kernels yet; set "
-            f"config.lav_eval_dropout=True (identity dropout, the parity configuration) or the probabilities to 0")
+        return float(p)
+    return 0.0
 
 
 class BertEmbeddings(nn.Module):
@@ -125,7 +128,6 @@ class BertEmbeddings(nn.Module):
             self.word_embeddings.weight[0].zero_()
 
     def forward(self, input_ids, token_type_ids=None, position_ids=None):
-        _check_dropout(self, self.config.hidden_dropout_prob, "BertEmbeddings")
         return _BertEmbedFn.apply(input_ids, token_type_ids, position_ids, self, self.word_embeddings.weight,
                                   self.position_embeddings.weight, self.token_type_embeddings.weight,
                                   self.LayerNorm.weight, self.LayerNorm.bias)
@@ -149,6 +151,9 @@ class _BertEmbedFn(torch.autograd.Function):
         s32, y32 = empty32(rows, H, device=dev), empty32(rows, H, device=dev)
         mean, rstd = empty32(rows, device=dev), empty32(rows, device=dev)
         ops.bert_embed_ln_fwd(ids1, ps1, tt1, word, pos, typ, gamma, beta, mod.LayerNorm.eps, s32, y32, mean, rstd, Lt=Lt)
+        ctx.drop = rng_for(dev).spec(_drop_p(mod, mod.config.hidden_dropout_prob))   # BertEmbeddings.dropout
+        if ctx.drop is not None:
+            ops.dropout_f32(y32, y32, ctx.drop)
         ctx.mod, ctx.saved, ctx.Lt = mod, (ids1, tt1, ps1, s32, mean, rstd), Lt
         ctx.params = (word, pos, typ, gamma, beta)
         return y32.view(*shp, H)
@@ -163,6 +168,8 @@ class _BertEmbedFn(torch.autograd.Function):
         g2 = gy.reshape(rows, H)
         if not g2.is_contiguous():
             g2 = g2.contiguous()
+        if ctx.drop is not None:
+            g2 = ops.dropout_f32(g2, empty32(rows, H, device=gy.device), ctx.drop)
         d = empty32(rows, H, device=gy.device)
         ops.layernorm_bwd(g2, s32, gamma, mean, rstd, rows=rows, C=H, dx32=d, dgamma=ar.g(gamma), dbeta=ar.g(beta))
         ops.bert_embed_bwd(d, ids1, ps1, tt1, ar.g(word), ar.g(pos), ar.g(typ), Lt=ctx.Lt)
@@ -195,10 +202,8 @@ class BertEncoder(nn.Module):
 
     def forward(self, hidden_states, attention_mask=None, output_attentions=False, **unused):
         require_cuda(hidden_states, "BertEncoder")
-        c = self.config
-        _check_dropout(self, max(c.hidden_dropout_prob, c.attention_probs_dropout_prob), "BertEncoder")
         B, Lq, H = hidden_states.shape
-        NPk = (Lq + 127) // 128 * 128
+        NPk = 384 if Lq <= 384 else (Lq + 127) // 128 * 128   # the forward kernel reads [nprob][384] rows (lavender_b200.h)
         kb = torch.full((B, NPk), NEG_INF, dtype=F32, device=hidden_states.device)
         if attention_mask is None:
             kb[:, :Lq] = 0.0
@@ -237,17 +242,20 @@ class _BertEncoderFn(torch.autograd.Function):
             x32 = x32.float()
         x16 = ops.scale_cast(x32, empty16(M, H, device=dev), rows=M, C=H)
         saved = []
+        rng = rng_for(dev)
+        p_hid, p_att = _drop_p(mod, c.hidden_dropout_prob), _drop_p(mod, c.attention_probs_dropout_prob)
         for lyr in mod.layer:
+            d_att, d_so, d_oo = rng.spec(p_att), rng.spec(p_hid), rng.spec(p_hid)   # three dropout sites per layer
             wqkv, bqkv = _layer_views(ar, lyr, H)
             qkv16 = empty16(M, 3 * H, device=dev)
             linear_fwd(x16, wqkv, bqkv, qkv16)
             ctx16 = empty16(M, H, device=dev)
             lse = empty32(nh, M, device=dev)
             ops.attn_fwd(qkv16, ctx16, lse, q_off=0, k_off=H, v_off=2 * H, head_dim=hd, nheads=nh, nprob=B, L_tok=Lq,
-                         scale=1.0 / math.sqrt(hd), key_bias=kb)
+                         scale=1.0 / math.sqrt(hd), key_bias=kb, drop=d_att)
             so = lyr.attention.output
             a_pre = empty32(M, H, device=dev)
-            linear_fwd(ctx16, ar.w16(so.dense.weight), so.dense.bias, a_pre, residual=x32)
+            linear_fwd(ctx16, ar.w16(so.dense.weight), so.dense.bias, a_pre, residual=x32, drop=d_so)
             a32, a16 = empty32(M, H, device=dev), empty16(M, H, device=dev)
             m1, r1 = empty32(M, device=dev), empty32(M, device=dev)
             ops.layernorm_fwd(a_pre, so.LayerNorm.weight, so.LayerNorm.bias, so.LayerNorm.eps, rows=M, C=H, out16=a16,
@@ -258,13 +266,13 @@ class _BertEncoderFn(torch.autograd.Function):
                        aux=pre16)
             oo = lyr.output
             o_pre = empty32(M, H, device=dev)
-            linear_fwd(i16, ar.w16(oo.dense.weight), oo.dense.bias, o_pre, residual=a32)
+            linear_fwd(i16, ar.w16(oo.dense.weight), oo.dense.bias, o_pre, residual=a32, drop=d_oo)
             y32, y16 = empty32(M, H, device=dev), empty16(M, H, device=dev)
             m2, r2 = empty32(M, device=dev), empty32(M, device=dev)
             ops.layernorm_fwd(o_pre, oo.LayerNorm.weight, oo.LayerNorm.bias, oo.LayerNorm.eps, rows=M, C=H, out16=y16,
                               out32=y32, mean=m2, rstd=r2)
             saved.append(dict(x16=x16, qkv16=qkv16, ctx16=ctx16, lse=lse, a_pre=a_pre, m1=m1, r1=r1, a16=a16,
-                              pre16=pre16, i16=i16, o_pre=o_pre, m2=m2, r2=r2))
+                              pre16=pre16, i16=i16, o_pre=o_pre, m2=m2, r2=r2, d_att=d_att, d_so=d_so, d_oo=d_oo))
             x32, x16 = y32, y16
         ctx.mod, ctx.saved, ctx.kb, ctx.geom = mod, saved, kb, (B, Lq, H, nh, hd)
         return x32.view(B, Lq, H)
@@ -287,7 +295,7 @@ class _BertEncoderFn(torch.autograd.Function):
             # y = LN2(o_pre), o_pre = W2 i + b2 + a
             go32, go16 = empty32(M, H, device=dev), empty16(M, H, device=dev)
             ops.layernorm_bwd(g, sv["o_pre"], oo.LayerNorm.weight, sv["m2"], sv["r2"], rows=M, C=H, dx32=go32, dx16=go16,
-                              dgamma=ar.g(oo.LayerNorm.weight), dbeta=ar.g(oo.LayerNorm.bias))
+                              dgamma=ar.g(oo.LayerNorm.weight), dbeta=ar.g(oo.LayerNorm.bias), drop16=sv["d_oo"])
             linear_wgrad(go16, sv["i16"], ar.g(oo.dense.weight), ar.g(oo.dense.bias))
             dpre16 = empty16(M, FF, device=dev)
             linear_dgrad(go16, ar.w16(oo.dense.weight), dpre16, act=L.ACT_GELU_BWD, aux=sv["pre16"])
@@ -297,14 +305,16 @@ class _BertEncoderFn(torch.autograd.Function):
             # a = LN1(a_pre), a_pre = Wo ctx + bo + x
             ga32, ga16 = empty32(M, H, device=dev), empty16(M, H, device=dev)
             ops.layernorm_bwd(da32, sv["a_pre"], so.LayerNorm.weight, sv["m1"], sv["r1"], rows=M, C=H, dx32=ga32,
-                              dx16=ga16, dgamma=ar.g(so.LayerNorm.weight), dbeta=ar.g(so.LayerNorm.bias))
+                              dx16=ga16, dgamma=ar.g(so.LayerNorm.weight), dbeta=ar.g(so.LayerNorm.bias),
+                              drop16=sv["d_so"])
             linear_wgrad(ga16, sv["ctx16"], ar.g(so.dense.weight), ar.g(so.dense.bias))
             dctx16 = empty16(M, H, device=dev)
             linear_dgrad(ga16, ar.w16(so.dense.weight), dctx16)
             dq_acc = torch.zeros(M, H, dtype=F32, device=dev)
             dqkv16 = empty16(M, 3 * H, device=dev)
             ops.attn_bwd(sv["qkv16"], sv["ctx16"], dctx16, sv["lse"], dq_acc, dqkv16, q_off=0, k_off=H, v_off=2 * H,
-                         head_dim=hd, nheads=nh, nprob=B, L_tok=Lq, scale=1.0 / math.sqrt(hd), key_bias=kb)
+                         head_dim=hd, nheads=nh, nprob=B, L_tok=Lq, scale=1.0 / math.sqrt(hd), key_bias=kb,
+                         drop=sv["d_att"])
             ops.scale_cast(dq_acc, dqkv16, rows=M, C=H)
             gw, gb = _layer_views(ar, lyr, H, grad=True)
             linear_wgrad(dqkv16, sv["x16"], gw, gb)

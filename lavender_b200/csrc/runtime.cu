@@ -52,16 +52,22 @@ static EncodeTiledFn get_encode_fn() {
 
 int encode_tmap_2d_f16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
                        uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swizzle) {
+  return encode_tmap_2d(map, ptr, 2, rows, cols, ld, box_rows, box_cols, swizzle);
+}
+
+int encode_tmap_2d(CUtensorMap* map, const void* ptr, int elt_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
+                   uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swizzle) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(LAV_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld % 8) != 0)
-    return set_error(LAV_E_INVALID, "TMA operand must be 16B aligned with ld %% 8 == 0 (ptr=%p ld=%llu)", ptr,
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || ((ld * elt_bytes) % 16) != 0 || (elt_bytes != 2 && elt_bytes != 4))
+    return set_error(LAV_E_INVALID, "TMA operand must be 16B aligned with a 16B-multiple row pitch (ptr=%p ld=%llu)", ptr,
                      (unsigned long long)ld);
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * 2};
+  cuuint64_t strides[1] = {ld * (uint64_t)elt_bytes};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = fn(map, elt_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)

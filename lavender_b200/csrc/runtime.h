@@ -17,6 +17,10 @@ int sm_count();  // of the current device (cached per device)
 int encode_tmap_2d_f16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
                        uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swizzle);
 
+// same for 2-byte (fp16) or 4-byte (fp32) elements; also used for TMA stores (out-of-bounds elements are not written)
+int encode_tmap_2d(CUtensorMap* map, const void* ptr, int elt_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
+                   uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swizzle);
+
 #define LAV_CHECK_CUDA(expr)                                                                          \
   do {                                                                                                \
     cudaError_t _e = (expr);                                                                          \

@@ -9,7 +9,8 @@ replayed with one `cudaGraphLaunch`:
     draws from the numpy RNG on the host: main_pretrain_mlm.py:90) that are refreshed by async copies;
   * the graph starts by zeroing the flat gradient arena, so `p.grad` stays bound to the arena views between steps
     (no zero_grad(set_to_none) in this mode);
-  * DropPath draws come from torch's graph-safe Philox generator (fresh numbers on every replay);
+  * DropPath draws come from torch's graph-safe Philox generator (fresh numbers on every replay); BERT dropout masks
+    are a function of a device-resident step counter that the graph increments first (dropout.py);
   * what stays eager after the replay: gradient all-reduce, unscale / clip / AdamW / LR schedule (agent.py).
 TMA descriptors are kernel parameters encoded on the host at capture time; they stay valid because every buffer the
 kernels touch belongs to the graph's private memory pool or to the model / arena.
@@ -18,6 +19,8 @@ from collections import defaultdict
 
 import numpy as np
 import torch
+
+from .dropout import rng_for
 
 _STATIC_KEYS = ("img", "txt", "mask", "ans_mtm", "vt_mask")
 
@@ -67,6 +70,7 @@ class GraphedPretrainStep:
 
     def _fwd_bwd(self):
         ag = self.agent
+        rng_for(self.static["img"].device).advance()   # captured: every replay draws new BERT dropout masks
         out = ag.forward_step(dict(self.static))
         l1 = ag.loss_func(out["out_mtm"].flatten(0, out["out_mtm"].dim() - 2), out["ans_mtm"].flatten())
         l2 = ag.loss_func(out["out_vtm"].flatten(0, out["out_vtm"].dim() - 2), out["ans_vtm"].flatten())

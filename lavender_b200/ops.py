@@ -48,8 +48,18 @@ def _chk16(t, name):
     assert t.is_cuda and t.dtype == F16 and t.stride(-1) == 1, f"{name}: need a row-major CUDA fp16 tensor"
 
 
+def _drop(d):
+    """d: None or (rng int64[2] device tensor, site, p) -> ctypes LavDropout pointer (or None)."""
+    if d is None or d[2] <= 0.0:
+        return None
+    rng, site, p = d
+    assert rng.is_cuda and rng.dtype == torch.int64 and rng.numel() >= 2
+    return ctypes.byref(L.Dropout(rng.data_ptr(), int(site) & 0xFFFFFFFF, float(p)))
+
+
 def gemm(a, b, out, *, M, N, K, a_major=L.MAJOR_K, b_major=L.MAJOR_K, bias=None, act=L.ACT_NONE, aux=None,
-         residual=None, row_map=None, row_scale=None, rows_per_scale=1, alpha=1.0, accumulate=False, split_k=0):
+         residual=None, row_map=None, row_scale=None, rows_per_scale=1, alpha=1.0, accumulate=False, split_k=0,
+         drop=None):
     """out[M,N] = epilogue(alpha * A·Bᵀ).  a/b are 2-D fp16 tensors stored per `*_major`
     (K-major: [rows, K]; MN-major: [K, rows]); `out` is fp16 or fp32 2-D."""
     _chk16(a, "a")
@@ -76,6 +86,8 @@ def gemm(a, b, out, *, M, N, K, a_major=L.MAJOR_K, b_major=L.MAJOR_K, bias=None,
         e.row_scale, e.rows_per_scale = row_scale.data_ptr(), rows_per_scale
     e.alpha = alpha
     e.accumulate = L.ACCUMULATE if accumulate else L.STORE
+    if drop is not None and drop[2] > 0.0:
+        e.drop = L.Dropout(drop[0].data_ptr(), int(drop[1]) & 0xFFFFFFFF, float(drop[2]))
     with _Timed("gemm", 2.0 * M * N * K, ("gemm", M, N, K, a_major, b_major, act, out.dtype == F16, accumulate)):
         rc = L.lib().lav_gemm_f16(_ptr(a), a.stride(0), a_major, _ptr(b), b.stride(0), b_major, M, N, K,
                                   ctypes.byref(e), split_k, _stream())
@@ -99,7 +111,7 @@ def layernorm_fwd(x, gamma, beta, eps, *, rows, C, G=1, row_map=None, out16=None
 
 
 def layernorm_bwd(dy, x, gamma, mean, rstd, *, rows, C, G=1, row_map=None, add32=None, dx32=None, dx16=None,
-                  dgamma=None, dbeta=None):
+                  dgamma=None, dbeta=None, drop16=None):
     assert dy.dtype in (F16, torch.float32) and x.dtype == torch.float32
     with _Timed("layernorm_bwd"):
         rc = L.lib().lav_layernorm_bwd(_p(dy), dy.stride(0), int(dy.dtype == torch.float32), _p(x), x.stride(0),
@@ -107,7 +119,7 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, *, rows, C, G=1, row_map=None, add32
                                        _p(add32), add32.stride(0) if add32 is not None else 0,
                                        _p(dx32), dx32.stride(0) if dx32 is not None else 0,
                                        _p(dx16), dx16.stride(0) if dx16 is not None else 0,
-                                       _p(dgamma), _p(dbeta), rows, _stream())
+                                       _p(dgamma), _p(dbeta), rows, _drop(drop16), _stream())
     L.check(rc, "lav_layernorm_bwd")
 
 
@@ -135,7 +147,7 @@ def colsum(x16, out, *, rows, N, alpha=1.0):
 
 
 def attn_fwd(qkv, out, lse, *, q_off, k_off, v_off, head_dim, nheads, nprob, L_tok, scale, bias16=None,
-             prob_class=None, key_bias=None):
+             prob_class=None, key_bias=None, drop=None):
     _chk16(qkv, "qkv")
     _chk16(out, "out")
     fam = "win_attn_fwd" if head_dim == 32 else "bert_attn_fwd"
@@ -143,12 +155,12 @@ def attn_fwd(qkv, out, lse, *, q_off, k_off, v_off, head_dim, nheads, nprob, L_t
       rc = L.lib().lav_attn_fwd_f16(_p(qkv), qkv.stride(0), qkv.shape[0], q_off, k_off, v_off, head_dim, nheads, nprob,
                                   L_tok, scale, _p(bias16), bias16.shape[-1] if bias16 is not None else 0,
                                   _p(prob_class), prob_class.numel() if prob_class is not None else 1, _p(key_bias),
-                                  _p(out), out.stride(0), _p(lse), _stream())
+                                  _p(out), out.stride(0), _p(lse), _drop(drop), _stream())
     L.check(rc, "lav_attn_fwd_f16")
 
 
 def attn_bwd(qkv, out, dout, lse, dq_acc, dqkv, *, q_off, k_off, v_off, head_dim, nheads, nprob, L_tok, scale,
-             bias16=None, prob_class=None, key_bias=None, ds16=None):
+             bias16=None, prob_class=None, key_bias=None, ds16=None, drop=None):
     fam = "win_attn_bwd" if head_dim == 32 else "bert_attn_bwd"
     with _Timed(fam, 8.0 * L_tok * L_tok * head_dim * nheads * nprob):
       rc = L.lib().lav_attn_bwd_f16(_p(qkv), qkv.stride(0), qkv.shape[0], q_off, k_off, v_off, head_dim, nheads, nprob,
@@ -157,7 +169,7 @@ def attn_bwd(qkv, out, dout, lse, dq_acc, dqkv, *, q_off, k_off, v_off, head_dim
                                   _p(key_bias), key_bias.shape[-1] if key_bias is not None else 0,
                                   _p(out), out.stride(0), _p(dout), dout.stride(0), _p(lse),
                                   _p(dq_acc), dq_acc.stride(0), _p(dqkv), dqkv.stride(0),
-                                  _p(ds16), ds16.shape[-1] if ds16 is not None else 0, _stream())
+                                  _p(ds16), ds16.shape[-1] if ds16 is not None else 0, _drop(drop), _stream())
     L.check(rc, "lav_attn_bwd_f16")
 
 
@@ -175,6 +187,26 @@ def relpos_bias_grad(ds16, rel_index, L_tok, dtable):
     with _Timed("relpos_grad"):
         rc = L.lib().lav_relpos_bias_grad(_p(ds16), nprob, nheads, NP, L_tok, _p(rel_index), _p(dtable), _stream())
     L.check(rc, "lav_relpos_bias_grad")
+
+
+def dropout_f32(x, out, drop):
+    """out = x * keep / (1 - p), fp32 2-D [rows, C] (C % 8 == 0); `drop` = (rng, site, p)."""
+    assert x.dtype == torch.float32 and out.dtype == torch.float32 and x.dim() == 2 and x.shape == out.shape
+    assert x.stride(1) == 1 and out.stride(1) == 1
+    d = L.Dropout(drop[0].data_ptr(), int(drop[1]) & 0xFFFFFFFF, float(drop[2]))
+    with _Timed("dropout"):
+        rc = L.lib().lav_dropout_f32(_p(x), x.stride(0), _p(out), out.stride(0), x.shape[0], x.shape[1], ctypes.byref(d),
+                                     _stream())
+    L.check(rc, "lav_dropout_f32")
+    return out
+
+
+def dropout_mask(rows, C, drop, head=-1):
+    """uint8 keep mask [rows, C] of a site (test helper; head >= 0: attention-probability index space)."""
+    keep = torch.empty(rows, C, dtype=torch.uint8, device=drop[0].device)
+    d = L.Dropout(drop[0].data_ptr(), int(drop[1]) & 0xFFFFFFFF, float(drop[2]))
+    L.check(L.lib().lav_dropout_mask(_p(keep), rows, C, head, ctypes.byref(d), _stream()), "lav_dropout_mask")
+    return keep
 
 
 def gelu_bwd(dy16, pre16, out16):
