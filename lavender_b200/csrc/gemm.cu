@@ -18,6 +18,7 @@ constexpr int BK = 64;  // 64 fp16 = one 128-byte swizzle atom
 constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = 128 + kEpiWarps * 32;
 constexpr int kEpiStride = 36;  // floats per staged accumulator row: 16-byte aligned, conflict-free for 128-bit access
+constexpr int kEpiWarpBytes = 8192;  // >= 32 * kEpiStride * 4; four 2 KB (fp16) or two 4 KB (fp32) TMA-store buffers
 
 // Persistent work streams: one CTA per SM, or one CTA pair per TPC.  The pair path (LAV_GEMM_PAIR=1) is correct and
 // wins on large square problems (8192^3: 1342 vs 1150 TFLOP/s) but not on the hot path's shapes, whose cost is the
@@ -41,7 +42,7 @@ struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BNL * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int EPI_BYTES = kEpiWarps * kEpiStride * 32 * 4;  // per-warp 32x32 fp32 transpose buffers
+  static constexpr int EPI_BYTES = kEpiWarps * kEpiWarpBytes;  // per-warp staging: transposes / TMA-store buffers
   static constexpr int BAR_BYTES = 256;
   static constexpr int STAGES_MAX = (232448 - 1024 - BAR_BYTES - EPI_BYTES) / STAGE_BYTES;
   static constexpr int STAGES_CAP = NCTA == 2 ? 8 : 6;
@@ -55,6 +56,7 @@ struct GemmParams {
   int M, N, K;
   int m_blocks, n_blocks, k_blocks, splits, kb_per_split;  // m_blocks counts tiles of BM * NCTA rows
   DropParams drop;  // resolved from epi.drop
+  int tma_store;    // 1: plain fp16 / fp32 store through TMA (no row map / residual / accumulation)
   int debug;  // LAV_GEMM_DEBUG (profiling only): bit 0 = epilogue drains without math / stores, bit 1 = no MMA issue
   LavGemmEpilogue epi;
 };
@@ -182,7 +184,7 @@ __device__ __forceinline__ void epilogue_warps(const GemmParams& p, float* epi_s
                                                int stream_id, int nstreams, int rank) {
   const int wg = (warp - 4) >> 2;
   const int q = warp & 3;  // TMEM lane quarter this warp may access
-  float* stg = epi_stage + (warp - 4) * (kEpiStride * 32);
+  float* stg = epi_stage + (warp - 4) * (kEpiWarpBytes / 4);
   const int rr = lane >> 3, cg = lane & 7;  // this lane's row-within-group / 4-column group in the store phase
   const LavGemmEpilogue& e = p.epi;
   constexpr bool use_res = PRE == 1;
@@ -326,9 +328,143 @@ __device__ __forceinline__ void epilogue_warps(const GemmParams& p, float* epi_s
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// TMA-store epilogue for the plain outputs (fp16 activations of qkv / fc1 / dgrad GEMMs, fp32 logits): the thread
+// that owns accumulator row r packs 32 columns into its row of a swizzled shared-memory tile and ONE lane hands the
+// 32 x 32 tile to the TMA unit.  No transposed read-back, no per-thread global addresses or bounds predicates (the
+// tensor map clips rows >= M and columns >= N); up to 3 stores per warp stay in flight.
+// ---------------------------------------------------------------------------------------------------------
+template <bool F32>
+__device__ __forceinline__ void stage_and_store(const CUtensorMap* tm, uint8_t* buf, uint32_t& nb, int lane,
+                                                const float (&v)[32], int col0, int row0, bool rows_valid) {
+  constexpr int ROWB = F32 ? 128 : 64;
+  constexpr int BUFB = 32 * ROWB;
+  constexpr int NB = kEpiWarpBytes / BUFB;
+  uint8_t* b = buf + (nb % NB) * BUFB;
+  if (lane == 0) tma_store_wait_read<NB - 1>();  // the store that last used this buffer has drained it
+  __syncwarp();
+  if (F32) {
+    uint8_t* row = b + lane * 128;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<float4*>(row + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  } else {
+    uint8_t* row = b + lane * 64;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<uint4*>(row + ((j ^ ((lane >> 1) & 3)) << 4)) =
+          make_uint4(pack_half2(v[8 * j], v[8 * j + 1]), pack_half2(v[8 * j + 2], v[8 * j + 3]),
+                     pack_half2(v[8 * j + 4], v[8 * j + 5]), pack_half2(v[8 * j + 6], v[8 * j + 7]));
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    if (rows_valid) tma_store_2d(tm, b, col0, row0);
+    tma_store_commit();
+  }
+  ++nb;
+}
+
+template <int BN, int NCTA, int ACT, bool F32>
+__device__ __forceinline__ void epilogue_warps_tma(const GemmParams& p, const CUtensorMap* tmOut, const CUtensorMap* tmAux,
+                                                   float* epi_stage, uint64_t* tmem_full, uint64_t* tmem_empty,
+                                                   uint32_t tmem_base, int warp, int lane, int total, int stream_id,
+                                                   int nstreams, int rank) {
+  const int wg = (warp - 4) >> 2;
+  const int q = warp & 3;
+  uint8_t* buf = reinterpret_cast<uint8_t*>(epi_stage) + (warp - 4) * kEpiWarpBytes;
+  const LavGemmEpilogue& e = p.epi;
+  const bool aux_out = ACT == LAV_ACT_GELU && e.aux != nullptr;
+  uint32_t nb = 0;
+  int iter = 0;
+  for (int item = stream_id; item < total; item += nstreams, ++iter) {
+    if ((iter & 1) != wg) continue;
+    const TileCoord t = decode_tile(p, item);
+    const int row_base = (t.m_blk * NCTA + rank) * BM + q * 32;
+    const bool rows_valid = row_base < p.M;
+    const int row = row_base + lane;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + wg * BN;
+    const int n0 = t.n_blk * BN;
+    const int nchunks = min(BN / 32, (p.N - n0 + 31) / 32);
+    mbar_wait(tmem_full + wg, (iter >> 1) & 1, 4);
+    tc_fence_after();
+    if (p.debug & 1) {
+      tc_fence_before();
+      if (NCTA == 2) mbar_arrive_cluster(tmem_empty + wg, 0);
+      else mbar_arrive(tmem_empty + wg);
+      continue;
+    }
+#pragma unroll 1
+    for (int c = 0; c < nchunks; ++c) {
+      const int col0 = n0 + c * 32;
+      const bool full = col0 + 32 <= p.N;
+      uint32_t acc[32];
+      tmem_ld_32x32(taddr + c * 32, acc);
+      // global inputs of this chunk are requested while the TMEM load is in flight
+      float4 bv[8];
+      if (e.bias && full) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bv[j] = __ldg(reinterpret_cast<const float4*>(e.bias + col0) + j);
+      }
+      uint4 ax[4];
+      if (ACT == LAV_ACT_GELU_BWD) {
+        const __half* xa = reinterpret_cast<const __half*>(e.aux) + (size_t)min(row, p.M - 1) * e.ldaux + col0;
+        if (full && (e.ldaux & 7) == 0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ax[j] = __ldg(reinterpret_cast<const uint4*>(xa) + j);
+        } else {
+          __half* h = reinterpret_cast<__half*>(ax);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) h[j] = col0 + j < p.N ? xa[j] : __float2half_rn(0.f);
+        }
+      }
+      tmem_ld_wait();
+      if (c == nchunks - 1) {  // accumulator fully read: hand the TMEM stage back to the MMA warp early
+        tc_fence_before();
+        if (NCTA == 2) mbar_arrive_cluster(tmem_empty + wg, 0);
+        else mbar_arrive(tmem_empty + wg);
+      }
+      float v[32];
+      if (e.alpha != 1.0f) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * e.alpha;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+      }
+      if (e.bias) {
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            v[4 * j] += bv[j].x, v[4 * j + 1] += bv[j].y, v[4 * j + 2] += bv[j].z, v[4 * j + 3] += bv[j].w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) v[j] += __ldg(e.bias + col0 + j);
+        }
+      }
+      if (ACT == LAV_ACT_GELU) {
+        if (aux_out) stage_and_store<false>(tmAux, buf, nb, lane, v, col0, row_base, rows_valid);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+      } else if (ACT == LAV_ACT_GELU_BWD) {
+        const __half2* h2 = reinterpret_cast<const __half2*>(ax);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float2 x = __half22float2(h2[j]);
+          v[2 * j] *= gelu_erf_grad(x.x), v[2 * j + 1] *= gelu_erf_grad(x.y);
+        }
+      }
+      stage_and_store<F32>(tmOut, buf, nb, lane, v, col0, row_base, rows_valid);
+    }
+  }
+  if (lane == 0) tma_store_wait_all();  // smem must outlive the reads; the writes complete before the grid does
+}
+
 template <int BN, int AMAJ, int BMAJ, int NCTA>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux,
                 const GemmParams p) {
   using Cfg = GemmCfg<BN, NCTA>;
   constexpr int BNL = Cfg::BNL;
@@ -352,6 +488,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_store) tma_prefetch_desc(&tmOut);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
@@ -463,7 +600,15 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #define LAV_EPI(A, P, S)                                                                                       \
   epilogue_warps<BN, NCTA, A, P, S>(p, epi_stage, tmem_full, tmem_empty, tmem_base, warp, lane, total, stream_id, \
                                     nstreams, rank)
-    if (e.act == LAV_ACT_GELU) {
+#define LAV_EPI_TMA(A, F)                                                                                        \
+  epilogue_warps_tma<BN, NCTA, A, F>(p, &tmOut, &tmAux, epi_stage, tmem_full, tmem_empty, tmem_base, warp, lane, total, \
+                                     stream_id, nstreams, rank)
+    if (p.tma_store) {
+      if (e.act == LAV_ACT_GELU) LAV_EPI_TMA(LAV_ACT_GELU, false);
+      else if (e.act == LAV_ACT_GELU_BWD) LAV_EPI_TMA(LAV_ACT_GELU_BWD, false);
+      else if (st == ST_F16) LAV_EPI_TMA(LAV_ACT_NONE, false);
+      else LAV_EPI_TMA(LAV_ACT_NONE, true);
+    } else if (e.act == LAV_ACT_GELU) {
       if (st == ST_F16 && !pre) LAV_EPI(LAV_ACT_GELU, 0, ST_F16);
       else LAV_EPI(LAV_ACT_GELU, 0, ST_F32);               // host restricts GELU to {f16, f32 store} without residual
     } else if (e.act == LAV_ACT_GELU_BWD) {
@@ -484,6 +629,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       else LAV_EPI(LAV_ACT_NONE, 1, ST_F32_RMW);
     }
 #undef LAV_EPI
+#undef LAV_EPI_TMA
   }
 
   tc_fence_before();
@@ -511,6 +657,18 @@ static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, G
     rc = encode_tmap_2d_f16(&tmB, B, p.K, p.N, ldb, BK, 64, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   p.n_blocks = (p.N + BN - 1) / BN;
+  CUtensorMap tmOut = tmA, tmAux = tmA;  // placeholders unless the TMA-store epilogue is selected
+  if (p.tma_store) {
+    const LavGemmEpilogue& e = p.epi;
+    const bool f32 = e.out_dtype == LAV_OUT_F32;
+    rc = encode_tmap_2d(&tmOut, e.out, f32 ? 4 : 2, p.M, p.N, e.ldo, 32, 32,
+                        f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+    if (e.act == LAV_ACT_GELU && e.aux) {
+      rc = encode_tmap_2d(&tmAux, e.aux, 2, p.M, p.N, e.ldaux, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc) return rc;
+    }
+  }
   auto kern = gemm_f16_kernel<BN, AMAJ, BMAJ, NCTA>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -529,7 +687,7 @@ static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, G
   attr[0].val.clusterDim.x = NCTA, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = NCTA == 2 ? 1 : 0;
-  LAV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+  LAV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, tmAux, p));
   count_launch();
   return LAV_OK;
 }
@@ -565,6 +723,21 @@ extern "C" int lav_gemm_f16(const void* A, int64_t lda, int a_major, const void*
   LAV_REQUIRE(!p.drop.on || (epi->act == LAV_ACT_NONE && epi->residual && epi->out_dtype == LAV_OUT_F32 &&
                              epi->accumulate != LAV_ACCUMULATE),
               "lav_gemm_f16: epilogue dropout needs (no activation, residual, fp32 store)");
+  {
+    // TMA-store epilogue: plain stores only (no scatter / residual / DropPath / accumulation / dropout), GELU outputs
+    // fp16, 16-byte aligned rows.  LAV_GEMM_TMA_STORE=0 keeps the register path (A/B testing).
+    static int tma_ok = -1;
+    if (tma_ok < 0) {
+      const char* ev = getenv("LAV_GEMM_TMA_STORE");
+      tma_ok = (ev && ev[0] == '0') ? 0 : 1;
+    }
+    const int eb = epi->out_dtype == LAV_OUT_F32 ? 4 : 2;
+    bool ok = tma_ok && !epi->row_map && !epi->residual && !epi->row_scale && epi->accumulate != LAV_ACCUMULATE &&
+              !p.drop.on && ((uintptr_t)epi->out % 16) == 0 && ((epi->ldo * eb) % 16) == 0;
+    if (epi->act != LAV_ACT_NONE) ok = ok && epi->out_dtype == LAV_OUT_F16;
+    if (epi->act == LAV_ACT_GELU && epi->aux) ok = ok && ((uintptr_t)epi->aux % 16) == 0 && (epi->ldaux % 8) == 0;
+    p.tma_store = ok ? 1 : 0;
+  }
   {
     static int dbg = -1;
     if (dbg < 0) {
