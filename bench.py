@@ -214,6 +214,19 @@ def run_native(a):
         gc.unfreeze()
         return ms.item(), _lib.launch_count() - n0, r, per_step
 
+    if a.profile_step:
+        # for `ncu --profile-from-start off`: one eager warm-up step (lazy kernel attributes, index-map caches), then
+        # exactly one eager step inside cudaProfilerStart/Stop so that only its ~2000 launches are instrumented
+        step_eager()
+        agent.optzr.zero_grad(set_to_none=True)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        step_eager()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        if rank == 0:
+            print(json.dumps({"profile_step": True}), flush=True)
+        return
     sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(max(a.warmup, 3)):
         step_resident()
@@ -379,6 +392,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--quick", action="store_true", help="resident steps only (for ncu runs)")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="one eager step between cudaProfilerStart/Stop (ncu --profile-from-start off)")
     ap.add_argument("--eval-dropout", action="store_true",
                     help="identity BERT dropout (default: active p=0.1 dropout as in the reference's train() step)")
     a = ap.parse_args()

@@ -157,8 +157,9 @@ int lav_colsum_f16(const void* x16, int64_t ld, int rows, int N, float* out, flo
  * O = softmax(scale * Q K^T + bias) V for `nprob` independent problems of L tokens each whose rows are
  * contiguous in the fused QKV activation [rows_total, ld] (Q/K/V of head h at columns *_off + h*head_dim).
  *   - WindowAttention3D.forward video_swin.py:147-167: head_dim 32, L = 245 (<= 256); `bias16` is the dense
- *     [ncls][nheads][256][256] fp16 tensor of lav_relpos_bias_expand (relative position bias :153-155 + shift
- *     mask :157-160 + -inf on padded keys); problem p uses class prob_class[p % class_period].
+ *     [ncls][nheads][256][256] fp16 tensor of lav_relpos_bias_expand built with inv_scale = 1 / scale (relative
+ *     position bias :153-155 + shift mask :157-160 + masked padded keys); problem p uses class
+ *     prob_class[p % class_period] (ncls <= 8).
  *   - HF BertSelfAttention (model.py:242): head_dim 64, L <= 384; key_bias is the additive [nprob][384] fp32
  *     row (0 for kept keys, -inf for masked / padded keys) of get_extended_attention_mask (model.py:239).
  * Writes O (fp16, [rows_total, ldo], head h at column h*head_dim) and lse[h][row] = log-sum-exp (fp32). */
@@ -180,10 +181,12 @@ int lav_attn_bwd_f16(const void* qkv, int64_t ld, int64_t rows_total, int q_off,
                      float* dq_acc, int64_t lddq, void* dqkv16, int64_t lddqkv, void* ds16, int NPs,
                      const LavDropout* drop, void* stream);
 
-/* dense16[cls][h][i][j] = table[rel_index[i*L+j]][h] + (labels[cls][i] != labels[cls][j] ? -100 : 0), -inf for
- * j >= L (video_swin.py:153-160 and compute_mask :290-305); labels may be NULL (unshifted block, ncls = 1). */
+/* dense16[cls][h][i][j] = inv_scale * (table[rel_index[i*L+j]][h] + (labels[cls][i] != labels[cls][j] ? -100 : 0)),
+ * and -30000 for the padded key columns j >= L (video_swin.py:153-160 and compute_mask :290-305); labels may be NULL
+ * (unshifted block, ncls = 1).  inv_scale = 1 / (softmax scale passed to lav_attn_*_f16): the attention kernels add
+ * the tile to the raw Q K^T accumulator with a tensor-core identity product and scale the sum. */
 int lav_relpos_bias_expand(const float* table, int nheads, const int32_t* rel_index, int L, const uint8_t* labels,
-                           int ncls, void* dense16, int NP, void* stream);
+                           int ncls, void* dense16, int NP, float inv_scale, void* stream);
 
 /* dtable[rel_index[i*L+j]][h] += sum_p ds16[p][h][i][j]  (gradient of relative_position_bias_table) */
 int lav_relpos_bias_grad(const void* ds16, int nprob, int nheads, int NP, int L, const int32_t* rel_index,

@@ -31,23 +31,31 @@ struct AttnBwdParams {
   DropParams drop;                          // attention-probability dropout of the forward (regenerated here)
 };
 
-template <int HD>
+constexpr int kIdentGroupsB = 30;                // see attention_fwd.cu: sliding 128 x 16 identity slices
+constexpr int kIdentBytesB = kIdentGroupsB * 256;
+
+// BMMA (window attention with the dense relative-position bias): S = Q K^T + I * Bias on the tensor core, the
+// 128 x 128 bias tile of each query tile TMA-staged (double-buffered like Q / dO) instead of being read by threads.
+template <int HD, bool BMMA>
 struct AttnBwdCfg {
   static constexpr int ROWB = HD * 2;
   static constexpr int TILE = 128 * ROWB;
   static constexpr int OFF_K = 0, OFF_V = TILE, OFF_Q = 2 * TILE, OFF_DO = 4 * TILE;  // Q, dO double-buffered
-  static constexpr int OFF_P = 6 * TILE, OFF_DS = OFF_P + 32768, OFF_BAR = OFF_DS + 32768;
+  static constexpr int OFF_P = 6 * TILE, OFF_DS = OFF_P + 32768;
+  static constexpr int OFF_BIAS = OFF_DS + 32768;                                     // 2 x [128][128] fp16
+  static constexpr int OFF_ID = OFF_BIAS + (BMMA ? 65536 : 0);
+  static constexpr int OFF_BAR = OFF_ID + (BMMA ? kIdentBytesB : 0);
   static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
   static constexpr uint32_t SWZ = (HD == 64) ? SWZ_128B : SWZ_64B;
   static constexpr uint32_t SBO = 8 * ROWB;
   static constexpr int COL_S = 0, COL_DP = 128, COL_DQ = 256, COL_DK = 320, COL_DV = 384;
 };
 
-template <int HD>
+template <int HD, bool BMMA>
 __global__ void __launch_bounds__(kAttnBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                const AttnBwdParams p) {
-  using Cfg = AttnBwdCfg<HD>;
+                const __grid_constant__ CUtensorMap tmBias, const AttnBwdParams p) {
+  using Cfg = AttnBwdCfg<HD, BMMA>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);  // 0 kv | 1,2 q/dO buf | 3 S,dP | 4 P,dS | 5 mma2
@@ -58,10 +66,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const int row0 = prob * p.L;
   const int nqt = (p.L + 127) / 128;
 
+  if (BMMA && warp < 4) {  // identity strip (zeros with a 16 x 16 identity block at groups 14-15), as in attention_fwd.cu
+    uint8_t* id = smem + Cfg::OFF_ID;
+    for (int i = threadIdx.x; i < kIdentBytesB / 16; i += 128) reinterpret_cast<uint4*>(id)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncwarp();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (threadIdx.x < 16) {
+      const int r = threadIdx.x;
+      const int off = r < 8 ? 14 * 256 + r * 16 + r * 2 : 15 * 256 + 128 + (r - 8) * 16 + (r - 8) * 2;
+      *reinterpret_cast<__half*>(id + off) = __float2half_rn(1.0f);
+    }
+    fence_proxy_async_smem();
+  }
   if (warp == 4) {
     if (lane == 0) {
       tma_prefetch_desc(&tmQKV);
       tma_prefetch_desc(&tmDO);
+      if (BMMA) tma_prefetch_desc(&tmBias);
       mbar_init(bars + 0, 1);
       mbar_init(bars + 1, 1);
       mbar_init(bars + 2, 1);
@@ -80,11 +101,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
   if (warp == 4) {
     if (lane == 0) {
+      const int bcls = (BMMA && p.prob_class) ? p.prob_class[prob % p.period] : 0;
       auto load_q = [&](int t) {
         const int b = t & 1;
-        mbar_arrive_expect_tx(bars + 1 + b, 2 * Cfg::TILE);
+        mbar_arrive_expect_tx(bars + 1 + b, 2 * Cfg::TILE + (BMMA ? 32768 : 0));
         tma_load_2d(smem + Cfg::OFF_Q + b * Cfg::TILE, &tmQKV, bars + 1 + b, p.q_off + h * HD, row0 + t * 128);
         tma_load_2d(smem + Cfg::OFF_DO + b * Cfg::TILE, &tmDO, bars + 1 + b, h * HD, row0 + t * 128);
+        if (BMMA) {  // bias rows t*128.., key columns c*128..: two boxes of [128 rows x 64 columns]
+          const int brow = (bcls * p.nheads + h) * p.NPb + t * 128;
+          tma_load_2d(smem + Cfg::OFF_BIAS + b * 32768, &tmBias, bars + 1 + b, c * 128, brow);
+          tma_load_2d(smem + Cfg::OFF_BIAS + b * 32768 + 16384, &tmBias, bars + 1 + b, c * 128 + 64, brow);
+        }
       };
       mbar_arrive_expect_tx(bars + 0, 2 * Cfg::TILE);
       tma_load_2d(smem + Cfg::OFF_K, &tmQKV, bars + 0, p.k_off + h * HD, row0 + c * 128);
@@ -107,6 +134,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         for (int k = 0; k < HD / 16; ++k)
           umma_f16_ss(tmem + Cfg::COL_S, make_smem_desc(sq + k * 32, 0, Cfg::SBO, Cfg::SWZ),
                       make_smem_desc(sk + k * 32, 0, Cfg::SBO, Cfg::SWZ), id_s, k > 0);
+        if (BMMA) {  // S += I * Bias
+          constexpr uint32_t id_b = make_idesc_f16(128, 128, 0, 1);
+          const uint32_t sid = smem_u32(smem + Cfg::OFF_ID), sbias = smem_u32(smem + Cfg::OFF_BIAS + b * 32768);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_f16_ss(tmem + Cfg::COL_S, make_smem_desc(sid + (14 - 2 * kk) * 256, 128, 256, SWZ_NONE),
+                        make_smem_desc(sbias + kk * 2048, 16384, 1024, SWZ_128B), id_b, 1u);
+        }
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
           umma_f16_ss(tmem + Cfg::COL_DP, make_smem_desc(sdo + k * 32, 0, Cfg::SBO, Cfg::SWZ),
@@ -165,7 +200,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           }
         }
       }
-      const __half* brow = p.bias16 ? p.bias16 + (((size_t)cls * p.nheads + h) * p.NPb + min(qi, p.NPb - 1)) * p.NPb + c * 128
+      const __half* brow = (!BMMA && p.bias16) ? p.bias16 + (((size_t)cls * p.nheads + h) * p.NPb + min(qi, p.NPb - 1)) * p.NPb + c * 128
                                     : nullptr;
       __half* dsg = (p.ds_out && valid) ? p.ds_out + (((size_t)prob * p.nheads + h) * p.NPs + qi) * p.NPs + c * 128
                                         : nullptr;
@@ -188,7 +223,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               float2 f = __half22float2(hh[q]);
-              pv[8 * j + 2 * q] += f.x * 1.4426950408889634f, pv[8 * j + 2 * q + 1] += f.y * 1.4426950408889634f;
+              // the dense bias holds bias / scale (lav_relpos_bias_expand): back to log2 units with scale * log2(e)
+              pv[8 * j + 2 * q] += f.x * sc_log2, pv[8 * j + 2 * q + 1] += f.y * sc_log2;
             }
           }
         }
@@ -248,7 +284,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         if (valid) {
           float* dst = p.dq_acc + (size_t)(row0 + qi) * p.lddq + h * HD + c0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(o[j]) * p.scale);
+          for (int j = 0; j < 8; ++j)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j),
+                         "f"(__uint_as_float(o[4 * j]) * p.scale), "f"(__uint_as_float(o[4 * j + 1]) * p.scale),
+                         "f"(__uint_as_float(o[4 * j + 2]) * p.scale), "f"(__uint_as_float(o[4 * j + 3]) * p.scale)
+                         : "memory");
         }
       }
       tc_fence_before();
@@ -313,23 +353,28 @@ relpos_bias_grad_kernel(const __half* ds, int nprob, int nheads, int NP, int L, 
   }
 }
 
-template <int HD>
+template <int HD, bool BMMA>
 static int launch_attn_bwd(const void* qkv, int64_t ld, const AttnBwdParams& p, int nkc, cudaStream_t s) {
-  using Cfg = AttnBwdCfg<HD>;
-  CUtensorMap tq, tdo;
+  using Cfg = AttnBwdCfg<HD, BMMA>;
+  CUtensorMap tq, tdo, tb;
   const CUtensorMapSwizzle sw = HD == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   int rc = encode_tmap_2d_f16(&tq, qkv, p.rows_total, ld, ld, 128, HD, sw);
   if (rc) return rc;
   rc = encode_tmap_2d_f16(&tdo, p.dout, p.rows_total, p.nheads * HD, p.lddo, 128, HD, sw);
   if (rc) return rc;
-  auto kern = attn_bwd_kernel<HD>;
+  tb = tq;
+  if (BMMA) {
+    rc = encode_tmap_2d_f16(&tb, p.bias16, (uint64_t)8 * p.nheads * p.NPb, p.NPb, p.NPb, 128, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  auto kern = attn_bwd_kernel<HD, BMMA>;
   static bool attr_set = false;
   if (!attr_set) {
     LAV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   dim3 grid(nkc, p.nheads, p.nprob);
-  kern<<<grid, kAttnBwdThreads, Cfg::SMEM_BYTES, s>>>(tq, tdo, p);
+  kern<<<grid, kAttnBwdThreads, Cfg::SMEM_BYTES, s>>>(tq, tdo, tb, p);
   LAV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return LAV_OK;
@@ -362,7 +407,9 @@ extern "C" int lav_attn_bwd_f16(const void* qkv, int64_t ld, int64_t rows_total,
   p.dqkv = (__half*)dqkv16, p.lddqkv = lddqkv, p.ds_out = (__half*)ds16, p.NPs = NPs;
   p.drop = make_drop(drop);
   cudaStream_t s = (cudaStream_t)stream;
-  return head_dim == 32 ? launch_attn_bwd<32>(qkv, ld, p, nkc, s) : launch_attn_bwd<64>(qkv, ld, p, nkc, s);
+  LAV_REQUIRE((lddq % 4) == 0 && ((uintptr_t)dq_acc % 16) == 0, "lav_attn_bwd_f16: dq_acc rows must be 16-byte aligned");
+  if (head_dim == 32 && bias16) return launch_attn_bwd<32, true>(qkv, ld, p, nkc, s);
+  return head_dim == 32 ? launch_attn_bwd<32, false>(qkv, ld, p, nkc, s) : launch_attn_bwd<64, false>(qkv, ld, p, nkc, s);
 }
 
 extern "C" int lav_relpos_bias_grad(const void* ds16, int nprob, int nheads, int NP, int L, const int32_t* rel_index,

@@ -5,8 +5,12 @@
 //     by TMA; S = Q Kᵀ is a tcgen05 MMA into TMEM (128 x NKC*128 fp32), softmax runs in registers straight from
 //     tcgen05.ld (one thread per query row), P goes to shared memory as fp16 in the UMMA K-major 128B-swizzle
 //     layout, O = P V is a second tcgen05 MMA whose accumulator aliases the dead S columns.
-//   * relative-position bias + shift mask (+ -inf on the padded key columns) come pre-expanded as a dense fp16
-//     [class][head][NP][NP] tensor (lav_relpos_bias_expand); BERT passes an additive per-key fp32 row instead.
+//   * relative-position bias + shift mask (+ a large negative on the padded key columns) come pre-expanded as a dense
+//     fp16 [class][head][NP][NP] tensor (lav_relpos_bias_expand, values already divided by `scale`).  The window
+//     kernel never touches it with a thread: the 128 x 256 bias tile is TMA-staged and ADDED BY THE TENSOR CORE,
+//     S = Q K^T + I * Bias, with the 128 x 128 identity supplied as eight 128 x 16 slices of one 7.5 KB
+//     shared-memory strip (a 16 x 16 identity block between zero rows, addressed through a sliding UMMA descriptor);
+//     the bias tile's shared memory is then reused for P.  BERT passes an additive per-key fp32 row instead.
 // Nothing of size [B_, nh, N, N] ever reaches HBM.
 #include "rng.cuh"
 #include "runtime.h"
@@ -28,27 +32,32 @@ struct AttnFwdParams {
   DropParams drop;                         // attention-probability dropout (BERT, train mode)
 };
 
-template <int HD, int NKC>
+constexpr int kIdentGroups = 30;                         // 16-group window sliding by 2 groups per k-step, 8 k-steps
+constexpr int kIdentBytes = kIdentGroups * 256;          // group = 8 rows x 16 k: two 128-byte core matrices
+
+template <int HD, int NKC, bool BMMA>
 struct AttnFwdCfg {
   static constexpr int ROWB = HD * 2;                    // bytes per Q/K/V smem row == TMA swizzle span
   static constexpr int Q_BYTES = 128 * ROWB;
   static constexpr int KV_BYTES = NKC * 128 * ROWB;      // per K or V
-  static constexpr int P_BYTES = 128 * NKC * 128 * 2;
+  static constexpr int P_BYTES = 128 * NKC * 128 * 2;    // bias tile (fp16 [128][NKC*128]) first, P afterwards
   static constexpr int OFF_K = Q_BYTES, OFF_V = OFF_K + KV_BYTES, OFF_P = OFF_V + KV_BYTES;
-  static constexpr int OFF_BAR = OFF_P + P_BYTES;
-  static constexpr int SMEM_BYTES = OFF_BAR + 64 + 1024;
+  static constexpr int OFF_ID = OFF_P + P_BYTES;
+  static constexpr int OFF_BAR = OFF_ID + (BMMA ? kIdentBytes : 0);
+  static constexpr int SMEM_BYTES = OFF_BAR + 64;        // the dynamic window itself is 1024-byte aligned (checked)
   static constexpr int TMEM_COLS = (NKC * 128 <= 256) ? 256 : 512;
   static constexpr uint32_t SWZ = (HD == 64) ? SWZ_128B : SWZ_64B;
   static constexpr uint32_t SBO = 8 * ROWB;              // 8-row core-matrix group stride for Q/K/V tiles
 };
 
-template <int HD, int NKC>
+template <int HD, int NKC, bool BMMA>
 __global__ void __launch_bounds__(kAttnThreads)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p) {
-  using Cfg = AttnFwdCfg<HD, NKC>;
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmBias,
+                const AttnFwdParams p) {
+  using Cfg = AttnFwdCfg<HD, NKC, BMMA>;
   constexpr int NP = NKC * 128;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // swizzled TMA / UMMA tiles need the 1024-byte alignment
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);  // 0 load, 1 S ready, 2 P ready, 3 O ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
@@ -56,9 +65,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
   const int t = blockIdx.x, h = blockIdx.y, prob = blockIdx.z;
   const int row0 = prob * p.L;  // first token row of this problem
 
+  if (BMMA && warp < 4) {
+    // identity strip: zero groups with one 16 x 16 identity block at groups 14-15 (K-major, no swizzle:
+    // group g = [8 rows x k 0..7 | 8 rows x k 8..15], 16 bytes per row and core matrix)
+    uint8_t* id = smem + Cfg::OFF_ID;
+    for (int i = threadIdx.x; i < kIdentBytes / 16; i += 128) reinterpret_cast<uint4*>(id)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncwarp();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (threadIdx.x < 16) {
+      const int r = threadIdx.x;
+      const int off = r < 8 ? 14 * 256 + r * 16 + r * 2 : 15 * 256 + 128 + (r - 8) * 16 + (r - 8) * 2;
+      *reinterpret_cast<__half*>(id + off) = __float2half_rn(1.0f);
+    }
+    fence_proxy_async_smem();
+  }
   if (warp == 4) {
     if (lane == 0) {
       tma_prefetch_desc(&tmQKV);
+      if (BMMA) tma_prefetch_desc(&tmBias);
       mbar_init(bars + 0, 1);
       mbar_init(bars + 1, 1);
       mbar_init(bars + 2, 128);
@@ -76,7 +100,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
   if (warp == 4) {
     if (lane == 0) {
       // ---- loads
-      mbar_arrive_expect_tx(bars + 0, Cfg::Q_BYTES + 2 * Cfg::KV_BYTES);
+      mbar_arrive_expect_tx(bars + 0, Cfg::Q_BYTES + 2 * Cfg::KV_BYTES + (BMMA ? Cfg::P_BYTES : 0));
+      if (BMMA) {  // bias tile rows t*128.., all NP key columns: NP/64 boxes of [128 rows x 64 columns]
+        const int cls = p.prob_class ? p.prob_class[prob % p.period] : 0;
+        const int brow = (cls * p.nheads + h) * p.NPb + t * 128;
+#pragma unroll
+        for (int jb = 0; jb < NP / 64; ++jb)
+          tma_load_2d(smem + Cfg::OFF_P + jb * 16384, &tmBias, bars + 0, jb * 64, brow);
+      }
       tma_load_2d(smem, &tmQKV, bars + 0, p.q_off + h * HD, row0 + t * 128);
 #pragma unroll
       for (int c = 0; c < NKC; ++c) {
@@ -94,6 +125,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
         for (int k = 0; k < HD / 16; ++k)
           umma_f16_ss(tmem + c * 128, make_smem_desc(sq + k * 32, 0, Cfg::SBO, Cfg::SWZ),
                       make_smem_desc(sk + c * 128 * Cfg::ROWB + k * 32, 0, Cfg::SBO, Cfg::SWZ), idesc_s, k > 0);
+      if (BMMA) {  // S += I * Bias: A = identity slice (K-major, no swizzle), B = bias tile (MN-major, 128B swizzle)
+        constexpr uint32_t idesc_b = make_idesc_f16(128, 128, 0, 1);
+        const uint32_t sid = smem_u32(smem + Cfg::OFF_ID), sbias = smem_u32(smem + Cfg::OFF_P);
+#pragma unroll
+        for (int c = 0; c < NKC; ++c)
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_f16_ss(tmem + c * 128, make_smem_desc(sid + (14 - 2 * kk) * 256, 128, 256, SWZ_NONE),
+                        make_smem_desc(sbias + c * 32768 + kk * 2048, 16384, 1024, SWZ_128B), idesc_b, 1u);
+      }
       umma_commit(bars + 1);
       // ---- O = P V  (M=128, N=HD, K=NP; A = P K-major 128B swizzle, B = V MN-major)
       mbar_wait(bars + 2, 0, 11);
@@ -113,7 +154,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
     const float sc = p.scale;
     const __half* brow = nullptr;
-    if (p.bias16) {
+    if (!BMMA && p.bias16) {
       const int cls = p.prob_class ? p.prob_class[prob % p.period] : 0;
       brow = p.bias16 + (((size_t)cls * p.nheads + h) * p.NPb + min(qi, p.NPb - 1)) * p.NPb;
     }
@@ -226,39 +267,51 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
   if (warp == 4) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
 }
 
-template <int HD, int NKC>
-static int launch_attn_fwd(const void* qkv, int64_t ld, int64_t rows_total, const AttnFwdParams& p, cudaStream_t s) {
-  using Cfg = AttnFwdCfg<HD, NKC>;
-  CUtensorMap tm;
+template <int HD, int NKC, bool BMMA>
+static int launch_attn_fwd(const void* qkv, int64_t ld, int64_t rows_total, const AttnFwdParams& p, int ncls,
+                           cudaStream_t s) {
+  using Cfg = AttnFwdCfg<HD, NKC, BMMA>;
+  CUtensorMap tm, tmb;
   int rc = encode_tmap_2d_f16(&tm, qkv, rows_total, ld, ld, 128, HD,
                               HD == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc) return rc;
-  auto kern = attn_fwd_kernel<HD, NKC>;
+  tmb = tm;
+  if (BMMA) {
+    rc = encode_tmap_2d_f16(&tmb, p.bias16, (uint64_t)ncls * p.nheads * p.NPb, p.NPb, p.NPb, 128, 64,
+                            CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  auto kern = attn_fwd_kernel<HD, NKC, BMMA>;
   static bool attr_set = false;
   if (!attr_set) {
     LAV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   dim3 grid((p.L + 127) / 128, p.nheads, p.nprob);
-  kern<<<grid, kAttnThreads, Cfg::SMEM_BYTES, s>>>(tm, p);
+  kern<<<grid, kAttnThreads, Cfg::SMEM_BYTES, s>>>(tm, tmb, p);
   LAV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return LAV_OK;
 }
 
-// dense[cls][h][i][j] = table[rel_index(i,j)][h] + (label[cls][i] != label[cls][j] ? -100 : 0), -inf for j >= L
-// (video_swin.py:153-160, compute_mask :290-305).  rel_index is passed in (int32 [L][L], the [:N,:N] slice).
+// dense[cls][h][i][j] = (table[rel_index(i,j)][h] + (label[cls][i] != label[cls][j] ? -100 : 0)) * inv_scale, and
+// kMaskedKey for the padded key columns j >= L (video_swin.py:153-160, compute_mask :290-305).  rel_index is passed in
+// (int32 [L][L], the [:N,:N] slice).  inv_scale = 1 / softmax scale: the attention kernels add the tile to the RAW
+// Q K^T accumulator (by an identity MMA) and apply `scale` to the sum.  kMaskedKey is finite on purpose: the identity
+// MMA multiplies every bias element by 0 or 1 and 0 * -inf would be NaN; exp() of it is exactly 0 all the same.
+constexpr float kMaskedKey = -30000.0f;
 __global__ void relpos_bias_expand_kernel(const float* table, int nheads, const int32_t* rel_index, int L,
-                                          const uint8_t* labels, int ncls, __half* dense, int NP) {
+                                          const uint8_t* labels, int ncls, __half* dense, int NP, float inv_scale) {
   const int i = blockIdx.x, h = blockIdx.y, cls = blockIdx.z;
   __half* drow = dense + (((size_t)cls * nheads + h) * NP + i) * NP;
   for (int j = threadIdx.x; j < NP; j += blockDim.x) {
     float v;
-    if (j >= L) v = -INFINITY;
+    if (j >= L) v = kMaskedKey;
     else if (i >= L) v = 0.f;
     else {
       v = table[(size_t)rel_index[i * L + j] * nheads + h];
       if (labels && labels[cls * NP + i] != labels[cls * NP + j]) v += -100.0f;
+      v *= inv_scale;
     }
     drow[j] = __float2half_rn(v);
   }
@@ -283,24 +336,28 @@ extern "C" int lav_attn_fwd_f16(const void* qkv, int64_t ld, int64_t rows_total,
   p.key_bias = key_bias, p.out = (__half*)out16, p.ldo = ldo, p.lse = lse, p.rows_total = rows_total;
   p.drop = make_drop(drop);
   cudaStream_t s = (cudaStream_t)stream;
+  const int ncls = 8;  // row extent of the bias tensor map: an upper bound on the classes a dense tensor holds (2^3
+                       // shifted axes); only the classes named by prob_class are ever addressed
   if (head_dim == 32 && L <= 256) {
     LAV_REQUIRE(!bias16 || NPb == 256, "lav_attn_fwd_f16: dense bias must be [*, *, 256, 256] for L <= 256");
-    return launch_attn_fwd<32, 2>(qkv, ld, rows_total, p, s);
+    if (bias16) return launch_attn_fwd<32, 2, true>(qkv, ld, rows_total, p, ncls, s);
+    return launch_attn_fwd<32, 2, false>(qkv, ld, rows_total, p, ncls, s);
   }
   if (head_dim == 64 && L <= 384) {
-    LAV_REQUIRE(!bias16 || NPb == 384, "lav_attn_fwd_f16: dense bias must be [*, *, 384, 384] for L <= 384");
-    return launch_attn_fwd<64, 3>(qkv, ld, rows_total, p, s);
+    LAV_REQUIRE(!bias16, "lav_attn_fwd_f16: a dense bias is supported for head_dim 32 only (BERT passes key_bias)");
+    return launch_attn_fwd<64, 3, false>(qkv, ld, rows_total, p, ncls, s);
   }
   return set_error(LAV_E_INVALID, "lav_attn_fwd_f16: unsupported (head_dim=%d, L=%d); supported: hd32 L<=256, hd64 L<=384",
                    head_dim, L);
 }
 
 extern "C" int lav_relpos_bias_expand(const float* table, int nheads, const int32_t* rel_index, int L,
-                                      const uint8_t* labels, int ncls, void* dense16, int NP, void* stream) {
+                                      const uint8_t* labels, int ncls, void* dense16, int NP, float inv_scale,
+                                      void* stream) {
   LAV_REQUIRE(table && rel_index && dense16 && ncls >= 1 && L <= NP, "lav_relpos_bias_expand: bad arguments");
   dim3 grid(NP, nheads, ncls);
   relpos_bias_expand_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(table, nheads, rel_index, L, labels, ncls,
-                                                                   (__half*)dense16, NP);
+                                                                   (__half*)dense16, NP, inv_scale);
   LAV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return LAV_OK;

@@ -113,6 +113,10 @@ __device__ __forceinline__ float4 load_dy4(const LnBwdParams& p, int r, int col)
   return make_float4(a.x, a.y, b.x, b.y);
 }
 
+// PARAMS: also accumulate dgamma / dbeta (G == 1, C <= 1024): every lane keeps the partial sums of its columns over
+// the rows its warp walks, the 8 warps of a block meet in shared memory and the block issues one atomic per column -
+// the separate parameter-gradient pass (a second read of x and dy) disappears.
+template <bool PARAMS>
 __global__ void __launch_bounds__(kRowThreads) ln_bwd_kernel(const LnBwdParams p) {
   const int lane = threadIdx.x & 31;
   const int wpb = kRowThreads / 32;
@@ -120,6 +124,11 @@ __global__ void __launch_bounds__(kRowThreads) ln_bwd_kernel(const LnBwdParams p
   const int c4 = p.C >> 2;
   DropKey dkey{};
   if (p.drop.on) dkey = drop_key(p.drop);
+  float4 ag[PARAMS ? 8 : 1], ab[PARAMS ? 8 : 1];
+  if (PARAMS) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ag[k] = make_float4(0.f, 0.f, 0.f, 0.f), ab[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < p.rows; r += gridDim.x * wpb) {
     int64_t srow[4];
 #pragma unroll
@@ -127,20 +136,40 @@ __global__ void __launch_bounds__(kRowThreads) ln_bwd_kernel(const LnBwdParams p
       if (g < p.G) srow[g] = p.map ? p.map[(int64_t)r * p.G + g] : (int64_t)r * p.G + g;
     const float mean = p.mean[r], rstd = p.rstd[r];
     float s1 = 0.f, s2 = 0.f;
+    if (PARAMS) {  // G == 1
 #pragma unroll
-    for (int g = 0; g < 4; ++g)
-      if (g < p.G)
-        for (int i = lane; i < c4; i += 32) {
-          const int col = g * p.C + i * 4;
-          float4 v = *reinterpret_cast<const float4*>(p.x + srow[g] * p.ldx + i * 4);
-          float4 d = load_dy4(p, r, col);
-          float4 ga = *reinterpret_cast<const float4*>(p.gamma + col);
+      for (int k = 0; k < 8; ++k) {
+        const int i = lane + 32 * k;
+        if (i < c4) {
+          float4 v = *reinterpret_cast<const float4*>(p.x + srow[0] * p.ldx + i * 4);
+          float4 d = load_dy4(p, r, i * 4);
+          float4 ga = *reinterpret_cast<const float4*>(p.gamma + i * 4);
           float a0 = d.x * ga.x, a1 = d.y * ga.y, a2 = d.z * ga.z, a3 = d.w * ga.w;
+          const float x0 = (v.x - mean) * rstd, x1 = (v.y - mean) * rstd, x2 = (v.z - mean) * rstd, x3 = (v.w - mean) * rstd;
           s1 += (a0 + a1) + (a2 + a3);
-          s2 += (a0 * (v.x - mean) + a1 * (v.y - mean)) + (a2 * (v.z - mean) + a3 * (v.w - mean));
+          s2 += (a0 * x0 + a1 * x1) + (a2 * x2 + a3 * x3);
+          ag[k].x += d.x * x0, ag[k].y += d.y * x1, ag[k].z += d.z * x2, ag[k].w += d.w * x3;
+          ab[k].x += d.x, ab[k].y += d.y, ab[k].z += d.z, ab[k].w += d.w;
         }
-    s1 = warp_sum(s1) / W;
-    s2 = warp_sum(s2) * rstd / W;  // mean_c(a * xhat)
+      }
+      s1 = warp_sum(s1) / W;
+      s2 = warp_sum(s2) / W;  // mean_c(a * xhat)
+    } else {
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        if (g < p.G)
+          for (int i = lane; i < c4; i += 32) {
+            const int col = g * p.C + i * 4;
+            float4 v = *reinterpret_cast<const float4*>(p.x + srow[g] * p.ldx + i * 4);
+            float4 d = load_dy4(p, r, col);
+            float4 ga = *reinterpret_cast<const float4*>(p.gamma + col);
+            float a0 = d.x * ga.x, a1 = d.y * ga.y, a2 = d.z * ga.z, a3 = d.w * ga.w;
+            s1 += (a0 + a1) + (a2 + a3);
+            s2 += (a0 * (v.x - mean) + a1 * (v.y - mean)) + (a2 * (v.z - mean) + a3 * (v.w - mean));
+          }
+      s1 = warp_sum(s1) / W;
+      s2 = warp_sum(s2) * rstd / W;  // mean_c(a * xhat)
+    }
 #pragma unroll
     for (int g = 0; g < 4; ++g)
       if (g < p.G)
@@ -169,6 +198,28 @@ __global__ void __launch_bounds__(kRowThreads) ln_bwd_kernel(const LnBwdParams p
                 make_uint2(pack_half2(o.x, o.y), pack_half2(o.z, o.w));
           }
         }
+  }
+  if (PARAMS) {
+    // block reduction of the per-lane column sums: [8 warps][C] floats, dgamma first, then dbeta through the same buffer
+    extern __shared__ float red[];
+    const int wy = threadIdx.x >> 5;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = lane + 32 * k;
+        if (i < c4) *reinterpret_cast<float4*>(red + wy * p.C + i * 4) = pass == 0 ? ag[k] : ab[k];
+      }
+      __syncthreads();
+      float* dst = pass == 0 ? p.dgamma : p.dbeta;
+      for (int c = threadIdx.x; c < p.C; c += kRowThreads) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w * p.C + c];
+        atomicAdd(dst + c, t);
+      }
+    }
   }
 }
 
@@ -356,6 +407,20 @@ extern "C" int lav_layernorm_bwd(const void* dy, int64_t lddy, int dy_is_f32, co
                 dx32, lddx32, (__half*)dx16, lddx16, dgamma, dbeta, rows, make_drop(drop16)};
   LAV_REQUIRE(!p.drop.on || (dx16 && G == 1), "lav_layernorm_bwd: drop16 needs dx16 and G == 1");
   cudaStream_t s = (cudaStream_t)stream;
+  if (dgamma && G == 1 && C <= 1024) {
+    // fused: few fat blocks (each warp walks many rows) so the per-block column reduction amortises
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((rows + 7) / 8, (int64_t)sm_count() * 2));
+    const size_t red_bytes = (size_t)8 * C * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+      LAV_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024 * 4));
+      attr_set = true;
+    }
+    ln_bwd_kernel<true><<<grid, kRowThreads, red_bytes, s>>>(p);
+    LAV_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return LAV_OK;
+  }
   if (dgamma) {  // must read x before an in-place dx32 overwrite of the same rows
     const int cb = (G * C + 127) / 128;
     const int rpb = slab_rows(rows, cb);
@@ -364,7 +429,7 @@ extern "C" int lav_layernorm_bwd(const void* dy, int64_t lddy, int dy_is_f32, co
     LAV_CHECK_CUDA(cudaGetLastError());
     count_launch();
   }
-  ln_bwd_kernel<<<row_grid(rows), kRowThreads, 0, s>>>(p);
+  ln_bwd_kernel<false><<<row_grid(rows), kRowThreads, 0, s>>>(p);
   LAV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return LAV_OK;

@@ -173,12 +173,13 @@ def attn_bwd(qkv, out, dout, lse, dq_acc, dqkv, *, q_off, k_off, v_off, head_dim
     L.check(rc, "lav_attn_bwd_f16")
 
 
-def relpos_bias_expand(table, rel_index, L_tok, labels, dense16):
-    """dense16: [ncls, nheads, NP, NP] fp16; labels: uint8 [ncls, NP] or None."""
+def relpos_bias_expand(table, rel_index, L_tok, labels, dense16, scale):
+    """dense16: [ncls, nheads, NP, NP] fp16 = (bias + shift mask) / scale; labels: uint8 [ncls, NP] or None;
+    `scale` is the softmax scale later passed to attn_fwd / attn_bwd."""
     ncls, nheads, NP, _ = dense16.shape
     with _Timed("relpos_expand"):
         rc = L.lib().lav_relpos_bias_expand(_p(table), nheads, _p(rel_index), L_tok, _p(labels), ncls, _p(dense16), NP,
-                                            _stream())
+                                            1.0 / float(scale), _stream())
     L.check(rc, "lav_relpos_bias_expand")
 
 

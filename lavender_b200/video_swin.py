@@ -387,7 +387,7 @@ def _block_fwd(ar, blk, x, M, C, N, NP, nprob, rmap, labels, cls_of, k1, k2, rps
     rel = _rel_index(at, N, dev)
     ncls = labels.shape[0] if labels is not None else 1
     dense = empty16(ncls, nh, NP, NP, device=dev)
-    ops.relpos_bias_expand(at.relative_position_bias_table, rel, N, labels, dense)
+    ops.relpos_bias_expand(at.relative_position_bias_table, rel, N, labels, dense, at.scale)
     o16 = empty16(M, C, device=dev)
     lse = empty32(nh, M, device=dev)
     ops.attn_fwd(qkv16, o16, lse, q_off=0, k_off=C, v_off=2 * C, head_dim=hd, nheads=nh, nprob=nprob, L_tok=N,

@@ -42,10 +42,10 @@ def test_window_attention_fwd_bwd(nimg, nW, nheads, shifted):
     qkv, table, rel, lab, cls, mask, nprob, L, hd, C = _window_case(nimg, nW, nheads, shifted)
     ncls = 4 if shifted else 1
     dense = torch.zeros(ncls, nheads, 256, 256, device="cuda", dtype=torch.float16)
-    ops.relpos_bias_expand(table, rel, L, lab, dense)
+    scale = hd ** -0.5
+    ops.relpos_bias_expand(table, rel, L, lab, dense, scale)
     out = torch.zeros(nprob * L, C, device="cuda", dtype=torch.float16)
     lse = torch.zeros(nheads, nprob * L, device="cuda")
-    scale = hd ** -0.5
     ops.attn_fwd(qkv, out, lse, q_off=0, k_off=C, v_off=2 * C, head_dim=hd, nheads=nheads, nprob=nprob, L_tok=L,
                  scale=scale, bias16=dense, prob_class=cls)
     torch.cuda.synchronize()
@@ -55,7 +55,8 @@ def test_window_attention_fwd_bwd(nimg, nW, nheads, shifted):
     x = qkv.float().view(nprob, L, 3, nheads, hd).permute(2, 0, 3, 1, 4).clone().requires_grad_(True)
     q, k, v = x[0], x[1], x[2]
     bias = t[rel.long().view(-1)].view(L, L, nheads).permute(2, 0, 1)
-    s = (q @ k.transpose(-1, -2)) * scale + bias.half().float().detach() + (bias - bias.detach())
+    # the kernel's dense table holds fp16(bias / scale) and the sum is scaled afterwards
+    s = (q @ k.transpose(-1, -2)) * scale + (bias / scale).half().float().detach() * scale + (bias - bias.detach())
     if shifted:
         s = s.view(nimg, nW, nheads, L, L) + mask.view(1, nW, 1, L, L)
         s = s.view(nprob, nheads, L, L)
