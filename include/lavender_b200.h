@@ -160,13 +160,15 @@ int lav_colsum_f16(const void* x16, int64_t ld, int rows, int N, float* out, flo
  *     [ncls][nheads][256][256] fp16 tensor of lav_relpos_bias_expand built with inv_scale = 1 / scale (relative
  *     position bias :153-155 + shift mask :157-160 + masked padded keys); problem p uses class
  *     prob_class[p % class_period] (ncls <= 8).
- *   - HF BertSelfAttention (model.py:242): head_dim 64, L <= 384; key_bias is the additive [nprob][384] fp32
- *     row (0 for kept keys, -inf for masked / padded keys) of get_extended_attention_mask (model.py:239).
+ *   - HF BertSelfAttention (model.py:242): head_dim 64, any L (blocked online-softmax kernel, 128-key blocks);
+ *     key_bias is the additive [nprob][NPk] fp32 row (0 for kept keys, -inf for masked / padded keys; NPk >= L
+ *     rounded up to 128) of get_extended_attention_mask (model.py:239).
+ *   - windows longer than 256 tokens (8 x 12 x 12 -> 720 at 384^2) use the same blocked kernel with the dense bias.
  * Writes O (fp16, [rows_total, ldo], head h at column h*head_dim) and lse[h][row] = log-sum-exp (fp32). */
 int lav_attn_fwd_f16(const void* qkv, int64_t ld, int64_t rows_total, int q_off, int k_off, int v_off, int head_dim,
                      int nheads, int nprob, int L, float scale, const void* bias16, int NPb,
-                     const int32_t* prob_class, int class_period, const float* key_bias, void* out16, int64_t ldo,
-                     float* lse, const LavDropout* drop, void* stream);
+                     const int32_t* prob_class, int class_period, const float* key_bias, int NPk, void* out16,
+                     int64_t ldo, float* lse, const LavDropout* drop, void* stream);
 /* drop (may be NULL): dropout of the attention probabilities (HF BertSelfAttention.dropout), element index
  * (global query row, key column, head); lse is that of the un-dropped softmax. */
 

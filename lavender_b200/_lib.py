@@ -58,7 +58,7 @@ SIGNATURES = {
     "lav_gelu_bwd_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "lav_colsum_f16": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_float, c_void_p]),
     "lav_attn_fwd_f16": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
-                                 c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p,
+                                 c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64, c_void_p,
                                  ctypes.POINTER(Dropout), c_void_p]),
     "lav_attn_bwd_f16": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                                  c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64, c_void_p,

@@ -203,7 +203,7 @@ class BertEncoder(nn.Module):
     def forward(self, hidden_states, attention_mask=None, output_attentions=False, **unused):
         require_cuda(hidden_states, "BertEncoder")
         B, Lq, H = hidden_states.shape
-        NPk = 384 if Lq <= 384 else (Lq + 127) // 128 * 128   # the forward kernel reads [nprob][384] rows (lavender_b200.h)
+        NPk = (Lq + 127) // 128 * 128
         kb = torch.full((B, NPk), NEG_INF, dtype=F32, device=hidden_states.device)
         if attention_mask is None:
             kb[:, :Lq] = 0.0

@@ -65,6 +65,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const int c = blockIdx.x, h = blockIdx.y, prob = blockIdx.z;
   const int row0 = prob * p.L;
   const int nqt = (p.L + 127) / 128;
+  const int jmax = min(128, (p.L - c * 128 + 31) & ~31);  // key columns of this chunk that can hold a valid key
 
   if (BMMA && warp < 4) {  // identity strip (zeros with a 16 x 16 identity block at groups 14-15), as in attention_fwd.cu
     uint8_t* id = smem + Cfg::OFF_ID;
@@ -119,7 +120,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       load_q(0);
       if (nqt > 1) load_q(1);
       mbar_wait(bars + 0, 0, 20);
-      constexpr uint32_t id_s = make_idesc_f16(128, 128, 0, 0);   // S / dP : K-major x K-major
+      const uint32_t id_s = make_idesc_f16(128, jmax, 0, 0);      // S / dP : K-major x K-major, narrow last chunk
       constexpr uint32_t id_t = make_idesc_f16(128, HD, 1, 1);    // dV / dK: MN-major A (P/dS transposed), MN-major B
       constexpr uint32_t id_q = make_idesc_f16(128, HD, 0, 1);    // dQ     : K-major A (dS), MN-major B (K)
       const uint32_t sk = smem_u32(smem + Cfg::OFF_K), sv = smem_u32(smem + Cfg::OFF_V);
@@ -158,8 +159,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           umma_f16_ss(tmem + Cfg::COL_DK, make_smem_desc(sds + k * 2048, 16384, 1024, SWZ_128B), b_q, id_t,
                       (t > 0 || k > 0));
         }
-#pragma unroll
-        for (int k = 0; k < 8; ++k)  // contraction over the 128 keys of this chunk
+#pragma unroll 4
+        for (int k = 0; k < jmax / 16; ++k)  // contraction over the (valid) keys of this chunk
           umma_f16_ss(tmem + Cfg::COL_DQ, make_smem_desc(sds + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024, SWZ_128B),
                       make_smem_desc(sk + k * 16 * Cfg::ROWB, 0, Cfg::SBO, Cfg::SWZ), id_q, k > 0);
         umma_commit(bars + 5);
@@ -207,7 +208,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       mbar_wait(bars + 3, t & 1, 24);
       tc_fence_after();
 #pragma unroll 1
-      for (int j0 = 0; j0 < 128; j0 += 32) {
+      for (int j0 = 0; j0 < jmax; j0 += 32) {
         uint32_t s[32], dp[32];
         tmem_ld_32x32(trow + Cfg::COL_S + j0, s);
         tmem_ld_32x32(trow + Cfg::COL_DP + j0, dp);

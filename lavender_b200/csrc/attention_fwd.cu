@@ -12,6 +12,8 @@
 //     shared-memory strip (a 16 x 16 identity block between zero rows, addressed through a sliding UMMA descriptor);
 //     the bias tile's shared memory is then reused for P.  BERT passes an additive per-key fp32 row instead.
 // Nothing of size [B_, nh, N, N] ever reaches HBM.
+#include <cstdlib>
+
 #include "rng.cuh"
 #include "runtime.h"
 #include "sm100.cuh"
@@ -64,6 +66,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x, h = blockIdx.y, prob = blockIdx.z;
   const int row0 = prob * p.L;  // first token row of this problem
+  const int ncol = min(NP, (p.L + 31) & ~31);  // key columns that can hold a valid key (BERT: 283 -> 288 of 384)
 
   if (BMMA && warp < 4) {
     // identity strip: zero groups with one 16 x 16 identity block at groups 14-15 (K-major, no swizzle:
@@ -117,14 +120,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       mbar_wait(bars + 0, 0, 10);
       tc_fence_after();
       // ---- S_c = Q K_cᵀ  (M=128, N=128, K=HD; both operands K-major)
-      constexpr uint32_t idesc_s = make_idesc_f16(128, 128, 0, 0);
       const uint32_t sq = smem_u32(smem), sk = smem_u32(smem + Cfg::OFF_K);
 #pragma unroll
-      for (int c = 0; c < NKC; ++c)
+      for (int c = 0; c < NKC; ++c) {
+        const int nc = min(128, ncol - c * 128);  // the last chunk may be narrow (MMA N is any multiple of 16)
+        if (nc <= 0) break;
+        const uint32_t idesc_s = make_idesc_f16(128, nc, 0, 0);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
           umma_f16_ss(tmem + c * 128, make_smem_desc(sq + k * 32, 0, Cfg::SBO, Cfg::SWZ),
                       make_smem_desc(sk + c * 128 * Cfg::ROWB + k * 32, 0, Cfg::SBO, Cfg::SWZ), idesc_s, k > 0);
+      }
       if (BMMA) {  // S += I * Bias: A = identity slice (K-major, no swizzle), B = bias tile (MN-major, 128B swizzle)
         constexpr uint32_t idesc_b = make_idesc_f16(128, 128, 0, 1);
         const uint32_t sid = smem_u32(smem + Cfg::OFF_ID), sbias = smem_u32(smem + Cfg::OFF_P);
@@ -132,7 +138,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         for (int c = 0; c < NKC; ++c)
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            umma_f16_ss(tmem + c * 128, make_smem_desc(sid + (14 - 2 * kk) * 256, 128, 256, SWZ_NONE),
+            if (c * 128 < ncol)
+              umma_f16_ss(tmem + c * 128, make_smem_desc(sid + (14 - 2 * kk) * 256, 128, 256, SWZ_NONE),
                         make_smem_desc(sbias + c * 32768 + kk * 2048, 16384, 1024, SWZ_128B), idesc_b, 1u);
       }
       umma_commit(bars + 1);
@@ -141,8 +148,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       tc_fence_after();
       constexpr uint32_t idesc_o = make_idesc_f16(128, HD, 0, 1);
       const uint32_t sp = smem_u32(smem + Cfg::OFF_P), sv = smem_u32(smem + Cfg::OFF_V);
-#pragma unroll
-      for (int k = 0; k < NP / 16; ++k)
+#pragma unroll 4
+      for (int k = 0; k < ncol / 16; ++k)
         umma_f16_ss(tmem, make_smem_desc(sp + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024, SWZ_128B),
                     make_smem_desc(sv + k * 16 * Cfg::ROWB, 0, Cfg::SBO, Cfg::SWZ), idesc_o, k > 0);
       umma_commit(bars + 3);
@@ -190,7 +197,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     tc_fence_after();
     float m = -INFINITY;
 #pragma unroll 1
-    for (int j0 = 0; j0 < NP; j0 += 32) {
+    for (int j0 = 0; j0 < ncol; j0 += 32) {
       uint32_t s[32];
       float v[32];
       tmem_ld_32x32(trow + j0, s);
@@ -204,7 +211,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     float l = 0.f;
     uint8_t* prow = smem + Cfg::OFF_P + i * 128;
 #pragma unroll 1
-    for (int j0 = 0; j0 < NP; j0 += 32) {
+    for (int j0 = 0; j0 < ncol; j0 += 32) {
       uint32_t s[32];
       float v[32];
       tmem_ld_32x32(trow + j0, s);
@@ -317,14 +324,19 @@ __global__ void relpos_bias_expand_kernel(const float* table, int nheads, const 
   }
 }
 
+int attn_fwd_flash(const void* qkv, int64_t ld, int64_t rows_total, int q_off, int k_off, int v_off, int head_dim,
+                   int nheads, int nprob, int L, float scale, const void* bias16, int NPb, const int32_t* prob_class,
+                   int class_period, const float* key_bias, int NPk, void* out16, int64_t ldo, float* lse,
+                   const LavDropout* drop, cudaStream_t s);  // attention_flash.cu
+
 }  // namespace lav
 
 using namespace lav;
 
 extern "C" int lav_attn_fwd_f16(const void* qkv, int64_t ld, int64_t rows_total, int q_off, int k_off, int v_off,
                                 int head_dim, int nheads, int nprob, int L, float scale, const void* bias16, int NPb,
-                                const int32_t* prob_class, int class_period, const float* key_bias, void* out16,
-                                int64_t ldo, float* lse, const LavDropout* drop, void* stream) {
+                                const int32_t* prob_class, int class_period, const float* key_bias, int NPk,
+                                void* out16, int64_t ldo, float* lse, const LavDropout* drop, void* stream) {
   LAV_REQUIRE(qkv && out16, "lav_attn_fwd_f16: null pointer");
   LAV_REQUIRE(nprob > 0 && nheads > 0 && L > 0, "lav_attn_fwd_f16: empty problem");
   LAV_REQUIRE((ldo % 8) == 0 && (q_off % 8) == 0 && (k_off % 8) == 0 && (v_off % 8) == 0,
@@ -338,17 +350,22 @@ extern "C" int lav_attn_fwd_f16(const void* qkv, int64_t ld, int64_t rows_total,
   cudaStream_t s = (cudaStream_t)stream;
   const int ncls = 8;  // row extent of the bias tensor map: an upper bound on the classes a dense tensor holds (2^3
                        // shifted axes); only the classes named by prob_class are ever addressed
-  if (head_dim == 32 && L <= 256) {
+  // one-shot kernels (whole key range in TMEM): windows of <= 256 tokens; LAV_ATTN_ONESHOT=1 also routes BERT
+  // sequences of <= 384 tokens to the one-shot hd-64 kernel (one CTA per SM: A/B reference for the blocked kernel)
+  static int oneshot64 = -1;
+  if (oneshot64 < 0) {
+    const char* e = getenv("LAV_ATTN_ONESHOT");
+    oneshot64 = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (head_dim == 32 && L <= 256 && (!key_bias || NPk == 256)) {
     LAV_REQUIRE(!bias16 || NPb == 256, "lav_attn_fwd_f16: dense bias must be [*, *, 256, 256] for L <= 256");
     if (bias16) return launch_attn_fwd<32, 2, true>(qkv, ld, rows_total, p, ncls, s);
     return launch_attn_fwd<32, 2, false>(qkv, ld, rows_total, p, ncls, s);
   }
-  if (head_dim == 64 && L <= 384) {
-    LAV_REQUIRE(!bias16, "lav_attn_fwd_f16: a dense bias is supported for head_dim 32 only (BERT passes key_bias)");
+  if (oneshot64 && head_dim == 64 && L <= 384 && !bias16 && (!key_bias || NPk == 384))
     return launch_attn_fwd<64, 3, false>(qkv, ld, rows_total, p, ncls, s);
-  }
-  return set_error(LAV_E_INVALID, "lav_attn_fwd_f16: unsupported (head_dim=%d, L=%d); supported: hd32 L<=256, hd64 L<=384",
-                   head_dim, L);
+  return attn_fwd_flash(qkv, ld, rows_total, q_off, k_off, v_off, head_dim, nheads, nprob, L, scale, bias16, NPb,
+                        prob_class, class_period, key_bias, NPk, out16, ldo, lse, drop, s);
 }
 
 extern "C" int lav_relpos_bias_expand(const float* table, int nheads, const int32_t* rel_index, int L,

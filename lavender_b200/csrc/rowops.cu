@@ -116,7 +116,7 @@ __device__ __forceinline__ float4 load_dy4(const LnBwdParams& p, int r, int col)
 // PARAMS: also accumulate dgamma / dbeta (G == 1, C <= 1024): every lane keeps the partial sums of its columns over
 // the rows its warp walks, the 8 warps of a block meet in shared memory and the block issues one atomic per column -
 // the separate parameter-gradient pass (a second read of x and dy) disappears.
-template <bool PARAMS>
+template <bool PARAMS, int NV = 8>  // NV: float4 column groups per lane kept in registers (C <= 128 * NV)
 __global__ void __launch_bounds__(kRowThreads) ln_bwd_kernel(const LnBwdParams p) {
   const int lane = threadIdx.x & 31;
   const int wpb = kRowThreads / 32;
@@ -124,10 +124,10 @@ __global__ void __launch_bounds__(kRowThreads) ln_bwd_kernel(const LnBwdParams p
   const int c4 = p.C >> 2;
   DropKey dkey{};
   if (p.drop.on) dkey = drop_key(p.drop);
-  float4 ag[PARAMS ? 8 : 1], ab[PARAMS ? 8 : 1];
+  float4 ag[PARAMS ? NV : 1], ab[PARAMS ? NV : 1];
   if (PARAMS) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) ag[k] = make_float4(0.f, 0.f, 0.f, 0.f), ab[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < NV; ++k) ag[k] = make_float4(0.f, 0.f, 0.f, 0.f), ab[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < p.rows; r += gridDim.x * wpb) {
     int64_t srow[4];
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(kRowThreads) ln_bwd_kernel(const LnBwdParams p
     float s1 = 0.f, s2 = 0.f;
     if (PARAMS) {  // G == 1
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
+      for (int k = 0; k < NV; ++k) {
         const int i = lane + 32 * k;
         if (i < c4) {
           float4 v = *reinterpret_cast<const float4*>(p.x + srow[0] * p.ldx + i * 4);
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(kRowThreads) ln_bwd_kernel(const LnBwdParams p
     for (int pass = 0; pass < 2; ++pass) {
       __syncthreads();
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
+      for (int k = 0; k < NV; ++k) {
         const int i = lane + 32 * k;
         if (i < c4) *reinterpret_cast<float4*>(red + wy * p.C + i * 4) = pass == 0 ? ag[k] : ab[k];
       }
@@ -408,15 +408,21 @@ extern "C" int lav_layernorm_bwd(const void* dy, int64_t lddy, int dy_is_f32, co
   LAV_REQUIRE(!p.drop.on || (dx16 && G == 1), "lav_layernorm_bwd: drop16 needs dx16 and G == 1");
   cudaStream_t s = (cudaStream_t)stream;
   if (dgamma && G == 1 && C <= 1024) {
-    // fused: few fat blocks (each warp walks many rows) so the per-block column reduction amortises
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((rows + 7) / 8, (int64_t)sm_count() * 2));
+    // fused: the per-block column reduction (2 * C atomics per block) must amortise over the rows a block walks, and
+    // narrow rows need many resident warps to cover the load latency: blocks per SM grow as the rows get narrower
     const size_t red_bytes = (size_t)8 * C * sizeof(float);
+    const int nv = C <= 128 ? 1 : C <= 256 ? 2 : C <= 512 ? 4 : 8;
+    const int per_sm = nv == 1 ? 8 : nv == 2 ? 6 : nv == 4 ? 4 : 2;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((rows + 7) / 8, (int64_t)sm_count() * per_sm));
     static bool attr_set = false;
     if (!attr_set) {
-      LAV_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024 * 4));
+      LAV_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024 * 4));
       attr_set = true;
     }
-    ln_bwd_kernel<true><<<grid, kRowThreads, red_bytes, s>>>(p);
+    if (nv == 1) ln_bwd_kernel<true, 1><<<grid, kRowThreads, red_bytes, s>>>(p);
+    else if (nv == 2) ln_bwd_kernel<true, 2><<<grid, kRowThreads, red_bytes, s>>>(p);
+    else if (nv == 4) ln_bwd_kernel<true, 4><<<grid, kRowThreads, red_bytes, s>>>(p);
+    else ln_bwd_kernel<true, 8><<<grid, kRowThreads, red_bytes, s>>>(p);
     LAV_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return LAV_OK;

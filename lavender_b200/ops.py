@@ -155,6 +155,7 @@ def attn_fwd(qkv, out, lse, *, q_off, k_off, v_off, head_dim, nheads, nprob, L_t
       rc = L.lib().lav_attn_fwd_f16(_p(qkv), qkv.stride(0), qkv.shape[0], q_off, k_off, v_off, head_dim, nheads, nprob,
                                   L_tok, scale, _p(bias16), bias16.shape[-1] if bias16 is not None else 0,
                                   _p(prob_class), prob_class.numel() if prob_class is not None else 1, _p(key_bias),
+                                  key_bias.shape[-1] if key_bias is not None else 0,
                                   _p(out), out.stride(0), _p(lse), _drop(drop), _stream())
     L.check(rc, "lav_attn_fwd_f16")
 

@@ -84,7 +84,7 @@ def test_window_attention_fwd_bwd(nimg, nW, nheads, shifted):
     assert (dtable - t.grad).abs().max().item() < 2e-2 * t.grad.abs().max().item()
 
 
-@pytest.mark.parametrize("nseq,L", [(3, 283), (2, 284), (2, 128), (1, 384), (2, 40)])
+@pytest.mark.parametrize("nseq,L", [(3, 283), (2, 284), (2, 128), (1, 384), (2, 40), (2, 758), (1, 1000)])
 def test_bert_attention_fwd_bwd(nseq, L):
     from lavender_b200 import ops
     g = torch.Generator().manual_seed(L)
@@ -93,7 +93,8 @@ def test_bert_attention_fwd_bwd(nseq, L):
     qkv = (torch.randn(nseq * L, 3 * H, generator=g) * 0.8).half().cuda()
     keep = torch.ones(nseq, L)
     keep[0, L - 7:] = 0  # padded tail of sequence 0
-    key_bias = torch.full((nseq, 384), float("-inf"))
+    NPk = max(384, (L + 127) // 128 * 128)   # 758 = configs[3]: 5 x (1 + 12 x 12) video tokens + 33 text tokens
+    key_bias = torch.full((nseq, NPk), float("-inf"))
     key_bias[:, :L] = torch.where(keep > 0, 0.0, float("-inf"))
     key_bias = key_bias.cuda()
     out = torch.zeros(nseq * L, H, device="cuda", dtype=torch.float16)
@@ -118,3 +119,46 @@ def test_bert_attention_fwd_bwd(nseq, L):
     assert (dq_acc - gx[:, :H]).abs().max().item() < 1e-2 * scl
     assert (dqkv[:, H:2 * H].float() - gx[:, H:2 * H]).abs().max().item() < 1e-2 * scl
     assert (dqkv[:, 2 * H:].float() - gx[:, 2 * H:]).abs().max().item() < 1e-2 * scl
+
+
+def test_long_window_attention_fwd_bwd():
+    """swin_large_384_patch244_window81212 (configs[3]): windows of 5 x 12 x 12 = 720 tokens go through the blocked
+    kernel with the dense relative-position bias added by the tensor core."""
+    import lavender_oracle as O
+    from lavender_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    nprob, nheads, hd, L, NP = 2, 2, 32, 720, 768
+    C = nheads * hd
+    qkv = (torch.randn(nprob * L, 3 * C, generator=g) * 0.7).half().cuda()
+    table = (torch.randn(15 * 23 * 23, nheads, generator=g) * 0.5).cuda()
+    rel = O.relative_position_index((8, 12, 12))[:L, :L].contiguous().int().cuda()
+    scale = hd ** -0.5
+    dense = torch.zeros(1, nheads, NP, NP, device="cuda", dtype=torch.float16)
+    ops.relpos_bias_expand(table, rel, L, None, dense, scale)
+    out = torch.zeros(nprob * L, C, device="cuda", dtype=torch.float16)
+    lse = torch.zeros(nheads, nprob * L, device="cuda")
+    ops.attn_fwd(qkv, out, lse, q_off=0, k_off=C, v_off=2 * C, head_dim=hd, nheads=nheads, nprob=nprob, L_tok=L,
+                 scale=scale, bias16=dense)
+    t = table.clone().requires_grad_(True)
+    x = qkv.float().view(nprob, L, 3, nheads, hd).permute(2, 0, 3, 1, 4).clone().requires_grad_(True)
+    bias = t[rel.long().view(-1)].view(L, L, nheads).permute(2, 0, 1)
+    s = (x[0] @ x[1].transpose(-1, -2)) * scale + (bias / scale).half().float().detach() * scale + (bias - bias.detach())
+    ref = (s.softmax(-1) @ x[2]).transpose(1, 2).reshape(nprob * L, C)
+    assert (out.float() - ref).abs().max().item() < 4e-3
+    lse_ref = torch.logsumexp(s, -1).permute(1, 0, 2).reshape(nheads, nprob * L)
+    assert (lse - lse_ref).abs().max().item() < 2e-3
+    dout = (torch.randn(nprob * L, C, device="cuda") * 0.5).half()
+    ref.backward(dout.float())
+    dq_acc = torch.zeros(nprob * L, C, device="cuda")
+    dqkv = torch.zeros(nprob * L, 3 * C, device="cuda", dtype=torch.float16)
+    ds = torch.zeros(nprob, nheads, NP, NP, device="cuda", dtype=torch.float16)
+    ops.attn_bwd(qkv, out, dout, lse, dq_acc, dqkv, q_off=0, k_off=C, v_off=2 * C, head_dim=hd, nheads=nheads,
+                 nprob=nprob, L_tok=L, scale=scale, bias16=dense, ds16=ds)
+    dtable = torch.zeros_like(table)
+    ops.relpos_bias_grad(ds, rel, L, dtable)
+    gx = x.grad.permute(1, 3, 0, 2, 4).reshape(nprob * L, 3 * C)
+    scl = gx.abs().max().item()
+    assert (dq_acc - gx[:, :C]).abs().max().item() < 1e-2 * scl
+    assert (dqkv[:, C:2 * C].float() - gx[:, C:2 * C]).abs().max().item() < 1e-2 * scl
+    assert (dqkv[:, 2 * C:].float() - gx[:, 2 * C:]).abs().max().item() < 1e-2 * scl
+    assert (dtable - t.grad).abs().max().item() < 2e-2 * t.grad.abs().max().item()
