@@ -172,7 +172,8 @@ int lav_attn_fwd_f16(const void* qkv, int64_t ld, int64_t rows_total, int q_off,
 /* drop (may be NULL): dropout of the attention probabilities (HF BertSelfAttention.dropout), element index
  * (global query row, key column, head); lse is that of the un-dropped softmax. */
 
-/* Backward of the above.  dq_acc: fp32 [rows_total, nheads*head_dim], zeroed by the caller (dQ is reduced
+/* Backward of the above.  delta_ws: caller-owned fp32 [nheads][rows_total] workspace (rowsum(dO * O), filled by a
+ * small pre-pass).  dq_acc: fp32 [rows_total, nheads*head_dim], zeroed by the caller (dQ is reduced
  * over key chunks with atomics); dK and dV are written as fp16 into dqkv16 at k_off / v_off.  When ds16 is
  * given ([nprob][nheads][NPs][NPs] fp16) the gradient wrt the pre-softmax logits is stored for
  * lav_relpos_bias_grad. */
@@ -180,7 +181,7 @@ int lav_attn_bwd_f16(const void* qkv, int64_t ld, int64_t rows_total, int q_off,
                      int nheads, int nprob, int L, float scale, const void* bias16, int NPb,
                      const int32_t* prob_class, int class_period, const float* key_bias, int NPk,
                      const void* out16, int64_t ldo, const void* dout16, int64_t lddo, const float* lse,
-                     float* dq_acc, int64_t lddq, void* dqkv16, int64_t lddqkv, void* ds16, int NPs,
+                     float* delta_ws, float* dq_acc, int64_t lddq, void* dqkv16, int64_t lddqkv, void* ds16, int NPs,
                      const LavDropout* drop, void* stream);
 
 /* dense16[cls][h][i][j] = inv_scale * (table[rel_index[i*L+j]][h] + (labels[cls][i] != labels[cls][j] ? -100 : 0)),

@@ -25,6 +25,7 @@ struct AttnBwdParams {
   const __half* out; int64_t ldo;           // forward output O
   const __half* dout; int64_t lddo;         // dO
   const float* lse; int64_t rows_total;
+  const float* delta;                       // [nheads][rows_total]: rowsum(dO * O), from attn_delta_kernel
   float* dq_acc; int64_t lddq;              // fp32 [rows_total, nheads*HD], pre-zeroed
   __half* dqkv; int64_t lddqkv;             // dK / dV written at k_off / v_off
   __half* ds_out; int NPs;                  // optional [nprob][nheads][NPs][NPs]
@@ -55,6 +56,7 @@ template <int HD, bool BMMA>
 __global__ void __launch_bounds__(kAttnBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                 const __grid_constant__ CUtensorMap tmBias, const AttnBwdParams p) {
+  griddep_launch();  // dependents (GEMMs) may start their prologue under this kernel's tail
   using Cfg = AttnBwdCfg<HD, BMMA>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -125,7 +127,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       constexpr uint32_t id_q = make_idesc_f16(128, HD, 0, 1);    // dQ     : K-major A (dS), MN-major B (K)
       const uint32_t sk = smem_u32(smem + Cfg::OFF_K), sv = smem_u32(smem + Cfg::OFF_V);
       const uint32_t sp = smem_u32(smem + Cfg::OFF_P), sds = smem_u32(smem + Cfg::OFF_DS);
-      for (int t = 0; t < nqt; ++t) {
+      // S_t = Q_t K^T (+ I * Bias_t), dP_t = dO_t V^T.  Issued one query tile AHEAD: the softmax warps have consumed
+      // S / dP of tile t when they publish P / dS, so the tile-(t+1) products run under their dQ read-out.
+      auto issue_s_dp = [&](int t) {
         const int b = t & 1;
         const uint32_t sq = smem_u32(smem + Cfg::OFF_Q + b * Cfg::TILE);
         const uint32_t sdo = smem_u32(smem + Cfg::OFF_DO + b * Cfg::TILE);
@@ -148,6 +152,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           umma_f16_ss(tmem + Cfg::COL_DP, make_smem_desc(sdo + k * 32, 0, Cfg::SBO, Cfg::SWZ),
                       make_smem_desc(sv + k * 32, 0, Cfg::SBO, Cfg::SWZ), id_s, k > 0);
         umma_commit(bars + 3);
+      };
+      issue_s_dp(0);
+      for (int t = 0; t < nqt; ++t) {
+        const int b = t & 1;
+        const uint32_t sq = smem_u32(smem + Cfg::OFF_Q + b * Cfg::TILE);
+        const uint32_t sdo = smem_u32(smem + Cfg::OFF_DO + b * Cfg::TILE);
         mbar_wait(bars + 4, t & 1, 22);
         tc_fence_after();
 #pragma unroll
@@ -164,6 +174,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           umma_f16_ss(tmem + Cfg::COL_DQ, make_smem_desc(sds + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024, SWZ_128B),
                       make_smem_desc(sk + k * 16 * Cfg::ROWB, 0, Cfg::SBO, Cfg::SWZ), id_q, k > 0);
         umma_commit(bars + 5);
+        if (t + 1 < nqt) issue_s_dp(t + 1);
         if (t + 2 < nqt) {  // refill this Q/dO buffer once the MMAs above have consumed it
           mbar_wait(bars + 5, t & 1, 23);
           load_q(t + 2);
@@ -185,21 +196,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       const int qi = t * 128 + i;
       const bool valid = qi < p.L;
       float lse_l2 = 0.f, delta = 0.f;
-      if (valid) {
+      if (valid) {  // two scalars per row, requested before the wait on the tensor core
         lse_l2 = p.lse[(size_t)h * p.rows_total + row0 + qi] * 1.4426950408889634f;
-        const uint4* po = reinterpret_cast<const uint4*>(p.out + (size_t)(row0 + qi) * p.ldo + h * HD);
-        const uint4* pd = reinterpret_cast<const uint4*>(p.dout + (size_t)(row0 + qi) * p.lddo + h * HD);
-#pragma unroll
-        for (int j = 0; j < HD / 8; ++j) {
-          uint4 a = po[j], b = pd[j];
-          const __half2* ha = reinterpret_cast<const __half2*>(&a);
-          const __half2* hb = reinterpret_cast<const __half2*>(&b);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float2 fa = __half22float2(ha[q]), fb = __half22float2(hb[q]);
-            delta += fa.x * fb.x + fa.y * fb.y;
-          }
-        }
+        delta = p.delta[(size_t)h * p.rows_total + row0 + qi];
       }
       const __half* brow = (!BMMA && p.bias16) ? p.bias16 + (((size_t)cls * p.nheads + h) * p.NPb + min(qi, p.NPb - 1)) * p.NPb + c * 128
                                     : nullptr;
@@ -231,7 +230,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         }
         if (kb) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) pv[j] += __ldg(kb + j0 + j) * 1.4426950408889634f;
+          for (int j = 0; j < 8; ++j) {
+            const float4 f = __ldg(reinterpret_cast<const float4*>(kb + j0) + j);
+            pv[4 * j] += f.x * 1.4426950408889634f, pv[4 * j + 1] += f.y * 1.4426950408889634f;
+            pv[4 * j + 2] += f.z * 1.4426950408889634f, pv[4 * j + 3] += f.w * 1.4426950408889634f;
+          }
         }
         if (!p.drop.on) {
 #pragma unroll
@@ -328,10 +331,41 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   if (warp == 4) tmem_dealloc<512>(tmem);
 }
 
+// delta[h][row] = sum_d dO[row, h*HD + d] * O[row, h*HD + d]   (softmax backward's row term; one warp per row,
+// 16-byte loads, HD/8 lanes per head).  Read once here instead of once per key chunk by a single thread per row.
+template <int HD>
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const __half* o, int64_t ldo, const __half* dout, int64_t lddo, float* delta, int64_t rows, int nheads) {
+  griddep_launch();  // dependents (GEMMs) may start their prologue under this kernel's tail
+  constexpr int LPH = HD / 8;  // lanes per head
+  const int lane = threadIdx.x & 31;
+  const int C = nheads * HD;
+  for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * 8) {
+    for (int cb = 0; cb < C; cb += 256) {  // warp-uniform trip count (the shuffles below need every lane)
+      const int c0 = cb + lane * 8;
+      const bool in = c0 < C;
+      const uint4 a = in ? *reinterpret_cast<const uint4*>(o + r * ldo + c0) : make_uint4(0u, 0u, 0u, 0u);
+      const uint4 b = in ? *reinterpret_cast<const uint4*>(dout + r * lddo + c0) : make_uint4(0u, 0u, 0u, 0u);
+      const __half2* ha = reinterpret_cast<const __half2*>(&a);
+      const __half2* hb = reinterpret_cast<const __half2*>(&b);
+      float acc = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 fa = __half22float2(ha[q]), fb = __half22float2(hb[q]);
+        acc += fa.x * fb.x + fa.y * fb.y;
+      }
+#pragma unroll
+      for (int o2 = 1; o2 < LPH; o2 <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
+      if (in && (lane & (LPH - 1)) == 0) delta[(int64_t)(c0 / HD) * rows + r] = acc;
+    }
+  }
+}
+
 // dtable[rel_index[i][j]][h] += sum_p ds[p][h][i][j]   (i, j < L).  One warp per (h, i) row and slab of problems.
 __global__ void __launch_bounds__(256)
 relpos_bias_grad_kernel(const __half* ds, int nprob, int nheads, int NP, int L, const int32_t* rel_index,
                         float* dtable, int probs_per_block) {
+  griddep_launch();  // dependents (GEMMs) may start their prologue under this kernel's tail
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);  // (h, i)
   if (row >= nheads * L) return;
@@ -389,9 +423,9 @@ extern "C" int lav_attn_bwd_f16(const void* qkv, int64_t ld, int64_t rows_total,
                                 int head_dim, int nheads, int nprob, int L, float scale, const void* bias16, int NPb,
                                 const int32_t* prob_class, int class_period, const float* key_bias, int NPk,
                                 const void* out16, int64_t ldo, const void* dout16, int64_t lddo, const float* lse,
-                                float* dq_acc, int64_t lddq, void* dqkv16, int64_t lddqkv, void* ds16, int NPs,
+                                float* delta_ws, float* dq_acc, int64_t lddq, void* dqkv16, int64_t lddqkv, void* ds16, int NPs,
                                 const LavDropout* drop, void* stream) {
-  LAV_REQUIRE(qkv && out16 && dout16 && lse && dq_acc && dqkv16, "lav_attn_bwd_f16: null pointer");
+  LAV_REQUIRE(qkv && out16 && dout16 && lse && delta_ws && dq_acc && dqkv16, "lav_attn_bwd_f16: null pointer");
   LAV_REQUIRE(nprob > 0 && nheads > 0 && L > 0, "lav_attn_bwd_f16: empty problem");
   LAV_REQUIRE((ldo % 8) == 0 && (lddo % 8) == 0 && (lddqkv % 8) == 0 && (q_off % 8) == 0 && (k_off % 8) == 0 &&
                   (v_off % 8) == 0, "lav_attn_bwd_f16: offsets / ld must be multiples of 8");
@@ -408,6 +442,16 @@ extern "C" int lav_attn_bwd_f16(const void* qkv, int64_t ld, int64_t rows_total,
   p.dqkv = (__half*)dqkv16, p.lddqkv = lddqkv, p.ds_out = (__half*)ds16, p.NPs = NPs;
   p.drop = make_drop(drop);
   cudaStream_t s = (cudaStream_t)stream;
+  p.delta = delta_ws;
+  {
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((rows_total + 7) / 8, (int64_t)sm_count() * 8));
+    if (head_dim == 32)
+      attn_delta_kernel<32><<<grid, 256, 0, s>>>((const __half*)out16, ldo, (const __half*)dout16, lddo, delta_ws, rows_total, nheads);
+    else
+      attn_delta_kernel<64><<<grid, 256, 0, s>>>((const __half*)out16, ldo, (const __half*)dout16, lddo, delta_ws, rows_total, nheads);
+    LAV_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+  }
   LAV_REQUIRE((lddq % 4) == 0 && ((uintptr_t)dq_acc % 16) == 0, "lav_attn_bwd_f16: dq_acc rows must be 16-byte aligned");
   if (head_dim == 32 && bias16) return launch_attn_bwd<32, true>(qkv, ld, p, nkc, s);
   return head_dim == 32 ? launch_attn_bwd<32, false>(qkv, ld, p, nkc, s) : launch_attn_bwd<64, false>(qkv, ld, p, nkc, s);

@@ -48,6 +48,7 @@ template <int HD, bool BMMA>
 __global__ void __launch_bounds__(kFlashThreads)
 attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmBias,
                       const FlashParams p) {
+  griddep_launch();  // dependents (GEMMs) may start their prologue under this kernel's tail
   using Cfg = FlashCfg<HD, BMMA>;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();

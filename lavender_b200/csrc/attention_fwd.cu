@@ -56,6 +56,7 @@ template <int HD, int NKC, bool BMMA>
 __global__ void __launch_bounds__(kAttnThreads)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmBias,
                 const AttnFwdParams p) {
+  griddep_launch();  // dependents (GEMMs) may start their prologue under this kernel's tail
   using Cfg = AttnFwdCfg<HD, NKC, BMMA>;
   constexpr int NP = NKC * 128;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -309,6 +310,7 @@ static int launch_attn_fwd(const void* qkv, int64_t ld, int64_t rows_total, cons
 constexpr float kMaskedKey = -30000.0f;
 __global__ void relpos_bias_expand_kernel(const float* table, int nheads, const int32_t* rel_index, int L,
                                           const uint8_t* labels, int ncls, __half* dense, int NP, float inv_scale) {
+  griddep_launch();  // dependents (GEMMs) may start their prologue under this kernel's tail
   const int i = blockIdx.x, h = blockIdx.y, cls = blockIdx.z;
   __half* drow = dense + (((size_t)cls * nheads + h) * NP + i) * NP;
   for (int j = threadIdx.x; j < NP; j += blockDim.x) {

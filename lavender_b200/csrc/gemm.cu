@@ -24,6 +24,14 @@ constexpr int kEpiWarpBytes = 8192;  // >= 32 * kEpiStride * 4; four 2 KB (fp16)
 // wins on large square problems (8192^3: 1342 vs 1150 TFLOP/s) but not on the hot path's shapes, whose cost is the
 // epilogue and the per-launch prologue rather than the operand feed (profiles/r1d_gemm_sweep.md), so it is opt-in.
 static int work_streams(int ncta) { return ncta == 2 ? std::max(1, sm_count() / 2) : sm_count(); }
+static bool pdl_enabled() {  // LAV_PDL=0 disables programmatic dependent launch of the GEMM kernels
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LAV_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 static bool pair_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -194,10 +202,10 @@ __device__ __forceinline__ void epilogue_warps(const GemmParams& p, float* epi_s
   if (DROP) dkey = drop_key(p.drop);
   int iter = 0;
   for (int item = stream_id; item < total; item += nstreams, ++iter) {
-    if ((iter & 1) != wg) continue;
+    const int as = iter & 1;  // accumulator stage; BOTH warpgroups drain every tile (even / odd 32-column chunks)
     const TileCoord t = decode_tile(p, item);
     const int row_base = (t.m_blk * NCTA + rank) * BM + q * 32;
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + wg * BN;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
     const int nchunks = min(BN / 32, (p.N - t.n_blk * BN + 31) / 32);
     // output rows of this lane's 8 store-phase rows (row map resolved once per tile)
     int orow[8];
@@ -238,27 +246,27 @@ __device__ __forceinline__ void epilogue_warps(const GemmParams& p, float* epi_s
       }
     };
     uint4 cur[8], nxt[8];
-    if (use_pre) prefetch(cur, 0);
-    mbar_wait(tmem_full + wg, (iter >> 1) & 1, 4);
+    if (use_pre && wg < nchunks) prefetch(cur, wg);
+    mbar_wait(tmem_full + as, (iter >> 1) & 1, 4);
     tc_fence_after();
-    if (p.debug & 1) {
+    if ((p.debug & 1) || wg >= nchunks) {  // (a warpgroup without a chunk of a narrow tile just releases the stage)
       tc_fence_before();
-      if (NCTA == 2) mbar_arrive_cluster(tmem_empty + wg, 0);
-      else mbar_arrive(tmem_empty + wg);
+      if (NCTA == 2) mbar_arrive_cluster(tmem_empty + as, 0);
+      else mbar_arrive(tmem_empty + as);
       continue;
     }
 #pragma unroll 1
-    for (int c = 0; c < nchunks; ++c) {
+    for (int c = wg; c < nchunks; c += 2) {
       const int col0 = t.n_blk * BN + c * 32;
       const int col = col0 + 4 * cg;  // this lane's columns in the transposed (store) phases
       uint32_t acc[32];
       tmem_ld_32x32(taddr + c * 32, acc);
-      if (use_pre && c + 1 < nchunks) prefetch(nxt, c + 1);
+      if (use_pre && c + 2 < nchunks) prefetch(nxt, c + 2);
       tmem_ld_wait();
-      if (c == nchunks - 1) {  // accumulator fully read: hand the TMEM stage back to the MMA warp early
+      if (c + 2 >= nchunks) {  // accumulator fully read: hand the TMEM stage back to the MMA warp early
         tc_fence_before();
-        if (NCTA == 2) mbar_arrive_cluster(tmem_empty + wg, 0);  // the leader's MMA warp waits for both CTAs
-        else mbar_arrive(tmem_empty + wg);
+        if (NCTA == 2) mbar_arrive_cluster(tmem_empty + as, 0);  // the leader's MMA warp waits for both CTAs
+        else mbar_arrive(tmem_empty + as);
       }
       float v[32];
 #pragma unroll
@@ -378,24 +386,24 @@ __device__ __forceinline__ void epilogue_warps_tma(const GemmParams& p, const CU
   uint32_t nb = 0;
   int iter = 0;
   for (int item = stream_id; item < total; item += nstreams, ++iter) {
-    if ((iter & 1) != wg) continue;
+    const int as = iter & 1;  // accumulator stage; BOTH warpgroups drain every tile (even / odd 32-column chunks)
     const TileCoord t = decode_tile(p, item);
     const int row_base = (t.m_blk * NCTA + rank) * BM + q * 32;
     const bool rows_valid = row_base < p.M;
     const int row = row_base + lane;
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + wg * BN;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
     const int n0 = t.n_blk * BN;
     const int nchunks = min(BN / 32, (p.N - n0 + 31) / 32);
-    mbar_wait(tmem_full + wg, (iter >> 1) & 1, 4);
+    mbar_wait(tmem_full + as, (iter >> 1) & 1, 4);
     tc_fence_after();
-    if (p.debug & 1) {
+    if ((p.debug & 1) || wg >= nchunks) {  // (a warpgroup without a chunk of a narrow tile just releases the stage)
       tc_fence_before();
-      if (NCTA == 2) mbar_arrive_cluster(tmem_empty + wg, 0);
-      else mbar_arrive(tmem_empty + wg);
+      if (NCTA == 2) mbar_arrive_cluster(tmem_empty + as, 0);
+      else mbar_arrive(tmem_empty + as);
       continue;
     }
 #pragma unroll 1
-    for (int c = 0; c < nchunks; ++c) {
+    for (int c = wg; c < nchunks; c += 2) {
       const int col0 = n0 + c * 32;
       const bool full = col0 + 32 <= p.N;
       uint32_t acc[32];
@@ -419,10 +427,10 @@ __device__ __forceinline__ void epilogue_warps_tma(const GemmParams& p, const CU
         }
       }
       tmem_ld_wait();
-      if (c == nchunks - 1) {  // accumulator fully read: hand the TMEM stage back to the MMA warp early
+      if (c + 2 >= nchunks) {  // this warpgroup's last chunk is read: hand its share of the TMEM stage back early
         tc_fence_before();
-        if (NCTA == 2) mbar_arrive_cluster(tmem_empty + wg, 0);
-        else mbar_arrive(tmem_empty + wg);
+        if (NCTA == 2) mbar_arrive_cluster(tmem_empty + as, 0);
+        else mbar_arrive(tmem_empty + as);
       }
       float v[32];
       if (e.alpha != 1.0f) {
@@ -497,7 +505,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tmem_full + s, 1);
-      mbar_init(tmem_empty + s, 128 * NCTA);
+      mbar_init(tmem_empty + s, 256 * NCTA);
     }
     fence_barrier_init();
   }
@@ -510,6 +518,10 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) touches no global data and
+  // may overlap the tail of the previous kernel; from here on operands / outputs of earlier kernels are accessed.
+  griddep_launch();
+  griddep_wait();
 
   const int total = p.m_blocks * p.n_blocks * p.splits;
 
@@ -682,11 +694,20 @@ static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, G
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = NCTA, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (NCTA == 2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = NCTA, attr[na].val.clusterDim.y = 1, attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {  // start this kernel's prologue under the previous kernel's tail (griddepcontrol.wait in the kernel)
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = NCTA == 2 ? 1 : 0;
+  cfg.numAttrs = na;
   LAV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, tmAux, p));
   count_launch();
   return LAV_OK;

@@ -29,6 +29,7 @@ struct LnFwdParams {
 };
 
 __global__ void __launch_bounds__(kRowThreads) ln_fwd_kernel(const LnFwdParams p) {
+  griddep_launch();  // dependents (GEMMs) may start their prologue under this kernel's tail
   const int lane = threadIdx.x & 31;
   const int wpb = kRowThreads / 32;
   const int W = p.G * p.C;  // normalised width
@@ -118,6 +119,7 @@ __device__ __forceinline__ float4 load_dy4(const LnBwdParams& p, int r, int col)
 // the separate parameter-gradient pass (a second read of x and dy) disappears.
 template <bool PARAMS, int NV = 8>  // NV: float4 column groups per lane kept in registers (C <= 128 * NV)
 __global__ void __launch_bounds__(kRowThreads) ln_bwd_kernel(const LnBwdParams p) {
+  griddep_launch();  // dependents (GEMMs) may start their prologue under this kernel's tail
   const int lane = threadIdx.x & 31;
   const int wpb = kRowThreads / 32;
   const int W = p.G * p.C;
@@ -227,6 +229,7 @@ __global__ void __launch_bounds__(kRowThreads) ln_bwd_kernel(const LnBwdParams p
 // Block = 8 warps; a warp covers 128 consecutive columns (one float4 / 4 halfs per lane) of one row at a time and
 // walks the rows of its slab with stride 8; partial sums meet in shared memory, one atomic per column per block.
 __global__ void __launch_bounds__(256) ln_bwd_params_kernel(const LnBwdParams p, int rows_per_block) {
+  griddep_launch();  // dependents (GEMMs) may start their prologue under this kernel's tail
   __shared__ float sg[8][128], sb[8][128];
   const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
   const int W = p.G * p.C;
@@ -267,6 +270,7 @@ __global__ void __launch_bounds__(256) ln_bwd_params_kernel(const LnBwdParams p,
 __global__ void __launch_bounds__(kRowThreads)
 scale_cast_kernel(const float* x, int64_t ldx, const int32_t* map, const float* scale, int rows_per_scale, float alpha,
                   __half* out, int64_t ldo, int rows, int C) {
+  griddep_launch();  // dependents (GEMMs) may start their prologue under this kernel's tail
   const int lane = threadIdx.x & 31, wpb = kRowThreads / 32;
   for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
     const int64_t sr = map ? map[r] : r;
@@ -287,6 +291,7 @@ scale_cast_kernel(const float* x, int64_t ldx, const int32_t* map, const float* 
 
 // flat fp32 -> fp16 (parameter shadow copy)
 __global__ void __launch_bounds__(256) cast_flat_kernel(const float* __restrict__ src, __half* __restrict__ dst, int64_t n) {
+  griddep_launch();  // dependents (GEMMs) may start their prologue under this kernel's tail
   const int64_t n4 = n >> 2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 v = reinterpret_cast<const float4*>(src)[i];
@@ -300,6 +305,7 @@ __global__ void __launch_bounds__(256) cast_flat_kernel(const float* __restrict_
 // one row (one 16-byte load per lane) and walks its slab of rows with stride 8.  Needs ld % 8 == 0.
 __global__ void __launch_bounds__(256)
 colsum_f16_kernel(const __half* x, int64_t ld, int rows, int N, float* out, float alpha, int rows_per_block) {
+  griddep_launch();  // dependents (GEMMs) may start their prologue under this kernel's tail
   __shared__ float sm[8][256];
   const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + lane * 8;
@@ -330,6 +336,7 @@ colsum_f16_kernel(const __half* x, int64_t ld, int rows, int N, float* out, floa
 
 // out16 = dy16 * gelu_erf'(pre16)   (flat, n % 2 == 0)
 __global__ void __launch_bounds__(256) gelu_bwd_kernel(const __half2* dy, const __half2* pre, __half2* out, int64_t n2) {
+  griddep_launch();  // dependents (GEMMs) may start their prologue under this kernel's tail
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
     float2 d = __half22float2(dy[i]), x = __half22float2(pre[i]);
     out[i] = __floats2half2_rn(d.x * gelu_erf_grad(x.x), d.y * gelu_erf_grad(x.y));
@@ -339,6 +346,7 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const __half2* dy, const 
 // out = x * keep / (1 - p), fp32 [rows, C], one thread per 8 consecutive columns (one Philox call)
 __global__ void __launch_bounds__(256)
 dropout_f32_kernel(const float* x, int64_t ldx, float* out, int64_t ldo, int rows, int C8, const DropParams d) {
+  griddep_launch();  // dependents (GEMMs) may start their prologue under this kernel's tail
   const DropKey key = drop_key(d);
   const int64_t n = (int64_t)rows * C8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -357,6 +365,7 @@ dropout_f32_kernel(const float* x, int64_t ldx, float* out, int64_t ldo, int row
 
 __global__ void __launch_bounds__(256)
 dropout_mask_kernel(uint8_t* keep, int rows, int C, int head, const DropParams d) {
+  griddep_launch();  // dependents (GEMMs) may start their prologue under this kernel's tail
   const DropKey key = drop_key(d);
   const int C8 = (C + 7) / 8;
   const int64_t n = (int64_t)rows * C8;

@@ -66,6 +66,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
   }
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// launch_dependents: the next kernel in the stream (if it was launched with the programmatic-serialization attribute)
+// may start its prologue once every CTA of this grid has executed this (or exited).  wait: blocks until the grids this
+// one depends on have completed and flushed; a no-op for a normally launched kernel.
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_proxy_async_smem() {  // generic-proxy smem writes -> async proxy (TMA/UMMA)
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
