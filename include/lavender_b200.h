@@ -106,6 +106,8 @@ typedef struct LavGemmEpilogue {
   float alpha;
   int32_t accumulate;      /* LAV_STORE / LAV_ACCUMULATE                                                  */
   int32_t reserved;
+  float* bias_grad;        /* wgrad only (A MN-major, LAV_ACCUMULATE): bias_grad[m] += alpha * sum_k A(m,k), i.e. the
+                              column sum of dY = the nn.Linear bias gradient, from one extra N=16 MMA per k-step    */
   LavDropout drop;         /* dropout of (value + bias) before row_scale / residual (BertSelfOutput / BertOutput
                               .dropout, element index = (GEMM row, column)); drop.p == 0 disables           */
 } LavGemmEpilogue;

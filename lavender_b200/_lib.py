@@ -25,7 +25,7 @@ class GemmEpilogue(ctypes.Structure):
         ("out", c_void_p), ("ldo", c_int64), ("out_dtype", ctypes.c_int32), ("act", ctypes.c_int32),
         ("bias", c_void_p), ("aux", c_void_p), ("ldaux", c_int64), ("residual", c_void_p), ("ldres", c_int64),
         ("row_map", c_void_p), ("row_scale", c_void_p), ("rows_per_scale", ctypes.c_int32), ("alpha", c_float),
-        ("accumulate", ctypes.c_int32), ("reserved", ctypes.c_int32), ("drop", Dropout),
+        ("accumulate", ctypes.c_int32), ("reserved", ctypes.c_int32), ("bias_grad", c_void_p), ("drop", Dropout),
     ]
 
 

@@ -51,12 +51,13 @@ struct GemmCfg {
   static constexpr int B_BYTES = BNL * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_BYTES = kEpiWarps * kEpiWarpBytes;  // per-warp staging: transposes / TMA-store buffers
-  static constexpr int BAR_BYTES = 256;
+  static constexpr int BAR_BYTES = 1024;  // mbarriers + TMEM slot in [0, 256), the all-ones operand tile in [256, 768)
   static constexpr int STAGES_MAX = (232448 - 1024 - BAR_BYTES - EPI_BYTES) / STAGE_BYTES;
   static constexpr int STAGES_CAP = NCTA == 2 ? 8 : 6;
   static constexpr int STAGES = STAGES_MAX > STAGES_CAP ? STAGES_CAP : STAGES_MAX;  // 1-CTA: 3 / 5 / 6 for BN = 256 / 128 / 64
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
-  static constexpr int TMEM_COLS = 2 * BN;                                    // 2 accumulator stages
+  static constexpr int BIAS_COLS = (BN <= 192 && NCTA == 1) ? 32 : 0;         // 2 x 16 columns: fused bias gradient
+  static constexpr int TMEM_COLS = 2 * BN + BIAS_COLS;                        // 2 accumulator stages
   static constexpr int TMEM_ALLOC = TMEM_COLS <= 128 ? 128 : TMEM_COLS <= 256 ? 256 : 512;  // power of 2
 };
 
@@ -64,6 +65,7 @@ struct GemmParams {
   int M, N, K;
   int m_blocks, n_blocks, k_blocks, splits, kb_per_split;  // m_blocks counts tiles of BM * NCTA rows
   DropParams drop;  // resolved from epi.drop
+  float* bias_grad; // wgrad only: bias_grad[m] += alpha * sum_k A(m, k), by one extra N = 16 MMA against an all-ones tile
   int tma_store;    // 1: plain fp16 / fp32 store through TMA (no row map / residual / accumulation)
   int debug;  // LAV_GEMM_DEBUG (profiling only): bit 0 = epilogue drains without math / stores, bit 1 = no MMA issue
   LavGemmEpilogue epi;
@@ -249,6 +251,14 @@ __device__ __forceinline__ void epilogue_warps(const GemmParams& p, float* epi_s
     if (use_pre && wg < nchunks) prefetch(cur, wg);
     mbar_wait(tmem_full + as, (iter >> 1) & 1, 4);
     tc_fence_after();
+    if (GemmCfg<BN, NCTA>::BIAS_COLS > 0 && p.bias_grad != nullptr && t.n_blk == 0 && wg == 0) {
+      // column 0 of the 128 x 16 side accumulator = row sums of A over this tile's k range
+      uint32_t bsum;
+      tmem_ld_32x1(tmem_base + ((uint32_t)(q * 32) << 16) + 2 * BN + as * 16, bsum);
+      tmem_ld_wait();
+      const int brow = row_base + lane;
+      if (brow < p.M) atomicAdd(p.bias_grad + brow, __uint_as_float(bsum) * e.alpha);
+    }
     if ((p.debug & 1) || wg >= nchunks) {  // (a warpgroup without a chunk of a narrow tile just releases the stage)
       tc_fence_before();
       if (NCTA == 2) mbar_arrive_cluster(tmem_empty + as, 0);
@@ -486,6 +496,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* tmem_full = bars + 2 * Cfg::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint8_t* ones_tile = reinterpret_cast<uint8_t*>(bars) + 256;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -508,6 +519,10 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_init(tmem_empty + s, 256 * NCTA);
     }
     fence_barrier_init();
+  }
+  if (warp == 3 && p.bias_grad != nullptr) {  // 16 x 16 tile of fp16 ones (0x3C00), visible to the async proxy
+    reinterpret_cast<uint4*>(ones_tile)[lane] = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+    fence_proxy_async_smem();
   }
   if (warp == 2) {
     if (NCTA == 2) tmem_alloc_pair<Cfg::TMEM_ALLOC>(tmem_slot);
@@ -591,6 +606,15 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint64_t bd = make_smem_desc(sb + k * b_kstep, b_lbo, 1024, SWZ_128B);
             if (NCTA == 2) umma_f16_ss_pair(d_tmem, ad, bd, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
             else umma_f16_ss(d_tmem, ad, bd, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
+          }
+          if (Cfg::BIAS_COLS > 0 && p.bias_grad != nullptr && t.n_blk == 0) {
+            // bias gradient: side accumulator [128 x 16] += A_tile * ones (K-major, no swizzle; every element is 1)
+            constexpr uint32_t idesc_ones = make_idesc_f16(BM, 16, AMAJ, 0);
+            const uint64_t od = make_smem_desc(smem_u32(ones_tile), 128, 256, SWZ_NONE);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_f16_ss(tmem_base + 2 * BN + as * 16, make_smem_desc(sa + k * a_kstep, a_lbo, 1024, SWZ_128B), od,
+                          idesc_ones, (kb > t.kb0 || k > 0) ? 1u : 0u);
           }
           // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
           if (NCTA == 2) umma_commit_pair(empty + stage);
@@ -741,6 +765,10 @@ extern "C" int lav_gemm_f16(const void* A, int64_t lda, int a_major, const void*
   p.k_blocks = (K + BK - 1) / BK;
   p.epi = *epi;
   p.drop = make_drop(&epi->drop);
+  p.bias_grad = epi->bias_grad;
+  LAV_REQUIRE(!epi->bias_grad || (a_major == LAV_MAJOR_MN && epi->accumulate == LAV_ACCUMULATE && epi->act == LAV_ACT_NONE &&
+                                  !epi->row_map && !epi->residual),
+              "lav_gemm_f16: bias_grad is a wgrad option (A MN-major, accumulating plain epilogue)");
   LAV_REQUIRE(!p.drop.on || (epi->act == LAV_ACT_NONE && epi->residual && epi->out_dtype == LAV_OUT_F32 &&
                              epi->accumulate != LAV_ACCUMULATE),
               "lav_gemm_f16: epilogue dropout needs (no activation, residual, fp32 store)");
@@ -768,7 +796,7 @@ extern "C" int lav_gemm_f16(const void* A, int64_t lda, int a_major, const void*
     p.debug = dbg;
   }
   // CTA pairs (256-row tiles, cta_group::2) whenever the problem has more than one 128-row block.
-  const int ncta = (pair_enabled() && M > BM) ? 2 : 1;
+  const int ncta = (pair_enabled() && M > BM && !epi->bias_grad) ? 2 : 1;
   p.m_blocks = (M + BM * ncta - 1) / (BM * ncta);
   // Tile width BN and split-K factor chosen by a small cost model (SM clocks):
   //   per k-block  max(MMA issue 2*BN, operand feed (BM + BN/ncta)*BK*2 bytes at ~110 B/clk/SM), times the number of
@@ -781,6 +809,7 @@ extern "C" int lav_gemm_f16(const void* A, int64_t lda, int a_major, const void*
   for (int ci = 0; ci < 4; ++ci) {
     const int c = cands[ci];
     if (ncta == 2 && c != 256 && c != 128) continue;        // pair tiles: B halves must be whole 64-row atoms
+    if (epi->bias_grad && c > 192) continue;                // the side accumulator needs 32 spare TMEM columns
     if (c > 64 && c >= 2 * ((N + 63) / 64 * 64) && !(ncta == 2 && c == 128)) continue;  // far wider than the problem
     const int tiles = p.m_blocks * ((N + c - 1) / c);
     const double kb_clk = std::max(2.0 * c, (BM + c / ncta) * BK * 2 / 110.0);

@@ -45,9 +45,8 @@ def linear_wgrad(dy16, x16, gw, gb=None, n_valid=None):
     T = dy16.shape[0]
     N = n_valid if n_valid is not None else dy16.shape[1]
     K = x16.shape[1]
-    ops.gemm(dy16, x16, gw, M=N, N=K, K=T, a_major=L.MAJOR_MN, b_major=L.MAJOR_MN, accumulate=True)
-    if gb is not None:
-        ops.colsum(dy16, gb, rows=T, N=N)
+    # the bias gradient (column sum of dY) rides on the wgrad GEMM: one extra N=16 MMA per k-step against a ones tile
+    ops.gemm(dy16, x16, gw, M=N, N=K, K=T, a_major=L.MAJOR_MN, b_major=L.MAJOR_MN, accumulate=True, bias_grad=gb)
 
 
 class LinearFn(torch.autograd.Function):

@@ -59,7 +59,7 @@ def _drop(d):
 
 def gemm(a, b, out, *, M, N, K, a_major=L.MAJOR_K, b_major=L.MAJOR_K, bias=None, act=L.ACT_NONE, aux=None,
          residual=None, row_map=None, row_scale=None, rows_per_scale=1, alpha=1.0, accumulate=False, split_k=0,
-         drop=None):
+         drop=None, bias_grad=None):
     """out[M,N] = epilogue(alpha * A·Bᵀ).  a/b are 2-D fp16 tensors stored per `*_major`
     (K-major: [rows, K]; MN-major: [K, rows]); `out` is fp16 or fp32 2-D."""
     _chk16(a, "a")
@@ -86,6 +86,9 @@ def gemm(a, b, out, *, M, N, K, a_major=L.MAJOR_K, b_major=L.MAJOR_K, bias=None,
         e.row_scale, e.rows_per_scale = row_scale.data_ptr(), rows_per_scale
     e.alpha = alpha
     e.accumulate = L.ACCUMULATE if accumulate else L.STORE
+    if bias_grad is not None:
+        assert bias_grad.dtype == torch.float32 and bias_grad.numel() >= M and accumulate and a_major == L.MAJOR_MN
+        e.bias_grad = bias_grad.data_ptr()
     if drop is not None and drop[2] > 0.0:
         e.drop = L.Dropout(drop[0].data_ptr(), int(drop[1]) & 0xFFFFFFFF, float(drop[2]))
     with _Timed("gemm", 2.0 * M * N * K, ("gemm", M, N, K, a_major, b_major, act, out.dtype == F16, accumulate)):

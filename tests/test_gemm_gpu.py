@@ -121,9 +121,14 @@ def test_wgrad_mn_mn_accumulate(T, N, K, split):
     x = _mk((T, K), 16, 0.3)
     init = torch.randn(N, K, device="cuda")
     out = init.clone()
-    ops.gemm(dy, x, out, M=N, N=K, K=T, a_major=L.MAJOR_MN, b_major=L.MAJOR_MN, accumulate=True, split_k=split)
+    binit = torch.randn(N, device="cuda")
+    gb = binit.clone()   # the nn.Linear bias gradient (column sum of dY) rides on the same kernel
+    ops.gemm(dy, x, out, M=N, N=K, K=T, a_major=L.MAJOR_MN, b_major=L.MAJOR_MN, accumulate=True, split_k=split,
+             bias_grad=gb)
     ref = init.double() + dy.double().t() @ x.double()
     assert (out.double() - ref).abs().max().item() < 2e-5 * T + 1e-3
+    bref = binit.double() + dy.double().sum(0)
+    assert (gb.double() - bref).abs().max().item() < 2e-5 * T + 1e-3
 
 
 def test_launch_count_increases():
