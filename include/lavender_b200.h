@@ -133,8 +133,10 @@ int lav_layernorm_fwd(const float* x, int64_t ldx, const int32_t* row_map, int G
 int lav_layernorm_bwd(const void* dy, int64_t lddy, int dy_is_f32, const float* x, int64_t ldx,
                       const int32_t* row_map, int G, int C, const float* gamma, const float* mean,
                       const float* rstd, const float* add32, int64_t ldadd, float* dx32, int64_t lddx32,
-                      void* dx16, int64_t lddx16, float* dgamma, float* dbeta, int rows, const LavDropout* drop16,
-                      void* stream);
+                      void* dx16, int64_t lddx16, float* dgamma, float* dbeta, float* param_ws, int64_t ws_floats,
+                      int rows, const LavDropout* drop16, void* stream);
+/* param_ws (may be NULL): caller-owned scratch of ws_floats fp32 (>= 8 * SM count * 2 * C is always enough) for the
+ * per-block partial sums of dgamma / dbeta; without it the blocks add to dgamma / dbeta with atomics. */
 /* drop16 (may be NULL): dx16 is additionally multiplied by the dropout mask of site drop16 at (r, column) — the
  * gradient entering a dense layer whose output was dropped in the forward epilogue — while dx32 stays unmasked
  * (the residual path). */

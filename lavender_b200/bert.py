@@ -450,7 +450,10 @@ class _XentFn(torch.autograd.Function):
     def backward(ctx, gout):
         logits, target, row_lse, acc = ctx.saved
         rows, V = logits.shape
-        d = empty32(rows, V, device=logits.device)
+        # rows padded to a multiple of 8 columns: 16-byte aligned rows for the vectorised kernels that consume the
+        # gradient (the MLM head's fp16 cast); the returned gradient is the [rows, V] view
+        Vp = (V + 7) // 8 * 8
+        d = empty32(rows, Vp, device=logits.device)[:, :V]
         g = gout.reshape(1).to(F32).contiguous()
         ops.xent_bwd(logits, target, ctx.ignore_index, row_lse, g, acc[1:2], d32=d)
         return d, None, None

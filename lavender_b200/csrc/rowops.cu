@@ -104,6 +104,7 @@ struct LnBwdParams {
   float* dgamma; float* dbeta;
   int rows;
   DropParams drop;  // mask applied to dx16 only
+  float* param_ws;  // fused parameter gradients: per-block partial sums [grid][2][C] (null: atomics straight to dgamma/dbeta)
 };
 
 __device__ __forceinline__ float4 load_dy4(const LnBwdParams& p, int r, int col) {
@@ -214,14 +215,38 @@ __global__ void __launch_bounds__(kRowThreads) ln_bwd_kernel(const LnBwdParams p
         if (i < c4) *reinterpret_cast<float4*>(red + wy * p.C + i * 4) = pass == 0 ? ag[k] : ab[k];
       }
       __syncthreads();
-      float* dst = pass == 0 ? p.dgamma : p.dbeta;
+      // hundreds of blocks adding to the same C addresses serialise in L2 (~17 us at C = 512): with a workspace the
+      // block stores its partial row instead and ln_param_reduce_kernel sums the rows
+      float* dst = p.param_ws ? p.param_ws + ((size_t)blockIdx.x * 2 + pass) * p.C : (pass == 0 ? p.dgamma : p.dbeta);
       for (int c = threadIdx.x; c < p.C; c += kRowThreads) {
         float t = 0.f;
 #pragma unroll
         for (int w = 0; w < 8; ++w) t += red[w * p.C + c];
-        atomicAdd(dst + c, t);
+        if (p.param_ws) dst[c] = t;
+        else atomicAdd(dst + c, t);
       }
     }
+  }
+}
+
+// dgamma[c] += sum_b ws[b][0][c] ; dbeta[c] += sum_b ws[b][1][c]   (second stage of the fused parameter gradients)
+__global__ void __launch_bounds__(1024) ln_param_reduce_kernel(const float* ws, int nblocks, int C, float* dgamma, float* dbeta) {
+  griddep_launch();
+  // block = 32 columns x 32 row slabs: coalesced 128-byte reads, 32-way parallel over the partial rows
+  __shared__ float sm[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;  // column of the [2C]-wide partial rows
+  float t = 0.f;
+  if (j < 2 * C)
+    for (int b = ty; b < nblocks; b += 32) t += ws[(size_t)b * 2 * C + j];
+  sm[ty][tx] = t;
+  __syncthreads();
+  if (ty == 0 && j < 2 * C) {
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) a += sm[k][tx];
+    if (j < C) dgamma[j] += a;
+    else dbeta[j - C] += a;
   }
 }
 
@@ -405,15 +430,15 @@ extern "C" int lav_layernorm_fwd(const float* x, int64_t ldx, const int32_t* row
 extern "C" int lav_layernorm_bwd(const void* dy, int64_t lddy, int dy_is_f32, const float* x, int64_t ldx,
                                  const int32_t* row_map, int G, int C, const float* gamma, const float* mean,
                                  const float* rstd, const float* add32, int64_t ldadd, float* dx32, int64_t lddx32,
-                                 void* dx16, int64_t lddx16, float* dgamma, float* dbeta, int rows, const LavDropout* drop16,
-                      void* stream) {
+                                 void* dx16, int64_t lddx16, float* dgamma, float* dbeta, float* param_ws, int64_t ws_floats,
+                      int rows, const LavDropout* drop16, void* stream) {
   LAV_REQUIRE(dy && x && gamma && mean && rstd && (dx32 || dx16), "lav_layernorm_bwd: null pointer");
   LAV_REQUIRE(G >= 1 && G <= 4 && C > 0 && (C % 4) == 0 && (ldx % 4) == 0 && (lddy % 4) == 0,
               "lav_layernorm_bwd: need C%%4==0, 1<=G<=4, ld%%4==0");
   LAV_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "lav_layernorm_bwd: dgamma/dbeta must come together");
   if (rows <= 0) return LAV_OK;
   LnBwdParams p{dy, lddy, dy_is_f32, x, ldx, row_map, G, C, gamma, mean, rstd, add32, ldadd,
-                dx32, lddx32, (__half*)dx16, lddx16, dgamma, dbeta, rows, make_drop(drop16)};
+                dx32, lddx32, (__half*)dx16, lddx16, dgamma, dbeta, rows, make_drop(drop16), nullptr};
   LAV_REQUIRE(!p.drop.on || (dx16 && G == 1), "lav_layernorm_bwd: drop16 needs dx16 and G == 1");
   cudaStream_t s = (cudaStream_t)stream;
   if (dgamma && G == 1 && C <= 1024) {
@@ -423,6 +448,7 @@ extern "C" int lav_layernorm_bwd(const void* dy, int64_t lddy, int dy_is_f32, co
     const int nv = C <= 128 ? 1 : C <= 256 ? 2 : C <= 512 ? 4 : 8;
     const int per_sm = nv == 1 ? 8 : nv == 2 ? 6 : nv == 4 ? 4 : 2;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((rows + 7) / 8, (int64_t)sm_count() * per_sm));
+    if (param_ws && ws_floats >= (int64_t)grid * 2 * C) p.param_ws = param_ws;
     static bool attr_set = false;
     if (!attr_set) {
       LAV_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024 * 4));
@@ -434,6 +460,11 @@ extern "C" int lav_layernorm_bwd(const void* dy, int64_t lddy, int dy_is_f32, co
     else ln_bwd_kernel<true, 8><<<grid, kRowThreads, red_bytes, s>>>(p);
     LAV_CHECK_CUDA(cudaGetLastError());
     count_launch();
+    if (p.param_ws) {
+      ln_param_reduce_kernel<<<(2 * C + 31) / 32, 1024, 0, s>>>(p.param_ws, grid, C, dgamma, dbeta);
+      LAV_CHECK_CUDA(cudaGetLastError());
+      count_launch();
+    }
     return LAV_OK;
   }
   if (dgamma) {  // must read x before an in-place dx32 overwrite of the same rows

@@ -116,13 +116,17 @@ def layernorm_fwd(x, gamma, beta, eps, *, rows, C, G=1, row_map=None, out16=None
 def layernorm_bwd(dy, x, gamma, mean, rstd, *, rows, C, G=1, row_map=None, add32=None, dx32=None, dx16=None,
                   dgamma=None, dbeta=None, drop16=None):
     assert dy.dtype in (F16, torch.float32) and x.dtype == torch.float32
+    ws = None
+    if dgamma is not None and G == 1 and C <= 1024:   # scratch for the per-block partial sums of dgamma / dbeta
+        ws = torch.empty(8 * 148 * 2 * C, dtype=torch.float32, device=x.device)
     with _Timed("layernorm_bwd"):
         rc = L.lib().lav_layernorm_bwd(_p(dy), dy.stride(0), int(dy.dtype == torch.float32), _p(x), x.stride(0),
                                        _p(row_map), G, C, _p(gamma), _p(mean), _p(rstd),
                                        _p(add32), add32.stride(0) if add32 is not None else 0,
                                        _p(dx32), dx32.stride(0) if dx32 is not None else 0,
                                        _p(dx16), dx16.stride(0) if dx16 is not None else 0,
-                                       _p(dgamma), _p(dbeta), rows, _drop(drop16), _stream())
+                                       _p(dgamma), _p(dbeta), _p(ws), ws.numel() if ws is not None else 0, rows,
+                                       _drop(drop16), _stream())
     L.check(rc, "lav_layernorm_bwd")
 
 
