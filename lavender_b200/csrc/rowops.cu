@@ -87,6 +87,60 @@ __global__ void __launch_bounds__(kRowThreads) ln_fwd_kernel(const LnFwdParams p
   }
 }
 
+// Register-resident variant (G == 1, C <= 128 * NV): the row is loaded ONCE, all loads issued before the first use, and
+// stays in registers for the statistics and the normalisation (the generic kernel re-reads it through L1 twice).
+template <int NV>
+__global__ void __launch_bounds__(kRowThreads) ln_fwd_reg_kernel(const LnFwdParams p) {
+  griddep_launch();
+  const int lane = threadIdx.x & 31;
+  const int wpb = kRowThreads / 32;
+  const int c4 = p.C >> 2;
+  const float invC = 1.0f / (float)p.C;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < p.rows; r += gridDim.x * wpb) {
+    const int64_t sr = p.map ? p.map[r] : r;
+    const float4* src = reinterpret_cast<const float4*>(p.x + sr * p.ldx);
+    float4 v[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int i = lane + 32 * k;
+      v[k] = i < c4 ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    const float mean = warp_sum(s) * invC;
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      if (lane + 32 * k < c4) {
+        const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+        ss += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(ss) * invC + p.eps);
+    if (lane == 0) {
+      if (p.mean) p.mean[r] = mean;
+      if (p.rstd) p.rstd[r] = rstd;
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int i = lane + 32 * k;
+      if (i < c4) {
+        const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gamma) + i);
+        const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta) + i);
+        float4 o;
+        o.x = (v[k].x - mean) * rstd * ga.x + be.x;
+        o.y = (v[k].y - mean) * rstd * ga.y + be.y;
+        o.z = (v[k].z - mean) * rstd * ga.z + be.z;
+        o.w = (v[k].w - mean) * rstd * ga.w + be.w;
+        if (p.y32) *reinterpret_cast<float4*>(p.y32 + (int64_t)r * p.ldy32 + i * 4) = o;
+        if (p.y16)
+          *reinterpret_cast<uint2*>(p.y16 + (int64_t)r * p.ldy16 + i * 4) = make_uint2(pack_half2(o.x, o.y), pack_half2(o.z, o.w));
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // LayerNorm backward (input gradient).  For output row r (same gather as forward):
 //   xhat = (x - mean) * rstd ; a = dy*gamma ; dx = rstd * (a - mean_c(a) - xhat * mean_c(a*xhat))
@@ -139,40 +193,72 @@ __global__ void __launch_bounds__(kRowThreads) ln_bwd_kernel(const LnBwdParams p
       if (g < p.G) srow[g] = p.map ? p.map[(int64_t)r * p.G + g] : (int64_t)r * p.G + g;
     const float mean = p.mean[r], rstd = p.rstd[r];
     float s1 = 0.f, s2 = 0.f;
-    if (PARAMS) {  // G == 1
+    if (PARAMS) {  // G == 1: the row lives in registers; every global load is issued before the first use
+      float4 v[NV], d[NV], ad[NV];
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int i = lane + 32 * k;
+        const bool in = i < c4;
+        v[k] = in ? *reinterpret_cast<const float4*>(p.x + srow[0] * p.ldx + i * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        d[k] = in ? load_dy4(p, r, i * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        ad[k] = (in && p.add32) ? *reinterpret_cast<const float4*>(p.add32 + srow[0] * p.ldadd + i * 4)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
         const int i = lane + 32 * k;
         if (i < c4) {
-          float4 v = *reinterpret_cast<const float4*>(p.x + srow[0] * p.ldx + i * 4);
-          float4 d = load_dy4(p, r, i * 4);
-          float4 ga = *reinterpret_cast<const float4*>(p.gamma + i * 4);
-          float a0 = d.x * ga.x, a1 = d.y * ga.y, a2 = d.z * ga.z, a3 = d.w * ga.w;
-          const float x0 = (v.x - mean) * rstd, x1 = (v.y - mean) * rstd, x2 = (v.z - mean) * rstd, x3 = (v.w - mean) * rstd;
-          s1 += (a0 + a1) + (a2 + a3);
-          s2 += (a0 * x0 + a1 * x1) + (a2 * x2 + a3 * x3);
-          ag[k].x += d.x * x0, ag[k].y += d.y * x1, ag[k].z += d.z * x2, ag[k].w += d.w * x3;
-          ab[k].x += d.x, ab[k].y += d.y, ab[k].z += d.z, ab[k].w += d.w;
+          const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gamma) + i);
+          const float x0 = (v[k].x - mean) * rstd, x1 = (v[k].y - mean) * rstd, x2 = (v[k].z - mean) * rstd,
+                      x3 = (v[k].w - mean) * rstd;
+          ag[k].x += d[k].x * x0, ag[k].y += d[k].y * x1, ag[k].z += d[k].z * x2, ag[k].w += d[k].w * x3;
+          ab[k].x += d[k].x, ab[k].y += d[k].y, ab[k].z += d[k].z, ab[k].w += d[k].w;
+          d[k].x *= ga.x, d[k].y *= ga.y, d[k].z *= ga.z, d[k].w *= ga.w;  // a = dy * gamma
+          v[k] = make_float4(x0, x1, x2, x3);                              // xhat
+          s1 += (d[k].x + d[k].y) + (d[k].z + d[k].w);
+          s2 += (d[k].x * x0 + d[k].y * x1) + (d[k].z * x2 + d[k].w * x3);
         }
       }
       s1 = warp_sum(s1) / W;
       s2 = warp_sum(s2) / W;  // mean_c(a * xhat)
-    } else {
 #pragma unroll
-      for (int g = 0; g < 4; ++g)
-        if (g < p.G)
-          for (int i = lane; i < c4; i += 32) {
-            const int col = g * p.C + i * 4;
-            float4 v = *reinterpret_cast<const float4*>(p.x + srow[g] * p.ldx + i * 4);
-            float4 d = load_dy4(p, r, col);
-            float4 ga = *reinterpret_cast<const float4*>(p.gamma + col);
-            float a0 = d.x * ga.x, a1 = d.y * ga.y, a2 = d.z * ga.z, a3 = d.w * ga.w;
-            s1 += (a0 + a1) + (a2 + a3);
-            s2 += (a0 * (v.x - mean) + a1 * (v.y - mean)) + (a2 * (v.z - mean) + a3 * (v.w - mean));
+      for (int k = 0; k < NV; ++k) {
+        const int i = lane + 32 * k;
+        if (i < c4) {
+          const int col = i * 4;
+          float4 o;
+          o.x = rstd * (d[k].x - s1 - v[k].x * s2) + ad[k].x;
+          o.y = rstd * (d[k].y - s1 - v[k].y * s2) + ad[k].y;
+          o.z = rstd * (d[k].z - s1 - v[k].z * s2) + ad[k].z;
+          o.w = rstd * (d[k].w - s1 - v[k].w * s2) + ad[k].w;
+          if (p.dx32) *reinterpret_cast<float4*>(p.dx32 + srow[0] * p.lddx32 + col) = o;
+          if (p.dx16) {
+            if (p.drop.on) {  // gradient entering a dense layer whose output was dropped at (r, col) in the forward
+              const uint32_t m = drop_keep8(dkey, p.drop.thresh, (uint32_t)r, (uint32_t)(col >> 3), 0u) >> (col & 7);
+              o.x = (m & 1u) ? o.x * p.drop.inv_keep : 0.f, o.y = (m & 2u) ? o.y * p.drop.inv_keep : 0.f;
+              o.z = (m & 4u) ? o.z * p.drop.inv_keep : 0.f, o.w = (m & 8u) ? o.w * p.drop.inv_keep : 0.f;
+            }
+            *reinterpret_cast<uint2*>(p.dx16 + (int64_t)r * p.lddx16 + col) =
+                make_uint2(pack_half2(o.x, o.y), pack_half2(o.z, o.w));
           }
-      s1 = warp_sum(s1) / W;
-      s2 = warp_sum(s2) * rstd / W;  // mean_c(a * xhat)
+        }
+      }
+      continue;
     }
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (g < p.G)
+        for (int i = lane; i < c4; i += 32) {
+          const int col = g * p.C + i * 4;
+          float4 v = *reinterpret_cast<const float4*>(p.x + srow[g] * p.ldx + i * 4);
+          float4 d = load_dy4(p, r, col);
+          float4 ga = *reinterpret_cast<const float4*>(p.gamma + col);
+          float a0 = d.x * ga.x, a1 = d.y * ga.y, a2 = d.z * ga.z, a3 = d.w * ga.w;
+          s1 += (a0 + a1) + (a2 + a3);
+          s2 += (a0 * (v.x - mean) + a1 * (v.y - mean)) + (a2 * (v.z - mean) + a3 * (v.w - mean));
+        }
+    s1 = warp_sum(s1) / W;
+    s2 = warp_sum(s2) * rstd / W;  // mean_c(a * xhat)
 #pragma unroll
     for (int g = 0; g < 4; ++g)
       if (g < p.G)
@@ -421,7 +507,16 @@ extern "C" int lav_layernorm_fwd(const float* x, int64_t ldx, const int32_t* row
   LAV_REQUIRE((!y16 || ldy16 % 4 == 0) && (!y32 || ldy32 % 4 == 0), "lav_layernorm_fwd: output ld must be %%4");
   if (rows <= 0) return LAV_OK;
   LnFwdParams p{x, ldx, row_map, G, C, gamma, beta, eps, (__half*)y16, ldy16, y32, ldy32, mean, rstd, rows};
-  ln_fwd_kernel<<<row_grid(rows), kRowThreads, 0, (cudaStream_t)stream>>>(p);
+  if (G == 1 && C <= 1024) {
+    const int grid = row_grid(rows);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C <= 128) ln_fwd_reg_kernel<1><<<grid, kRowThreads, 0, st>>>(p);
+    else if (C <= 256) ln_fwd_reg_kernel<2><<<grid, kRowThreads, 0, st>>>(p);
+    else if (C <= 512) ln_fwd_reg_kernel<4><<<grid, kRowThreads, 0, st>>>(p);
+    else ln_fwd_reg_kernel<8><<<grid, kRowThreads, 0, st>>>(p);
+  } else {
+    ln_fwd_kernel<<<row_grid(rows), kRowThreads, 0, (cudaStream_t)stream>>>(p);
+  }
   LAV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return LAV_OK;
@@ -446,7 +541,7 @@ extern "C" int lav_layernorm_bwd(const void* dy, int64_t lddy, int dy_is_f32, co
     // narrow rows need many resident warps to cover the load latency: blocks per SM grow as the rows get narrower
     const size_t red_bytes = (size_t)8 * C * sizeof(float);
     const int nv = C <= 128 ? 1 : C <= 256 ? 2 : C <= 512 ? 4 : 8;
-    const int per_sm = nv == 1 ? 8 : nv == 2 ? 6 : nv == 4 ? 4 : 2;
+    const int per_sm = nv == 1 ? 8 : nv == 2 ? 5 : nv == 4 ? 2 : 1;  // = resident blocks per SM at each variant's register count
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((rows + 7) / 8, (int64_t)sm_count() * per_sm));
     if (param_ws && ws_floats >= (int64_t)grid * 2 * C) p.param_ws = param_ws;
     static bool attr_set = false;
