@@ -113,6 +113,9 @@ def summarize_clocks(samples):
             "reasons": reasons, "samples": len(samples)}
 
 
+_emit = print
+
+
 def make_host_batch(B, seed, pin):
     import torch
     g = torch.Generator().manual_seed(1000 + seed)
@@ -225,24 +228,32 @@ def run_native(a):
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStop()
         if rank == 0:
-            print(json.dumps({"profile_step": True}), flush=True)
+            _emit(json.dumps({"profile_step": True}))
         return
+    def phase(msg):   # progress on stderr (stdout carries the one JSON line)
+        if rank == 0:
+            print(f"[bench] {msg}", file=sys.stderr, flush=True)
+
     sampler = ClockSampler(local) if rank == 0 else None
+    phase(f"warm-up ({max(a.warmup, 3)} steps, world {world})")
     for _ in range(max(a.warmup, 3)):
         step_resident()
+    phase("timed resident steps")
     ms, launches, last, per_step = timed(step_resident, a.steps)
     if a.quick:   # profiling runs (ncu): just the resident steps
         if rank == 0:
-            print(json.dumps({"quick": True, "ms_per_step": ms / a.steps, "gpu_launches": int(launches)}), flush=True)
+            _emit(json.dumps({"quick": True, "ms_per_step": ms / a.steps, "gpu_launches": int(launches)}))
         return
+    phase("timed end-to-end steps")
     for _ in range(2):
         step_e2e()
     ms_e2e, _, last_e2e, per_step_e2e = timed(step_e2e, a.steps)
     samples = sampler.stop() if sampler is not None else []
 
     # ---- one extra instrumented step: per-kernel-family device time (CUDA events around every C-ABI call)
+    phase("instrumented step")
     fams = {}
-    if rank == 0:
+    if True:   # every rank runs it (the step contains the gradient all-reduce); rank 0's numbers are reported
         ops.PROFILE = []
         t0 = torch.cuda.Event(enable_timing=True)
         t1 = torch.cuda.Event(enable_timing=True)
@@ -315,7 +326,7 @@ def run_native(a):
     }
     if not a.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_oracle_baseline(steps=1, warmup=0)
-    print(json.dumps(out), flush=True)
+    _emit(json.dumps(out))
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -386,10 +397,13 @@ def run_reference(a):
                       "algorithmic_gflop_per_clip_fwd_bwd": round(3 * fwd / 1e9, 1)},
            "cpu_baseline": cb,
            "e2e": {"value": cb["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out), flush=True)
+    _emit(json.dumps(out))
 
 
 def main():
+    import faulthandler
+    # a hung collective or kernel must not sit silently until an outer time limit: dump every thread's stack and exit
+    faulthandler.dump_traceback_later(int(os.environ.get("LAV_BENCH_WATCHDOG_S", "1500")), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -403,6 +417,13 @@ def main():
     ap.add_argument("--eval-dropout", action="store_true",
                     help="identity BERT dropout (default: active p=0.1 dropout as in the reference's train() step)")
     a = ap.parse_args()
+    # stdout carries exactly ONE JSON line: libraries that write to fd 1 (NCCL prints its version banner there) are
+    # routed to stderr; the result line goes to the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global _emit
+    _emit = lambda line: os.write(real_stdout, (line + "\n").encode())
     if a.impl == "reference":
         run_reference(a)
     else:
