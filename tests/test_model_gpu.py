@@ -75,6 +75,43 @@ def test_swin_tiny_forward_backward_vs_oracle():
     print("swin worst grad rel err", worst)
 
 
+def test_swin_window81212_at_384_vs_oracle():
+    """BASELINE configs[3] geometry (swin_large_384_patch244_window81212: 5 x 384 x 384 clips, windows of 5 x 12 x 12 =
+    720 tokens, cyclic shift (0, 6, 6)) on a narrow / shallow backbone so that the CPU oracle finishes in seconds:
+    exercises the blocked attention kernel with the tensor-core bias, 4 shift-mask classes and the patch merging at
+    this geometry, forward and backward."""
+    import lavender_oracle as O
+    from lavender_b200.video_swin import SwinTransformer3D
+    cfg = O.SwinCfg(64, (2, 2, 2, 2), (2, 4, 8, 16), (8, 12, 12))
+    full = O.make_state_dict(O.ModelCfg(swin=cfg, bert_layers=1), seed=4)
+    sd = {k[len("enc_img.swin."):]: v for k, v in full.items() if k.startswith("enc_img.swin.")}
+    m = SwinTransformer3D(embed_dim=64, depths=[2, 2, 2, 2], num_heads=[2, 4, 8, 16], window_size=(8, 12, 12))
+    m.load_state_dict(sd, strict=True)
+    m.cuda().train()
+    B = 1
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(B, 3, 5, 384, 384, generator=g)
+    nblk = sum(cfg.depths)
+    kp = 1.0 - torch.linspace(0, 0.2, nblk).view(-1, 1, 1)
+    keep = torch.ones(nblk, 2, B) / kp * (torch.rand(nblk, 2, B, generator=g) < 2.0)   # all paths kept, scaled 1/keep_prob
+    cot = torch.randn(B, 5, 12, 12, 512, generator=g)
+    sdg = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point else v) for k, v in sd.items()}
+    ref = O.swin_forward({"s." + k: v for k, v in sdg.items()}, "s.", x, cfg, keep)
+    (ref * cot).sum().backward()
+    out = m.forward_features(x.cuda(), keep=keep.cuda())
+    (out * cot.cuda() * 256.0).sum().backward()
+    torch.cuda.synchronize()
+    err = (out.cpu() - ref.detach()).abs().max().item()
+    print("swin(8,12,12)@384 forward max abs err", err, "ref absmax", ref.abs().max().item())
+    assert err < 2e-2
+    worst = 0.0
+    for n, p in m.named_parameters():
+        e = _rel(p.grad.cpu() / 256.0, sdg[n].grad)
+        worst = max(worst, e)
+        assert e < GRAD_REL, (n, e)
+    print("swin(8,12,12)@384 worst grad rel err", worst)
+
+
 @pytest.mark.parametrize("name,size,layers,B,task,seed", [("tiny_l2_b2", "tiny", 2, 2, True, 0),
                                                           ("tiny_l1_b3_notask", "tiny", 1, 3, False, 3)])
 def test_pretrain_vs_reference_golden(name, size, layers, B, task, seed):
