@@ -128,7 +128,10 @@ class ParamArena:
 
     def finalize_grads(self):
         """After backward: gradients that torch autograd produced for glue ops (e.g. `emb_task` indexing) are moved
-        into the arena so that the flat buffer holds every gradient (one all-reduce, one clip, one optimizer pass)."""
+        into the arena so that the flat buffer holds every gradient (one all-reduce, one clip, one optimizer pass).
+        Also the join point of the weight-gradient side stream (streams.py)."""
+        from . import streams
+        streams.join(self.grad.device)
         for p in self.params:
             if p.grad is not None:
                 gv = self.g(p)

@@ -8,6 +8,7 @@ import torch
 
 from . import ops
 from . import _lib as L
+from . import streams
 from .arena import arena_of
 
 F16, F32 = torch.float16, torch.float32
@@ -46,6 +47,13 @@ def linear_wgrad(dy16, x16, gw, gb=None, n_valid=None):
     N = n_valid if n_valid is not None else dy16.shape[1]
     K = x16.shape[1]
     # the bias gradient (column sum of dY) rides on the wgrad GEMM: one extra N=16 MMA per k-step against a ones tile
+    if streams.enabled():
+        # off the critical path: launched on the side stream, joined when the gradient arena is finalised (streams.py)
+        dev = dy16.device
+        with torch.cuda.stream(streams.fork(dev)):
+            ops.gemm(dy16, x16, gw, M=N, N=K, K=T, a_major=L.MAJOR_MN, b_major=L.MAJOR_MN, accumulate=True, bias_grad=gb)
+        streams.hold(dev, dy16, x16)
+        return
     ops.gemm(dy16, x16, gw, M=N, N=K, K=T, a_major=L.MAJOR_MN, b_major=L.MAJOR_MN, accumulate=True, bias_grad=gb)
 
 

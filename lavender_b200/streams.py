@@ -1,0 +1,70 @@
+"""Side stream for the weight-gradient GEMMs.
+
+In backward every nn.Linear needs two products of the same dY: dgrad (on the critical path: the next layer waits for
+it) and wgrad (+ bias gradient; nobody waits for it until the optimizer).  The persistent GEMM kernels leave SMs idle
+in their last wave (3.35 waves of tiles on 148 SMs) and every kernel has a serial prologue / tail; wgrad launched on
+a second stream fills those holes instead of extending the critical path.  Under CUDA-graph capture the fork / join
+become parallel branches of the graph.
+
+    fork(dev)        -> stream on which to launch (it waits for everything enqueued on the current stream so far)
+    hold(*tensors)      keeps operands alive until join() (they were allocated on the main stream: the caching
+                        allocator must not hand their memory out while the side stream still reads it)
+    join(dev)           the current stream waits for the side stream; queued as an end-of-backward callback of the
+                        autograd engine and called by ParamArena.finalize_grads(), i.e. before anything reads the
+                        gradient arena (all-reduce, clipping, optimizer, end of a graph capture)
+LAV_WGRAD_STREAM=0 disables it (everything on the current stream).
+"""
+import os
+
+import torch
+
+_ENABLED = os.environ.get("LAV_WGRAD_STREAM", "1") != "0"
+_STATE = {}
+
+
+class _Side:
+    def __init__(self, device):
+        self.stream = torch.cuda.Stream(device=device)
+        self.held = []
+        self.dirty = False
+
+
+def enabled():
+    return _ENABLED
+
+
+def _get(device):
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    st = _STATE.get(key)
+    if st is None:
+        st = _STATE[key] = _Side(device)
+    return st
+
+
+def fork(device):
+    st = _get(device)
+    st.stream.wait_stream(torch.cuda.current_stream(device))
+    if not st.dirty:
+        st.dirty = True
+        try:   # inside autograd's backward: join automatically when this backward pass ends, so that code which reads
+            #    p.grad right after loss.backward() (a plain torch optimizer, clip_grad_norm_) is ordered after wgrad
+            torch.autograd.Variable._execution_engine.queue_callback(lambda: join(device))
+        except RuntimeError:
+            pass   # not called from a backward pass (direct use of the functional API): the caller joins
+    return st.stream
+
+
+def hold(device, *tensors):
+    _get(device).held.extend(t for t in tensors if t is not None)
+
+
+def join(device):
+    if not _ENABLED or not torch.cuda.is_available():
+        return
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    st = _STATE.get(key)
+    if st is None or not st.dirty:
+        return
+    torch.cuda.current_stream(device).wait_stream(st.stream)
+    st.held.clear()
+    st.dirty = False

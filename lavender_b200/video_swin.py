@@ -20,6 +20,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from . import streams
 from . import _lib as L
 from .arena import arena_of
 from .functional import F16, F32, empty16, empty32, linear_dgrad, linear_fwd, linear_wgrad, require_cuda
@@ -363,6 +364,8 @@ class _SwinFn(torch.autograd.Function):
             for b in range(layer.depth - 1, -1, -1):
                 bi -= 1
                 g = _block_bwd(ar, layer.blocks[b], g, blocks[bi], ds_ws, dev)
+        for old in ds_ws.values():   # the side stream may still read the last dS workspaces
+            streams.hold(dev, *old["bufs"])
         cols16, y, pm, pr = saved["pe"]
         pe = mod.patch_embed
         M0, C0 = y.shape
@@ -432,15 +435,34 @@ def _block_bwd(ar, blk, g, sv, ds_ws, dev):
     linear_dgrad(go16, ar.w16(at.proj.weight), do16)
     dq_acc = torch.zeros(M, C, dtype=F32, device=dev)
     dqkv16 = empty16(M, 3 * C, device=dev)
+    # dS workspace: two buffers per shape, alternated, because the table-gradient reduction that reads one of them runs
+    # on the side stream (off the critical path, like the weight gradients) while the next block's attention backward
+    # already fills the other (up to 2 x 268 MB at stage 0, B=8)
     key = (nprob, nh, NP)
-    ds16 = ds_ws.get(key)
-    if ds16 is None:
-        ds_ws.clear()  # one live workspace at a time (up to 268 MB at stage 0, B=8)
-        ds16 = ds_ws[key] = empty16(nprob, nh, NP, NP, device=dev)
+    slot = ds_ws.get(key)
+    if slot is None:
+        for old in ds_ws.values():
+            streams.hold(dev, *old["bufs"])
+        ds_ws.clear()
+        slot = ds_ws[key] = {"bufs": [empty16(nprob, nh, NP, NP, device=dev) for _ in range(2 if streams.enabled() else 1)],
+                             "ev": [None, None], "i": 0}
+    i = slot["i"]
+    ds16 = slot["bufs"][i]
+    if slot["ev"][i] is not None:
+        torch.cuda.current_stream(dev).wait_event(slot["ev"][i])   # its previous reader (two blocks ago) is done
     ops.attn_bwd(sv["qkv16"], sv["o16"], do16, sv["lse"], dq_acc, dqkv16, q_off=0, k_off=C, v_off=2 * C, head_dim=hd,
                  nheads=nh, nprob=nprob, L_tok=N, scale=at.scale, bias16=sv["dense"], prob_class=sv["cls_of"], ds16=ds16)
     ops.scale_cast(dq_acc, dqkv16, rows=M, C=C)  # Q block of dqkv (columns 0..C)
-    ops.relpos_bias_grad(ds16, sv["rel"], N, ar.g(at.relative_position_bias_table))
+    if streams.enabled():
+        side = streams.fork(dev)
+        with torch.cuda.stream(side):
+            ops.relpos_bias_grad(ds16, sv["rel"], N, ar.g(at.relative_position_bias_table))
+            ev = slot["ev"][i] or torch.cuda.Event()
+            ev.record(side)
+            slot["ev"][i] = ev
+        slot["i"] = i ^ 1
+    else:
+        ops.relpos_bias_grad(ds16, sv["rel"], N, ar.g(at.relative_position_bias_table))
     linear_wgrad(dqkv16, sv["y16"], ar.g(at.qkv.weight), ar.g(at.qkv.bias))
     dy1 = empty16(M, C, device=dev)
     linear_dgrad(dqkv16, ar.w16(at.qkv.weight), dy1)
