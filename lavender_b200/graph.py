@@ -63,7 +63,11 @@ class GraphedPretrainStep:
         self.graph = torch.cuda.CUDAGraph()
         agent.optzr.zero_grad(set_to_none=True)   # first prepare_grads inside the capture records one arena memset
         ar._ver16 = None                           # ... and the first refresh16 records the fp32 -> fp16 weight cast
-        with torch.cuda.graph(self.graph):
+        # the critical path is captured on a high-priority stream: the side-stream branches (weight gradients, default
+        # priority) then only get SMs the critical-path kernels leave idle
+        import os
+        cap = torch.cuda.Stream(priority=-1) if os.environ.get("LAV_GRAPH_PRIORITY", "1") != "0" else None
+        with torch.cuda.graph(self.graph, stream=cap):
             self.l_mtm, self.l_vtm = self._fwd_bwd()
         self.native_launches = _lib.launch_count() - n0   # kernels of the C-ABI library inside one replay
         ar.on_swin_backward = hook
