@@ -177,7 +177,7 @@ int lav_attn_fwd_f16(const void* qkv, int64_t ld, int64_t rows_total, int q_off,
  * (global query row, key column, head); lse is that of the un-dropped softmax. */
 
 /* Backward of the above.  delta_ws: caller-owned fp32 [nheads][rows_total] workspace (rowsum(dO * O), filled by a
- * small pre-pass).  dq_acc: fp32 [rows_total, nheads*head_dim], zeroed by the caller (dQ is reduced
+ * small pre-pass).  dq_acc: fp32 [rows_total, nheads*head_dim] scratch, zeroed by the pre-pass (dQ is reduced
  * over key chunks with atomics); dK and dV are written as fp16 into dqkv16 at k_off / v_off.  When ds16 is
  * given ([nprob][nheads][NPs][NPs] fp16) the gradient wrt the pre-softmax logits is stored for
  * lav_relpos_bias_grad. */

@@ -310,7 +310,7 @@ class _BertEncoderFn(torch.autograd.Function):
             linear_wgrad(ga16, sv["ctx16"], ar.g(so.dense.weight), ar.g(so.dense.bias))
             dctx16 = empty16(M, H, device=dev)
             linear_dgrad(ga16, ar.w16(so.dense.weight), dctx16)
-            dq_acc = torch.zeros(M, H, dtype=F32, device=dev)
+            dq_acc = empty32(M, H, device=dev)   # zeroed by the attention backward's pre-pass
             dqkv16 = empty16(M, 3 * H, device=dev)
             ops.attn_bwd(sv["qkv16"], sv["ctx16"], dctx16, sv["lse"], dq_acc, dqkv16, q_off=0, k_off=H, v_off=2 * H,
                          head_dim=hd, nheads=nh, nprob=B, L_tok=Lq, scale=1.0 / math.sqrt(hd), key_bias=kb,

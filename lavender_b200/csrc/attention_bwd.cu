@@ -335,7 +335,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 // 16-byte loads, HD/8 lanes per head).  Read once here instead of once per key chunk by a single thread per row.
 template <int HD>
 __global__ void __launch_bounds__(256)
-attn_delta_kernel(const __half* o, int64_t ldo, const __half* dout, int64_t lddo, float* delta, int64_t rows, int nheads) {
+attn_delta_kernel(const __half* o, int64_t ldo, const __half* dout, int64_t lddo, float* delta, int64_t rows, int nheads,
+                  float* dq_acc, int64_t lddq) {
   griddep_launch();  // dependents (GEMMs) may start their prologue under this kernel's tail
   constexpr int LPH = HD / 8;  // lanes per head
   const int lane = threadIdx.x & 31;
@@ -357,6 +358,10 @@ attn_delta_kernel(const __half* o, int64_t ldo, const __half* dout, int64_t lddo
 #pragma unroll
       for (int o2 = 1; o2 < LPH; o2 <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
       if (in && (lane & (LPH - 1)) == 0) delta[(int64_t)(c0 / HD) * rows + r] = acc;
+      if (in) {  // the dQ accumulator of this row segment starts from zero (the main kernel reduces into it)
+        float4* z = reinterpret_cast<float4*>(dq_acc + r * lddq + c0);
+        z[0] = make_float4(0.f, 0.f, 0.f, 0.f), z[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
   }
 }
@@ -443,16 +448,18 @@ extern "C" int lav_attn_bwd_f16(const void* qkv, int64_t ld, int64_t rows_total,
   p.drop = make_drop(drop);
   cudaStream_t s = (cudaStream_t)stream;
   p.delta = delta_ws;
+  LAV_REQUIRE((lddq % 4) == 0 && ((uintptr_t)dq_acc % 16) == 0, "lav_attn_bwd_f16: dq_acc rows must be 16-byte aligned");
   {
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((rows_total + 7) / 8, (int64_t)sm_count() * 8));
     if (head_dim == 32)
-      attn_delta_kernel<32><<<grid, 256, 0, s>>>((const __half*)out16, ldo, (const __half*)dout16, lddo, delta_ws, rows_total, nheads);
+      attn_delta_kernel<32><<<grid, 256, 0, s>>>((const __half*)out16, ldo, (const __half*)dout16, lddo, delta_ws, rows_total, nheads,
+                                                 dq_acc, lddq);
     else
-      attn_delta_kernel<64><<<grid, 256, 0, s>>>((const __half*)out16, ldo, (const __half*)dout16, lddo, delta_ws, rows_total, nheads);
+      attn_delta_kernel<64><<<grid, 256, 0, s>>>((const __half*)out16, ldo, (const __half*)dout16, lddo, delta_ws, rows_total, nheads,
+                                                 dq_acc, lddq);
     LAV_CHECK_CUDA(cudaGetLastError());
     count_launch();
   }
-  LAV_REQUIRE((lddq % 4) == 0 && ((uintptr_t)dq_acc % 16) == 0, "lav_attn_bwd_f16: dq_acc rows must be 16-byte aligned");
   if (head_dim == 32 && bias16) return launch_attn_bwd<32, true>(qkv, ld, p, nkc, s);
   return head_dim == 32 ? launch_attn_bwd<32, false>(qkv, ld, p, nkc, s) : launch_attn_bwd<64, false>(qkv, ld, p, nkc, s);
 }

@@ -433,7 +433,7 @@ def _block_bwd(ar, blk, g, sv, ds_ws, dev):
     linear_wgrad(go16, sv["o16"], ar.g(at.proj.weight), ar.g(at.proj.bias))
     do16 = empty16(M, C, device=dev)
     linear_dgrad(go16, ar.w16(at.proj.weight), do16)
-    dq_acc = torch.zeros(M, C, dtype=F32, device=dev)
+    dq_acc = empty32(M, C, device=dev)   # zeroed by the attention backward's pre-pass
     dqkv16 = empty16(M, 3 * C, device=dev)
     # dS workspace: two buffers per shape, alternated, because the table-gradient reduction that reads one of them runs
     # on the side stream (off the critical path, like the weight gradients) while the next block's attention backward
