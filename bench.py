@@ -191,8 +191,19 @@ def run_native(a):
         agent.backward_step(l1 + l2)
         return l1, l2
 
+    # End to end through the Agent API, inputs in pinned host memory.  Software-pipelined as a training loop would be:
+    # while step i runs on the GPU the host masks batch i+1 and its H2D copy proceeds on a copy stream; every step
+    # still copies its own inputs (h2d_bytes_per_step) and reads its own two losses back (d2h_bytes_per_step).
+    pipe = {"h": None}
+
     def step_e2e():
-        return agent.step(agent.prepare_batch(masked_host()), True)   # H2D + fwd/bwd/opt + 2x .item()
+        if a.no_pipeline:
+            return agent.step(agent.prepare_batch(masked_host()), True)   # H2D + fwd/bwd/opt + 2x .item(), serial
+        if pipe["h"] is None:
+            pipe["h"] = agent.prefetch(masked_host())
+        pend = agent.step_async(pipe["h"])
+        pipe["h"] = agent.prefetch(masked_host())
+        return agent.finish(pend)
 
     def barrier():
         if world > 1:
@@ -260,15 +271,23 @@ def run_native(a):
         # The eager step is host-bound (one ctypes call per kernel): with an idle GPU the event pair around a launch
         # would also time the host's launch latency.  A device-side spin first lets the host run ahead, so the queue
         # stays full and every event pair brackets device time only.
+        from lavender_b200 import streams as _streams
+        side_was, _streams._ENABLED = _streams._ENABLED, False   # one stream: a pair brackets exactly one kernel
         torch.cuda._sleep(int(0.4 * 1.9e9))
+        cal = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(64)]
+        for c0, c1 in cal:   # cost of an empty event pair in a full queue, subtracted from every launch below
+            c0.record()
+            c1.record()
         t0.record()
         step_eager()
         agent.optzr.zero_grad(set_to_none=True)
         t1.record()
         torch.cuda.synchronize()
+        _streams._ENABLED = side_was
+        pair = sorted(c0.elapsed_time(c1) for c0, c1 in cal)[len(cal) // 2]
         for name, s, e, fl, _meta in ops.PROFILE:
             f = fams.setdefault(name, {"ms": 0.0, "flops": 0.0, "launches": 0})
-            f["ms"] += s.elapsed_time(e)
+            f["ms"] += max(s.elapsed_time(e) - pair, 0.0)
             f["flops"] += fl
             f["launches"] += 1
         step_ms_prof = t0.elapsed_time(t1)
@@ -306,7 +325,9 @@ def run_native(a):
         "clocks": summarize_clocks(samples), "cuda_graph": bool(args.cuda_graph),
         "e2e": {"value": round(clips / (ms_e2e * 1e-3), 2), "unit": "clips/s",
                 "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values()) + B * 33 * 8),
-                "d2h_bytes_per_step": 8, "ms_per_step": round(ms_e2e / a.steps, 3)},
+                "d2h_bytes_per_step": 8, "ms_per_step": round(ms_e2e / a.steps, 3),
+                "api": "Agent_Pretrain_MLM.step" if a.no_pipeline else
+                "Agent_Pretrain_MLM.prefetch / step_async / finish (next batch's masking + H2D under this step)"},
         "gpu_launches": int(launches) if not args.cuda_graph else
         int(agent.graphs.get(dev_batch).native_launches * a.steps),
         "loss": {"mtm": round(float(last[0].detach()), 4), "vtm": round(float(last[1].detach()), 4)},
@@ -314,8 +335,10 @@ def run_native(a):
                      "frac": round(tf / peak_tf, 4), "traffic": None, "peak_source": peak_src,
                      "launches_per_step": fams[top]["launches"], "ms_per_step": round(fams[top]["ms"], 3),
                      "share_of_step": round(fams[top]["ms"] / max(kern_total, 1e-9), 3),
-                     "how": "CUDA events around every launch of one eager step issued behind a device-side spin (queue "
-                            "kept full, so the pairs bracket device time); share = of the summed kernel time"},
+                     "how": "CUDA events around every launch of one single-stream eager step issued behind a "
+                            "device-side spin (queue kept full, so a pair brackets device time), minus the measured cost "
+                            "of an empty event pair; share = of the summed kernel time",
+                     "event_pair_us": round(pair * 1e3, 2)},
         "step_roofline": {"achieved": round(step_flops / (ms / a.steps * 1e-3) / 1e12, 1), "peak": peak_tf,
                           "unit": "TFLOP/s", "frac": round(step_flops / (ms / a.steps * 1e-3) / 1e12 / peak_tf, 4)},
         "kernels": {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
@@ -412,6 +435,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--quick", action="store_true", help="resident steps only (for ncu runs)")
+    ap.add_argument("--no-pipeline", action="store_true", help="e2e leg without the prefetch pipeline (serial H2D)")
     ap.add_argument("--profile-step", action="store_true",
                     help="one eager step between cudaProfilerStart/Stop (ncu --profile-from-start off)")
     ap.add_argument("--eval-dropout", action="store_true",

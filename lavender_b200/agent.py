@@ -211,15 +211,54 @@ class Agent_Pretrain_MLM(Agent_Base):
         gt = (lab == self.true_token_id).nonzero()[:, 1]
         return float((pred == gt).float().sum() / B)
 
-    def step(self, batch, is_train=True):
-        self.model.train(is_train)
-        if is_train and getattr(self.args, "cuda_graph", False) and batch.get("vtm_prompt") is None:
+    def _train_step_device(self, batch):
+        """One training step, everything enqueued, nothing read back: returns the two losses as device scalars."""
+        self.model.train(True)
+        if getattr(self.args, "cuda_graph", False) and batch.get("vtm_prompt") is None:
             if self.graphs is None:
                 from .graph import GraphCache
                 self.graphs = GraphCache(self)
             ls_mtm, ls_vtm = self.graphs.get(batch)(batch)
             self.backward_step(None, graphed=True)
-            return {"mtm": ls_mtm.item(), "vtm": ls_vtm.item()}
+            return ls_mtm, ls_vtm
+        out = self.forward_step(batch)
+        out_mtm, out_vtm, ans_mtm, ans_vtm = out["out_mtm"], out["out_vtm"], out["ans_mtm"], out["ans_vtm"]
+        ls_mtm = self.loss_func(out_mtm.flatten(0, out_mtm.dim() - 2), ans_mtm.flatten())
+        ls_vtm = self.cal_vtm_loss(batch["txt"], out_vtm, ans_vtm, True)
+        self.backward_step(ls_mtm + ls_vtm)
+        return ls_mtm.detach(), ls_vtm.detach()
+
+    # ---- pipelined input path: the next batch's host work and H2D copy run under the current step's kernels ----
+    def prefetch(self, host_batch):
+        """Starts the host->device copy of a (masked, ideally pinned) host batch on a copy stream and returns a handle
+        for `step_async`.  Called right after `step_async` of the previous batch, it overlaps that step's compute."""
+        if self.__dict__.get("_copy_stream") is None:
+            self._copy_stream = torch.cuda.Stream()
+        with torch.cuda.stream(self._copy_stream):
+            dev = self.prepare_batch(host_batch)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        return dev, ev
+
+    def step_async(self, handle):
+        """Enqueues one training step on the batch of `prefetch`; returns the pending losses (see `finish`)."""
+        dev, ev = handle
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev)
+        for v in dev.values():   # allocated on the copy stream, consumed here: keep the allocator from recycling early
+            if isinstance(v, torch.Tensor) and v.is_cuda:
+                v.record_stream(cur)
+        return self._train_step_device(dev)
+
+    @staticmethod
+    def finish(pending):
+        """Device->host read of a step's two losses (the only synchronisation of the step)."""
+        return {"mtm": pending[0].item(), "vtm": pending[1].item()}
+
+    def step(self, batch, is_train=True):
+        self.model.train(is_train)
+        if is_train and getattr(self.args, "cuda_graph", False) and batch.get("vtm_prompt") is None:
+            return self.finish(self._train_step_device(batch))
         with torch.set_grad_enabled(is_train):
             out = self.forward_step(batch)
             out_mtm, out_vtm, ans_mtm, ans_vtm = out["out_mtm"], out["out_vtm"], out["ans_mtm"], out["ans_vtm"]

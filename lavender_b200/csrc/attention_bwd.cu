@@ -13,7 +13,7 @@
 
 namespace lav {
 
-constexpr int kAttnBwdThreads = 160;
+constexpr int kAttnBwdThreads = 288;  // warps 0-7: softmax (lane quarter w & 3, key-column half w >> 2); warp 8: TMA + MMA + TMEM
 
 struct AttnBwdParams {
   int L, nheads, nprob;
@@ -69,11 +69,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const int nqt = (p.L + 127) / 128;
   const int jmax = min(128, (p.L - c * 128 + 31) & ~31);  // key columns of this chunk that can hold a valid key
 
-  if (BMMA && warp < 4) {  // identity strip (zeros with a 16 x 16 identity block at groups 14-15), as in attention_fwd.cu
+  if (BMMA && warp < 8) {  // identity strip (zeros with a 16 x 16 identity block at groups 14-15), as in attention_fwd.cu
     uint8_t* id = smem + Cfg::OFF_ID;
-    for (int i = threadIdx.x; i < kIdentBytesB / 16; i += 128) reinterpret_cast<uint4*>(id)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < kIdentBytesB / 16; i += 256) reinterpret_cast<uint4*>(id)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncwarp();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     if (threadIdx.x < 16) {
       const int r = threadIdx.x;
       const int off = r < 8 ? 14 * 256 + r * 16 + r * 2 : 15 * 256 + 128 + (r - 8) * 16 + (r - 8) * 2;
@@ -81,7 +81,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     }
     fence_proxy_async_smem();
   }
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       tma_prefetch_desc(&tmQKV);
       tma_prefetch_desc(&tmDO);
@@ -90,7 +90,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       mbar_init(bars + 1, 1);
       mbar_init(bars + 2, 1);
       mbar_init(bars + 3, 1);
-      mbar_init(bars + 4, 128);
+      mbar_init(bars + 4, 256);
       mbar_init(bars + 5, 1);
       fence_barrier_init();
     }
@@ -102,7 +102,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       const int bcls = (BMMA && p.prob_class) ? p.prob_class[prob % p.period] : 0;
       auto load_q = [&](int t) {
@@ -182,8 +182,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       }
     }
   } else {
-    const int i = warp * 32 + lane;
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    // 8 softmax warps: warp w owns accumulator rows (w & 3) * 32 .. +31 (its TMEM lane quarter) and the key columns
+    // [hsel * 64, hsel * 64 + 64) of the chunk (hsel = w >> 2): two threads per query row halve the latency-bound
+    // exp / dS phase; no cross-thread reduction is needed in backward (lse and delta are known per row).
+    const int hsel = warp >> 2;
+    const int i = (warp & 3) * 32 + lane;
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    constexpr int HW = HD / 2;  // output columns of dQ / dK / dV handled by each half
     const float sc_log2 = p.scale * 1.4426950408889634f;
     const int cls = (p.bias16 && p.prob_class) ? p.prob_class[prob % p.period] : 0;
     const float* kb = p.key_bias ? p.key_bias + (size_t)prob * p.NPk + c * 128 : nullptr;
@@ -207,7 +212,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       mbar_wait(bars + 3, t & 1, 24);
       tc_fence_after();
 #pragma unroll 1
-      for (int j0 = 0; j0 < jmax; j0 += 32) {
+      for (int j0 = hsel * 64; j0 < min(jmax, hsel * 64 + 64); j0 += 32) {
         uint32_t s[32], dp[32];
         tmem_ld_32x32(trow + Cfg::COL_S + j0, s);
         tmem_ld_32x32(trow + Cfg::COL_DP + j0, dp);
@@ -280,15 +285,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
       mbar_wait(bars + 5, t & 1, 25);
       tc_fence_after();
-#pragma unroll
-      for (int c0 = 0; c0 < HD; c0 += 32) {
-        uint32_t o[32];
-        tmem_ld_32x32(trow + Cfg::COL_DQ + c0, o);
+      {
+        uint32_t o[HW];
+        tmem_ld_cols<HW>(trow + Cfg::COL_DQ + hsel * HW, o);
         tmem_ld_wait();
         if (valid) {
-          float* dst = p.dq_acc + (size_t)(row0 + qi) * p.lddq + h * HD + c0;
+          float* dst = p.dq_acc + (size_t)(row0 + qi) * p.lddq + h * HD + hsel * HW;
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
+          for (int j = 0; j < HW / 4; ++j)
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j),
                          "f"(__uint_as_float(o[4 * j]) * p.scale), "f"(__uint_as_float(o[4 * j + 1]) * p.scale),
                          "f"(__uint_as_float(o[4 * j + 2]) * p.scale), "f"(__uint_as_float(o[4 * j + 3]) * p.scale)
@@ -300,17 +304,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     // ---- dK_c, dV_c : thread = key row of this chunk
     const int kj = c * 128 + i;
     const bool kvalid = kj < p.L;
-#pragma unroll
-    for (int c0 = 0; c0 < HD; c0 += 32) {
-      uint32_t dk[32], dv[32];
-      tmem_ld_32x32(trow + Cfg::COL_DK + c0, dk);
-      tmem_ld_32x32(trow + Cfg::COL_DV + c0, dv);
+    {
+      uint32_t dk[HW], dv[HW];
+      tmem_ld_cols<HW>(trow + Cfg::COL_DK + hsel * HW, dk);
+      tmem_ld_cols<HW>(trow + Cfg::COL_DV + hsel * HW, dv);
       tmem_ld_wait();
       if (kvalid) {
-        __half* gk = p.dqkv + (size_t)(row0 + kj) * p.lddqkv + p.k_off + h * HD + c0;
-        __half* gv = p.dqkv + (size_t)(row0 + kj) * p.lddqkv + p.v_off + h * HD + c0;
+        __half* gk = p.dqkv + (size_t)(row0 + kj) * p.lddqkv + p.k_off + h * HD + hsel * HW;
+        __half* gv = p.dqkv + (size_t)(row0 + kj) * p.lddqkv + p.v_off + h * HD + hsel * HW;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < HW / 8; ++j) {
           uint4 u, w;
           u.x = pack_half2(__uint_as_float(dk[8 * j]) * p.scale, __uint_as_float(dk[8 * j + 1]) * p.scale);
           u.y = pack_half2(__uint_as_float(dk[8 * j + 2]) * p.scale, __uint_as_float(dk[8 * j + 3]) * p.scale);
@@ -328,7 +331,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc<512>(tmem);
+  if (warp == 8) tmem_dealloc<512>(tmem);
 }
 
 // delta[h][row] = sum_d dO[row, h*HD + d] * O[row, h*HD + d]   (softmax backward's row term; one warp per row,
