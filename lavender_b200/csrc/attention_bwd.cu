@@ -98,6 +98,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     tmem_alloc<512>(tmem_slot);
   }
   tc_fence_before();
+  griddep_wait();  // the prologue above touched no global data; from here on it does (PDL, see gemm.cu)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
@@ -341,6 +342,7 @@ __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __half* o, int64_t ldo, const __half* dout, int64_t lddo, float* delta, int64_t rows, int nheads,
                   float* dq_acc, int64_t lddq) {
   griddep_launch();  // dependents (GEMMs) may start their prologue under this kernel's tail
+  griddep_wait();    // launched with the PDL attribute: wait before touching global data
   constexpr int LPH = HD / 8;  // lanes per head
   const int lane = threadIdx.x & 31;
   const int C = nheads * HD;
@@ -374,6 +376,7 @@ __global__ void __launch_bounds__(256)
 relpos_bias_grad_kernel(const __half* ds, int nprob, int nheads, int NP, int L, const int32_t* rel_index,
                         float* dtable, int probs_per_block) {
   griddep_launch();  // dependents (GEMMs) may start their prologue under this kernel's tail
+  griddep_wait();    // launched with the PDL attribute: wait before touching global data
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);  // (h, i)
   if (row >= nheads * L) return;
@@ -417,7 +420,7 @@ static int launch_attn_bwd(const void* qkv, int64_t ld, const AttnBwdParams& p, 
     attr_set = true;
   }
   dim3 grid(nkc, p.nheads, p.nprob);
-  kern<<<grid, kAttnBwdThreads, Cfg::SMEM_BYTES, s>>>(tq, tdo, tb, p);
+  LAV_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kAttnBwdThreads), Cfg::SMEM_BYTES, s, tq, tdo, tb, p));
   LAV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return LAV_OK;
@@ -455,11 +458,11 @@ extern "C" int lav_attn_bwd_f16(const void* qkv, int64_t ld, int64_t rows_total,
   {
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((rows_total + 7) / 8, (int64_t)sm_count() * 8));
     if (head_dim == 32)
-      attn_delta_kernel<32><<<grid, 256, 0, s>>>((const __half*)out16, ldo, (const __half*)dout16, lddo, delta_ws, rows_total, nheads,
-                                                 dq_acc, lddq);
+      LAV_CHECK_CUDA(launch_pdl(attn_delta_kernel<32>, dim3(grid), dim3(256), 0, s, (const __half*)out16, ldo, (const __half*)dout16, lddo, delta_ws, rows_total, nheads,
+                                                 dq_acc, lddq));
     else
-      attn_delta_kernel<64><<<grid, 256, 0, s>>>((const __half*)out16, ldo, (const __half*)dout16, lddo, delta_ws, rows_total, nheads,
-                                                 dq_acc, lddq);
+      LAV_CHECK_CUDA(launch_pdl(attn_delta_kernel<64>, dim3(grid), dim3(256), 0, s, (const __half*)out16, ldo, (const __half*)dout16, lddo, delta_ws, rows_total, nheads,
+                                                 dq_acc, lddq));
     LAV_CHECK_CUDA(cudaGetLastError());
     count_launch();
   }
@@ -475,8 +478,8 @@ extern "C" int lav_relpos_bias_grad(const void* ds16, int nprob, int nheads, int
   int slabs = std::max(1, std::min(nprob, (4 * sm_count() + xb - 1) / xb));
   const int ppb = (nprob + slabs - 1) / slabs;
   dim3 grid(xb, (nprob + ppb - 1) / ppb);
-  relpos_bias_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)ds16, nprob, nheads, NP, L, rel_index,
-                                                                 dtable, ppb);
+  LAV_CHECK_CUDA(launch_pdl(relpos_bias_grad_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const __half*)ds16, nprob, nheads, NP, L, rel_index,
+                                                                 dtable, ppb));
   LAV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return LAV_OK;

@@ -88,6 +88,7 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
     tmem_alloc<256>(tmem_slot);
   }
   tc_fence_before();
+  griddep_wait();  // the prologue above touched no global data; from here on it does (PDL, see gemm.cu)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
@@ -308,7 +309,7 @@ static int launch_flash(const void* qkv, int64_t ld, int64_t rows_total, const v
     attr_set = true;
   }
   dim3 grid((p.L + 127) / 128, p.nheads, p.nprob);
-  kern<<<grid, kFlashThreads, Cfg::SMEM_BYTES, s>>>(tm, tmb, p);
+  LAV_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kFlashThreads), Cfg::SMEM_BYTES, s, tm, tmb, p));
   LAV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return LAV_OK;

@@ -97,6 +97,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   }
   tc_fence_before();
+  griddep_wait();  // the prologue above touched no global data; from here on it does (PDL, see gemm.cu)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
@@ -296,7 +297,7 @@ static int launch_attn_fwd(const void* qkv, int64_t ld, int64_t rows_total, cons
     attr_set = true;
   }
   dim3 grid((p.L + 127) / 128, p.nheads, p.nprob);
-  kern<<<grid, kAttnThreads, Cfg::SMEM_BYTES, s>>>(tm, tmb, p);
+  LAV_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kAttnThreads), Cfg::SMEM_BYTES, s, tm, tmb, p));
   LAV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return LAV_OK;
@@ -311,6 +312,7 @@ constexpr float kMaskedKey = -30000.0f;
 __global__ void relpos_bias_expand_kernel(const float* table, int nheads, const int32_t* rel_index, int L,
                                           const uint8_t* labels, int ncls, __half* dense, int NP, float inv_scale) {
   griddep_launch();  // dependents (GEMMs) may start their prologue under this kernel's tail
+  griddep_wait();    // launched with the PDL attribute: wait before touching global data
   const int i = blockIdx.x, h = blockIdx.y, cls = blockIdx.z;
   __half* drow = dense + (((size_t)cls * nheads + h) * NP + i) * NP;
   for (int j = threadIdx.x; j < NP; j += blockDim.x) {
@@ -375,8 +377,8 @@ extern "C" int lav_relpos_bias_expand(const float* table, int nheads, const int3
                                       void* stream) {
   LAV_REQUIRE(table && rel_index && dense16 && ncls >= 1 && L <= NP, "lav_relpos_bias_expand: bad arguments");
   dim3 grid(NP, nheads, ncls);
-  relpos_bias_expand_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(table, nheads, rel_index, L, labels, ncls,
-                                                                   (__half*)dense16, NP, inv_scale);
+  LAV_CHECK_CUDA(launch_pdl(relpos_bias_expand_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, table, nheads, rel_index, L, labels, ncls,
+                                                                   (__half*)dense16, NP, inv_scale));
   LAV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return LAV_OK;

@@ -24,14 +24,6 @@ constexpr int kEpiWarpBytes = 8192;  // >= 32 * kEpiStride * 4; four 2 KB (fp16)
 // wins on large square problems (8192^3: 1342 vs 1150 TFLOP/s) but not on the hot path's shapes, whose cost is the
 // epilogue and the per-launch prologue rather than the operand feed (profiles/r1d_gemm_sweep.md), so it is opt-in.
 static int work_streams(int ncta) { return ncta == 2 ? std::max(1, sm_count() / 2) : sm_count(); }
-static bool pdl_enabled() {  // LAV_PDL=0 disables programmatic dependent launch of the GEMM kernels
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("LAV_PDL");
-    v = (e && e[0] == '0') ? 0 : 1;
-  }
-  return v == 1;
-}
 static bool pair_enabled() {
   static int v = -1;
   if (v < 0) {

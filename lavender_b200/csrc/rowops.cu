@@ -29,7 +29,8 @@ struct LnFwdParams {
 };
 
 __global__ void __launch_bounds__(kRowThreads) ln_fwd_kernel(const LnFwdParams p) {
-  griddep_launch();  // dependents (GEMMs) may start their prologue under this kernel's tail
+  griddep_launch();  // the next kernel may start its prologue under this kernel's tail
+  griddep_wait();    // (this one may have started under its predecessor's: wait before touching global data)
   const int lane = threadIdx.x & 31;
   const int wpb = kRowThreads / 32;
   const int W = p.G * p.C;  // normalised width
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(kRowThreads) ln_fwd_kernel(const LnFwdParams p
 template <int NV>
 __global__ void __launch_bounds__(kRowThreads) ln_fwd_reg_kernel(const LnFwdParams p) {
   griddep_launch();
+  griddep_wait();
   const int lane = threadIdx.x & 31;
   const int wpb = kRowThreads / 32;
   const int c4 = p.C >> 2;
@@ -174,7 +176,8 @@ __device__ __forceinline__ float4 load_dy4(const LnBwdParams& p, int r, int col)
 // the separate parameter-gradient pass (a second read of x and dy) disappears.
 template <bool PARAMS, int NV = 8>  // NV: float4 column groups per lane kept in registers (C <= 128 * NV)
 __global__ void __launch_bounds__(kRowThreads) ln_bwd_kernel(const LnBwdParams p) {
-  griddep_launch();  // dependents (GEMMs) may start their prologue under this kernel's tail
+  griddep_launch();  // the next kernel may start its prologue under this kernel's tail
+  griddep_wait();    // (this one may have started under its predecessor's: wait before touching global data)
   const int lane = threadIdx.x & 31;
   const int wpb = kRowThreads / 32;
   const int W = p.G * p.C;
@@ -318,6 +321,7 @@ __global__ void __launch_bounds__(kRowThreads) ln_bwd_kernel(const LnBwdParams p
 // dgamma[c] += sum_b ws[b][0][c] ; dbeta[c] += sum_b ws[b][1][c]   (second stage of the fused parameter gradients)
 __global__ void __launch_bounds__(1024) ln_param_reduce_kernel(const float* ws, int nblocks, int C, float* dgamma, float* dbeta) {
   griddep_launch();
+  griddep_wait();
   // block = 32 columns x 32 row slabs: coalesced 128-byte reads, 32-way parallel over the partial rows
   __shared__ float sm[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -340,7 +344,8 @@ __global__ void __launch_bounds__(1024) ln_param_reduce_kernel(const float* ws, 
 // Block = 8 warps; a warp covers 128 consecutive columns (one float4 / 4 halfs per lane) of one row at a time and
 // walks the rows of its slab with stride 8; partial sums meet in shared memory, one atomic per column per block.
 __global__ void __launch_bounds__(256) ln_bwd_params_kernel(const LnBwdParams p, int rows_per_block) {
-  griddep_launch();  // dependents (GEMMs) may start their prologue under this kernel's tail
+  griddep_launch();  // the next kernel may start its prologue under this kernel's tail
+  griddep_wait();    // (this one may have started under its predecessor's: wait before touching global data)
   __shared__ float sg[8][128], sb[8][128];
   const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
   const int W = p.G * p.C;
@@ -381,7 +386,8 @@ __global__ void __launch_bounds__(256) ln_bwd_params_kernel(const LnBwdParams p,
 __global__ void __launch_bounds__(kRowThreads)
 scale_cast_kernel(const float* x, int64_t ldx, const int32_t* map, const float* scale, int rows_per_scale, float alpha,
                   __half* out, int64_t ldo, int rows, int C) {
-  griddep_launch();  // dependents (GEMMs) may start their prologue under this kernel's tail
+  griddep_launch();  // the next kernel may start its prologue under this kernel's tail
+  griddep_wait();    // (this one may have started under its predecessor's: wait before touching global data)
   const int lane = threadIdx.x & 31, wpb = kRowThreads / 32;
   for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
     const int64_t sr = map ? map[r] : r;
@@ -402,7 +408,8 @@ scale_cast_kernel(const float* x, int64_t ldx, const int32_t* map, const float* 
 
 // flat fp32 -> fp16 (parameter shadow copy)
 __global__ void __launch_bounds__(256) cast_flat_kernel(const float* __restrict__ src, __half* __restrict__ dst, int64_t n) {
-  griddep_launch();  // dependents (GEMMs) may start their prologue under this kernel's tail
+  griddep_launch();  // the next kernel may start its prologue under this kernel's tail
+  griddep_wait();    // (this one may have started under its predecessor's: wait before touching global data)
   const int64_t n4 = n >> 2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 v = reinterpret_cast<const float4*>(src)[i];
@@ -416,7 +423,8 @@ __global__ void __launch_bounds__(256) cast_flat_kernel(const float* __restrict_
 // one row (one 16-byte load per lane) and walks its slab of rows with stride 8.  Needs ld % 8 == 0.
 __global__ void __launch_bounds__(256)
 colsum_f16_kernel(const __half* x, int64_t ld, int rows, int N, float* out, float alpha, int rows_per_block) {
-  griddep_launch();  // dependents (GEMMs) may start their prologue under this kernel's tail
+  griddep_launch();  // the next kernel may start its prologue under this kernel's tail
+  griddep_wait();    // (this one may have started under its predecessor's: wait before touching global data)
   __shared__ float sm[8][256];
   const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + lane * 8;
@@ -447,7 +455,8 @@ colsum_f16_kernel(const __half* x, int64_t ld, int rows, int N, float* out, floa
 
 // out16 = dy16 * gelu_erf'(pre16)   (flat, n % 2 == 0)
 __global__ void __launch_bounds__(256) gelu_bwd_kernel(const __half2* dy, const __half2* pre, __half2* out, int64_t n2) {
-  griddep_launch();  // dependents (GEMMs) may start their prologue under this kernel's tail
+  griddep_launch();  // the next kernel may start its prologue under this kernel's tail
+  griddep_wait();    // (this one may have started under its predecessor's: wait before touching global data)
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
     float2 d = __half22float2(dy[i]), x = __half22float2(pre[i]);
     out[i] = __floats2half2_rn(d.x * gelu_erf_grad(x.x), d.y * gelu_erf_grad(x.y));
@@ -457,7 +466,8 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const __half2* dy, const 
 // out = x * keep / (1 - p), fp32 [rows, C], one thread per 8 consecutive columns (one Philox call)
 __global__ void __launch_bounds__(256)
 dropout_f32_kernel(const float* x, int64_t ldx, float* out, int64_t ldo, int rows, int C8, const DropParams d) {
-  griddep_launch();  // dependents (GEMMs) may start their prologue under this kernel's tail
+  griddep_launch();  // the next kernel may start its prologue under this kernel's tail
+  griddep_wait();    // (this one may have started under its predecessor's: wait before touching global data)
   const DropKey key = drop_key(d);
   const int64_t n = (int64_t)rows * C8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -476,7 +486,8 @@ dropout_f32_kernel(const float* x, int64_t ldx, float* out, int64_t ldo, int row
 
 __global__ void __launch_bounds__(256)
 dropout_mask_kernel(uint8_t* keep, int rows, int C, int head, const DropParams d) {
-  griddep_launch();  // dependents (GEMMs) may start their prologue under this kernel's tail
+  griddep_launch();  // the next kernel may start its prologue under this kernel's tail
+  griddep_wait();    // (this one may have started under its predecessor's: wait before touching global data)
   const DropKey key = drop_key(d);
   const int C8 = (C + 7) / 8;
   const int64_t n = (int64_t)rows * C8;
@@ -510,12 +521,12 @@ extern "C" int lav_layernorm_fwd(const float* x, int64_t ldx, const int32_t* row
   if (G == 1 && C <= 1024) {
     const int grid = row_grid(rows);
     cudaStream_t st = (cudaStream_t)stream;
-    if (C <= 128) ln_fwd_reg_kernel<1><<<grid, kRowThreads, 0, st>>>(p);
-    else if (C <= 256) ln_fwd_reg_kernel<2><<<grid, kRowThreads, 0, st>>>(p);
-    else if (C <= 512) ln_fwd_reg_kernel<4><<<grid, kRowThreads, 0, st>>>(p);
-    else ln_fwd_reg_kernel<8><<<grid, kRowThreads, 0, st>>>(p);
+    if (C <= 128) LAV_CHECK_CUDA(launch_pdl(ln_fwd_reg_kernel<1>, dim3(grid), dim3(kRowThreads), 0, st, p));
+    else if (C <= 256) LAV_CHECK_CUDA(launch_pdl(ln_fwd_reg_kernel<2>, dim3(grid), dim3(kRowThreads), 0, st, p));
+    else if (C <= 512) LAV_CHECK_CUDA(launch_pdl(ln_fwd_reg_kernel<4>, dim3(grid), dim3(kRowThreads), 0, st, p));
+    else LAV_CHECK_CUDA(launch_pdl(ln_fwd_reg_kernel<8>, dim3(grid), dim3(kRowThreads), 0, st, p));
   } else {
-    ln_fwd_kernel<<<row_grid(rows), kRowThreads, 0, (cudaStream_t)stream>>>(p);
+    LAV_CHECK_CUDA(launch_pdl(ln_fwd_kernel, dim3(row_grid(rows)), dim3(kRowThreads), 0, (cudaStream_t)stream, p));
   }
   LAV_CHECK_CUDA(cudaGetLastError());
   count_launch();
@@ -549,14 +560,14 @@ extern "C" int lav_layernorm_bwd(const void* dy, int64_t lddy, int dy_is_f32, co
       LAV_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024 * 4));
       attr_set = true;
     }
-    if (nv == 1) ln_bwd_kernel<true, 1><<<grid, kRowThreads, red_bytes, s>>>(p);
-    else if (nv == 2) ln_bwd_kernel<true, 2><<<grid, kRowThreads, red_bytes, s>>>(p);
-    else if (nv == 4) ln_bwd_kernel<true, 4><<<grid, kRowThreads, red_bytes, s>>>(p);
-    else ln_bwd_kernel<true, 8><<<grid, kRowThreads, red_bytes, s>>>(p);
+    if (nv == 1) LAV_CHECK_CUDA(launch_pdl(ln_bwd_kernel<true, 1>, dim3(grid), dim3(kRowThreads), red_bytes, s, p));
+    else if (nv == 2) LAV_CHECK_CUDA(launch_pdl(ln_bwd_kernel<true, 2>, dim3(grid), dim3(kRowThreads), red_bytes, s, p));
+    else if (nv == 4) LAV_CHECK_CUDA(launch_pdl(ln_bwd_kernel<true, 4>, dim3(grid), dim3(kRowThreads), red_bytes, s, p));
+    else LAV_CHECK_CUDA(launch_pdl(ln_bwd_kernel<true, 8>, dim3(grid), dim3(kRowThreads), red_bytes, s, p));
     LAV_CHECK_CUDA(cudaGetLastError());
     count_launch();
     if (p.param_ws) {
-      ln_param_reduce_kernel<<<(2 * C + 31) / 32, 1024, 0, s>>>(p.param_ws, grid, C, dgamma, dbeta);
+      LAV_CHECK_CUDA(launch_pdl(ln_param_reduce_kernel, dim3((2 * C + 31) / 32), dim3(1024), 0, s, p.param_ws, grid, C, dgamma, dbeta));
       LAV_CHECK_CUDA(cudaGetLastError());
       count_launch();
     }
@@ -566,11 +577,11 @@ extern "C" int lav_layernorm_bwd(const void* dy, int64_t lddy, int dy_is_f32, co
     const int cb = (G * C + 127) / 128;
     const int rpb = slab_rows(rows, cb);
     dim3 grid(cb, (rows + rpb - 1) / rpb);
-    ln_bwd_params_kernel<<<grid, 256, 0, s>>>(p, rpb);
+    LAV_CHECK_CUDA(launch_pdl(ln_bwd_params_kernel, dim3(grid), dim3(256), 0, s, p, rpb));
     LAV_CHECK_CUDA(cudaGetLastError());
     count_launch();
   }
-  ln_bwd_kernel<false><<<row_grid(rows), kRowThreads, 0, s>>>(p);
+  LAV_CHECK_CUDA(launch_pdl(ln_bwd_kernel<false>, dim3(row_grid(rows)), dim3(kRowThreads), 0, s, p));
   LAV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return LAV_OK;
@@ -582,8 +593,8 @@ extern "C" int lav_scale_cast_f16(const float* x, int64_t ldx, const int32_t* ro
   LAV_REQUIRE(x && out16, "lav_scale_cast_f16: null pointer");
   LAV_REQUIRE((ldo % 4) == 0, "lav_scale_cast_f16: output ld must be %%4");
   if (rows <= 0) return LAV_OK;
-  scale_cast_kernel<<<row_grid(rows), kRowThreads, 0, (cudaStream_t)stream>>>(
-      x, ldx, row_map, row_scale, rows_per_scale > 0 ? rows_per_scale : 1, alpha, (__half*)out16, ldo, rows, C);
+  LAV_CHECK_CUDA(launch_pdl(scale_cast_kernel, dim3(row_grid(rows)), dim3(kRowThreads), 0, (cudaStream_t)stream, 
+      x, ldx, row_map, row_scale, rows_per_scale > 0 ? rows_per_scale : 1, alpha, (__half*)out16, ldo, rows, C));
   LAV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return LAV_OK;
@@ -594,7 +605,7 @@ extern "C" int lav_cast_f32_to_f16(const float* src, void* dst, int64_t n, void*
   LAV_REQUIRE(((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 8) == 0, "lav_cast_f32_to_f16: unaligned");
   if (n <= 0) return LAV_OK;
   int grid = (int)std::min<int64_t>((n / 4 + 255) / 256 + 1, (int64_t)sm_count() * 8);
-  cast_flat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, (__half*)dst, n);
+  LAV_CHECK_CUDA(launch_pdl(cast_flat_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, src, (__half*)dst, n));
   LAV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return LAV_OK;
@@ -607,7 +618,7 @@ extern "C" int lav_colsum_f16(const void* x16, int64_t ld, int rows, int N, floa
   const int cb = (N + 255) / 256;
   const int rpb = slab_rows(rows, cb);
   dim3 grid(cb, (rows + rpb - 1) / rpb);
-  colsum_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)x16, ld, rows, N, out, alpha, rpb);
+  LAV_CHECK_CUDA(launch_pdl(colsum_f16_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const __half*)x16, ld, rows, N, out, alpha, rpb));
   LAV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return LAV_OK;
@@ -617,7 +628,7 @@ extern "C" int lav_gelu_bwd_f16(const void* dy16, const void* pre16, void* out16
   LAV_REQUIRE(dy16 && pre16 && out16 && (n % 2) == 0, "lav_gelu_bwd_f16: bad arguments");
   if (n <= 0) return LAV_OK;
   int grid = (int)std::min<int64_t>((n / 2 + 255) / 256, (int64_t)sm_count() * 8);
-  gelu_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half2*)dy16, (const __half2*)pre16, (__half2*)out16, n / 2);
+  LAV_CHECK_CUDA(launch_pdl(gelu_bwd_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const __half2*)dy16, (const __half2*)pre16, (__half2*)out16, n / 2));
   LAV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return LAV_OK;
@@ -633,7 +644,7 @@ extern "C" int lav_dropout_f32(const float* x, int64_t ldx, float* out, int64_t 
   if (!d.on) d.on = 1, d.rng = drop->rng, d.site = drop->site, d.thresh = 0, d.inv_keep = 1.f;  // p == 0: copy
   const int64_t n = (int64_t)rows * (C / 8);
   const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 8);
-  dropout_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, out, ldo, rows, C / 8, d);
+  LAV_CHECK_CUDA(launch_pdl(dropout_f32_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, x, ldx, out, ldo, rows, C / 8, d));
   LAV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return LAV_OK;
@@ -646,7 +657,7 @@ extern "C" int lav_dropout_mask(uint8_t* keep, int rows, int C, int head, const 
   if (!d.on) d.on = 1, d.rng = drop->rng, d.site = drop->site, d.thresh = 0, d.inv_keep = 1.f;
   const int64_t n = (int64_t)rows * ((C + 7) / 8);
   const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 8);
-  dropout_mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(keep, rows, C, head, d);
+  LAV_CHECK_CUDA(launch_pdl(dropout_mask_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, keep, rows, C, head, d));
   LAV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return LAV_OK;

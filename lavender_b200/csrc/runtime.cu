@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 namespace lav {
@@ -19,6 +20,24 @@ int set_error(int code, const char* fmt, ...) {
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+bool pdl_enabled() {  // LAV_PDL=0 disables programmatic dependent launch
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LAV_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+bool pdl_all_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LAV_PDL_ALL");
+    v = (pdl_enabled() && e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
 
 int sm_count() {
   static int cached[64];
