@@ -27,6 +27,7 @@ class _Side:
         self.stream = torch.cuda.Stream(device=device)
         self.held = []
         self.dirty = False
+        self.cb_queued = False
 
 
 def enabled():
@@ -44,13 +45,14 @@ def _get(device):
 def fork(device):
     st = _get(device)
     st.stream.wait_stream(torch.cuda.current_stream(device))
-    if not st.dirty:
-        st.dirty = True
+    st.dirty = True
+    if not st.cb_queued:
         try:   # inside autograd's backward: join automatically when this backward pass ends, so that code which reads
             #    p.grad right after loss.backward() (a plain torch optimizer, clip_grad_norm_) is ordered after wgrad
             torch.autograd.Variable._execution_engine.queue_callback(lambda: join(device))
+            st.cb_queued = True
         except RuntimeError:
-            pass   # not called from a backward pass (direct use of the functional API): the caller joins
+            pass   # not in a backward pass (forward-side use, direct functional calls): the caller synchronises
     return st.stream
 
 
@@ -68,3 +70,4 @@ def join(device):
     torch.cuda.current_stream(device).wait_stream(st.stream)
     st.held.clear()
     st.dirty = False
+    st.cb_queued = False
