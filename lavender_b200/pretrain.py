@@ -7,6 +7,7 @@ RNG call sequence (main_pretrain_mlm.py:90) and therefore the outputs are identi
 The reference's own `LAVENDER_Pretrain_MLM` (the unchanged script) also runs on top of lavender_b200.model —
 see INTEGRATION.md.
 """
+import os
 from collections import defaultdict
 
 import numpy as np
@@ -24,6 +25,8 @@ class LAVENDER_Pretrain_MLM(LAVENDER_Base):
         self.vtm_batch = min(args.size_batch, 4)
         self.task_tok2id = {"vtm": 0, "mc": 1, "oe": 2, "cap": 3}
         self.emb_task = nn.Parameter(0.02 * torch.randn(10, self.hidden_size))
+        # one merged fusion-encoder pass for MLM + VTM (see forward); LAV_MERGE_PASSES=0 keeps the two passes
+        self.merge_passes = os.environ.get("LAV_MERGE_PASSES", "1") != "0"
 
     @staticmethod
     def draw_negatives(B, O):
@@ -50,8 +53,6 @@ class LAVENDER_Pretrain_MLM(LAVENDER_Base):
         O = min(B, self.vtm_batch)
 
         feat_img, mask_img, feat_txt, mask_txt = self.go_feat(img, txt, mask, vt_mask=batch["vt_mask"])
-        out, _ = self.go_cross(feat_img, mask_img, feat_txt, mask_txt)
-        out_mtm = self.fc_mtm(out[:, Lv:])
 
         # VTM: clip i paired with its own caption (label "true") then with O-1 other captions ("false")
         dev = img.device
@@ -63,8 +64,30 @@ class LAVENDER_Pretrain_MLM(LAVENDER_Base):
                                                        prompt=batch["vtm_prompt"])
         ans_vtm = torch.full_like(p_txt, -1)
         ans_vtm[:, -1] = lab.to(ans_vtm.dtype)
-        out, _ = self.go_cross(feat_img[vi], mask_img[vi], p_feat, p_mask)
-        out_vtm = self.fc_mtm(out[:, Lv:])
+
+        if not self.merge_passes:   # the reference's two fusion-encoder passes (main_pretrain_mlm.py:68-69, 112-115)
+            out, _ = self.go_cross(feat_img, mask_img, feat_txt, mask_txt)
+            out_mtm = self.fc_mtm(out[:, Lv:])
+            out, _ = self.go_cross(feat_img[vi], mask_img[vi], p_feat, p_mask)
+            out_vtm = self.fc_mtm(out[:, Lv:])
+            return {"out_vtm": out_vtm, "out_mtm": out_mtm, "ans_vtm": ans_vtm, "ans_mtm": batch["ans_mtm"]}
+
+        # ONE fusion-encoder pass over the B MLM sequences and the B*O VTM sequences (same weights, independent
+        # sequences): the MLM sequences are padded behind the video tokens with as many key-masked dummy tokens as
+        # the VTM sequences carry task / prompt tokens (one with enable_task_token).  A masked key has attention
+        # weight exactly 0 and the dummy rows' outputs are dropped, so every real token sees what it sees in the
+        # reference's separate pass — but the small MLM pass (8 x 283 rows: GEMMs of 18 row blocks) no longer runs
+        # its own 12 layers of under-filled kernels.
+        Lt, Lp = feat_txt.shape[1], p_feat.shape[1]
+        d = Lp - Lt
+        Hh = feat_txt.shape[-1]
+        pad_f = feat_txt.new_zeros(B, d, Hh)
+        pad_m = mask_txt.new_zeros(B, d)
+        feat = torch.cat([torch.cat([feat_img, pad_f, feat_txt], dim=1), torch.cat([feat_img[vi], p_feat], dim=1)], dim=0)
+        amask = torch.cat([torch.cat([mask_img, pad_m, mask_txt], dim=1), torch.cat([mask_img[vi], p_mask], dim=1)], dim=0)
+        out = self.trsfr(feat, amask, output_attentions=True)["last_hidden_state"]
+        out_mtm = self.fc_mtm(out[:B, Lv + d:])   # (two head calls: one merged logits tensor would make autograd
+        out_vtm = self.fc_mtm(out[B:, Lv:])       #  materialise two zero-padded [rows, vocab] gradients and add them)
         return {"out_vtm": out_vtm, "out_mtm": out_mtm, "ans_vtm": ans_vtm, "ans_mtm": batch["ans_mtm"]}
 
 
