@@ -27,6 +27,7 @@ class LAVENDER_Pretrain_MLM(LAVENDER_Base):
         self.emb_task = nn.Parameter(0.02 * torch.randn(10, self.hidden_size))
         # one merged fusion-encoder pass for MLM + VTM (see forward); LAV_MERGE_PASSES=0 keeps the two passes
         self.merge_passes = os.environ.get("LAV_MERGE_PASSES", "1") != "0"
+        self.vtm_last_token_only = os.environ.get("LAV_VTM_FULL_LOGITS", "0") != "1"
 
     @staticmethod
     def draw_negatives(B, O):
@@ -87,7 +88,16 @@ class LAVENDER_Pretrain_MLM(LAVENDER_Base):
         amask = torch.cat([torch.cat([mask_img, pad_m, mask_txt], dim=1), torch.cat([mask_img[vi], p_mask], dim=1)], dim=0)
         out = self.trsfr(feat, amask, output_attentions=True)["last_hidden_state"]
         out_mtm = self.fc_mtm(out[:B, Lv + d:])   # (two head calls: one merged logits tensor would make autograd
-        out_vtm = self.fc_mtm(out[B:, Lv:])       #  materialise two zero-padded [rows, vocab] gradients and add them)
+        #                                            materialise two zero-padded [rows, vocab] gradients and add them)
+        if self.training and self.vtm_last_token_only:
+            # in training only the last text position of a VTM sequence carries a label (ans_vtm is -1
+            # elsewhere, main_pretrain_mlm.py:103-105), so the 30522-wide head runs on those B*O rows instead of
+            # B*O*34; loss and gradients are identical (unlabelled rows contribute nothing to the cross-entropy).
+            # eval() keeps the reference's full [B*O, Lt, vocab] logits.
+            out_vtm = self.fc_mtm(out[B:, -1:])
+            ans_vtm = ans_vtm[:, -1:]
+        else:
+            out_vtm = self.fc_mtm(out[B:, Lv:])
         return {"out_vtm": out_vtm, "out_mtm": out_mtm, "ans_vtm": ans_vtm, "ans_mtm": batch["ans_mtm"]}
 
 

@@ -194,3 +194,40 @@ def test_reference_style_loop_equals_batched_pairs():
         o2, _ = m.go_cross(torch.cat(pf), torch.cat(pm), torch.cat(pt_), torch.cat(pmt))
         o2 = m.fc_mtm(o2[:, Lv:])
     assert torch.equal(out["out_vtm"], o2)
+
+
+def test_merged_pass_and_last_token_head_equal_the_two_pass_formulation():
+    """train()-mode step (DropPath active with a fixed seed, BERT dropout off) in three formulations that must agree:
+    the reference's two fusion-encoder passes with full VTM logits; one merged pass (MLM rows padded with key-masked
+    dummy tokens); merged pass + the MLM head on the labelled (last) VTM position only."""
+    import lavender_oracle as O
+    from lavender_b200.bert import CrossEntropyLoss
+    m, cfg, sd = _build("tiny", 2, 3, True, 1)
+    for c in (m.trsfr.config, m.enc_txt.emb_txt.config):
+        c.lav_eval_dropout = True
+    m.train()
+    batch = {k: v.cuda() for k, v in O.make_batch(3, seed=1).items()}
+    ce = CrossEntropyLoss(ignore_index=-1)
+    res = []
+    for merge, last in ((False, False), (True, False), (True, True)):
+        m.merge_passes, m.vtm_last_token_only = merge, last
+        for p in m.parameters():
+            p.grad = None
+        torch.manual_seed(7)
+        np.random.seed(7)
+        out = m(dict(batch))
+        assert out["out_vtm"].shape[1] == (1 if last else 34)
+        l1 = ce(out["out_mtm"].flatten(0, 1), out["ans_mtm"].flatten())
+        l2 = ce(out["out_vtm"].flatten(0, 1), out["ans_vtm"].flatten())
+        ((l1 + l2) * 1024.0).backward()
+        m.arena().finalize_grads()
+        torch.cuda.synchronize()
+        res.append((l1.item(), l2.item(), {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}))
+    base = res[0]
+    for l1, l2, grads in res[1:]:
+        assert abs(l1 - base[0]) < 2e-4 and abs(l2 - base[1]) < 2e-4, (l1, l2, base[:2])
+        for n, g in grads.items():
+            ref = base[2][n]
+            if ref.norm().item() < 1e-3 or n.endswith("key.bias"):   # key.bias: exactly 0 in exact arithmetic
+                continue                                              # (softmax shift invariance) -> rounding noise
+            assert _rel(g, ref) < 5e-3, (n, _rel(g, ref))
