@@ -321,6 +321,9 @@ def run_native(a):
                    "l2": "working set (activations > 10 GB/step) far exceeds the 126 MB L2; no explicit flush",
                    "drop_path": "active (rate linspace(0,0.2))",
                    "bert_dropout": "identity" if a.eval_dropout else "active (p=0.1)",
+                   "fusion_passes": "one merged pass over the MLM and VTM sequences" if model.merge_passes else "two",
+                   "vtm_head": "labelled (last) position only in train()" if model.vtm_last_token_only else "all positions",
+                   "executed_tflop_per_step": round(sum(f["flops"] for f in fams.values()) / 1e12, 3),
                    "algorithmic_gflop_per_clip_fwd_bwd": round(3 * fwd / 1e9, 1)},
         "clocks": summarize_clocks(samples), "cuda_graph": bool(args.cuda_graph),
         "e2e": {"value": round(clips / (ms_e2e * 1e-3), 2), "unit": "clips/s",
@@ -340,7 +343,9 @@ def run_native(a):
                             "of an empty event pair; share = of the summed kernel time",
                      "event_pair_us": round(pair * 1e3, 2)},
         "step_roofline": {"achieved": round(step_flops / (ms / a.steps * 1e-3) / 1e12, 1), "peak": peak_tf,
-                          "unit": "TFLOP/s", "frac": round(step_flops / (ms / a.steps * 1e-3) / 1e12 / peak_tf, 4)},
+                          "unit": "TFLOP/s", "frac": round(step_flops / (ms / a.steps * 1e-3) / 1e12 / peak_tf, 4),
+                          "flops": "algorithmic FLOPs of the reference formulation (SURVEY 8d); see "
+                                   "config.executed_tflop_per_step for what the kernels executed"},
         "kernels": {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
                         "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1) if v["flops"] else None}
                     for k, v in sorted(fams.items(), key=lambda kv: -kv[1]["ms"])},
