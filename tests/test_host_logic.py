@@ -149,3 +149,28 @@ def test_warmup_linear_lr():
         sch.step()
     assert lrs[0] == pytest.approx(1e-8) and lrs[5] == pytest.approx(0.5) and lrs[10] == pytest.approx(1.0)
     assert lrs[55] == pytest.approx(0.5) and lrs[99] == pytest.approx(1 / 90, rel=1e-3)
+
+
+def test_dropout_rng_sites_and_specs():
+    """Host side of the kernel dropout: fresh site id per call, None for p == 0, reseed resets the step counter."""
+    import torch
+    from lavender_b200 import dropout as DR
+    st = DR.DropoutRNG(torch.device("cpu"))
+    assert st.spec(0.0) is None
+    a, b = st.spec(0.1), st.spec(0.1)
+    assert a[0] is st.state and a[2] == 0.1 and b[1] == a[1] + 1
+    step0 = int(st.state[1])
+    st.advance()
+    assert int(st.state[1]) == step0 + 1
+    torch.manual_seed(3)
+    s1 = DR.DropoutRNG(torch.device("cpu")).state[0].item()
+    torch.manual_seed(3)
+    s2 = DR.DropoutRNG(torch.device("cpu")).state[0].item()
+    assert s1 == s2   # torch.manual_seed makes the mask stream reproducible
+
+
+def test_side_stream_helpers_are_noops_without_cuda():
+    import torch
+    from lavender_b200 import streams
+    streams.join(torch.device("cpu"))   # nothing forked, no CUDA: must not raise
+    assert isinstance(streams.enabled(), bool)
