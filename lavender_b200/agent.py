@@ -248,11 +248,27 @@ class Agent_Pretrain_MLM(Agent_Base):
         for v in dev.values():   # allocated on the copy stream, consumed here: keep the allocator from recycling early
             if isinstance(v, torch.Tensor) and v.is_cuda:
                 v.record_stream(cur)
-        return self._train_step_device(dev)
+        l1, l2 = self._train_step_device(dev)
+        # the losses of a graphed step live in static tensors that the next replay overwrites: park this step's pair
+        # in pinned host memory (async D2H + event), so `finish` may be called after later steps were enqueued
+        slots = self.__dict__.setdefault("_loss_slots", [])
+        if not slots:
+            slots.extend((torch.empty(2, dtype=torch.float32).pin_memory(), torch.cuda.Event()) for _ in range(4))
+            self._loss_i = 0
+        buf, done = slots[self._loss_i % len(slots)]
+        self._loss_i += 1
+        buf.copy_(torch.stack([l1.detach().float(), l2.detach().float()]), non_blocking=True)
+        done.record(cur)
+        return buf, done
 
     @staticmethod
     def finish(pending):
-        """Device->host read of a step's two losses (the only synchronisation of the step)."""
+        """Device->host read of a step's two losses: waits for THAT step only (later steps may already be queued; at
+        most 3 steps may be outstanding)."""
+        if isinstance(pending[1], torch.cuda.Event):
+            buf, done = pending
+            done.synchronize()
+            return {"mtm": float(buf[0]), "vtm": float(buf[1])}
         return {"mtm": pending[0].item(), "vtm": pending[1].item()}
 
     def step(self, batch, is_train=True):
