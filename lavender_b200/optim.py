@@ -56,7 +56,10 @@ class FlatAdamW(torch.optim.Optimizer):
         self._active = None
         self.group_of_block = torch.empty(arena.total // 8, dtype=torch.uint8, device=dev)
         n = len(self.param_groups)
-        self._hyper_host = torch.zeros(2, n, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(2, n)
+        # ring of pinned staging buffers: the host may run several steps ahead of the device (pipelined input path)
+        self._hyper_ring = [torch.zeros(2, n, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(2, n)
+                            for _ in range(4)]
+        self._hyper_i = 0
         self.hyper = torch.zeros(2, n, dtype=torch.float32, device=dev)
 
     def _refresh_active(self):
@@ -79,10 +82,12 @@ class FlatAdamW(torch.optim.Optimizer):
             raise RuntimeError("FlatAdamW: the parameter arena was rebuilt (model moved?) - recreate the optimizer")
         ar.finalize_grads()
         self._refresh_active()
+        host = self._hyper_ring[self._hyper_i % len(self._hyper_ring)]
+        self._hyper_i += 1
         for gi, g in enumerate(self.param_groups):
-            self._hyper_host[0, gi] = g["lr"]
-            self._hyper_host[1, gi] = g["weight_decay"]
-        self.hyper.copy_(self._hyper_host, non_blocking=True)
+            host[0, gi] = g["lr"]
+            host[1, gi] = g["weight_decay"]
+        self.hyper.copy_(host, non_blocking=True)
         b1, b2 = self.param_groups[0]["betas"]
         sc = self.scaler
         ops.grad_stats(ar.grad, sc.state)

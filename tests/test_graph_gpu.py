@@ -65,3 +65,31 @@ def test_graph_replay_matches_eager():
         r2 = a2.step(dict(b2), True)
         assert abs(r1["mtm"] - r2["mtm"]) < 5e-3 and abs(r1["vtm"] - r2["vtm"]) < 5e-3, (it, r1, r2)
     assert len(a2.graphs.graphs) == 1
+
+
+def test_pipelined_input_path_matches_step():
+    """Agent.prefetch / step_async / finish (next batch copied under the running step, losses read one step late) gives
+    the loss trajectory of plain Agent.step on the same host batches."""
+    import lavender_oracle as O
+    m1, a1, _ = _setup(True)
+    m2, a2, _ = _setup(True)
+    host = [{k: v.pin_memory() for k, v in O.make_batch(3, seed=s).items()} for s in range(4)]
+    ref = []
+    for it, hb in enumerate(host):
+        np.random.seed(20 + it)
+        ref.append(a1.step(a1.prepare_batch({k: v.clone() for k, v in hb.items()}), True))
+    got, pend = [], None
+    np.random.seed(20)
+    h = a2.prefetch({k: v.clone().pin_memory() for k, v in host[0].items()})
+    for it in range(len(host)):
+        np.random.seed(20 + it)          # the VTM negatives are drawn from the numpy RNG when the step is enqueued
+        cur = a2.step_async(h)
+        if it + 1 < len(host):
+            h = a2.prefetch({k: v.clone().pin_memory() for k, v in host[it + 1].items()})
+        if pend is not None:
+            got.append(a2.finish(pend))
+        pend = cur
+    got.append(a2.finish(pend))
+    assert len(got) == len(ref)
+    for it, (r, g) in enumerate(zip(ref, got)):
+        assert abs(r["mtm"] - g["mtm"]) < 5e-3 and abs(r["vtm"] - g["vtm"]) < 5e-3, (it, r, g)
