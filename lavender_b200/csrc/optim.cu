@@ -80,7 +80,8 @@ __global__ void adamw_prepare_kernel(float* state, float max_norm, float beta1, 
 __global__ void __launch_bounds__(256)
 adamw_update_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                     int64_t nblocks8, const uint8_t* __restrict__ group_of_block, const float* __restrict__ group_lr,
-                    const float* __restrict__ group_wd, float beta1, float beta2, float eps, const float* __restrict__ state) {
+                    const float* __restrict__ group_wd, float beta1, float beta2, float eps, const float* __restrict__ state,
+                    __half* __restrict__ p16) {
   if (state[ST_FOUND] != 0.f) return;  // GradScaler.step: skip the update when a non-finite gradient was found
   const float gmul = state[ST_GMUL], bc1 = state[ST_BC1], bc2s = state[ST_BC2S];
   for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nblocks8; b += (int64_t)gridDim.x * blockDim.x) {
@@ -108,6 +109,8 @@ adamw_update_kernel(float* __restrict__ p, const float* __restrict__ g, float* _
       reinterpret_cast<float4*>(p)[i] = pv;
       reinterpret_cast<float4*>(m)[i] = mv;
       reinterpret_cast<float4*>(v)[i] = vv;
+      if (p16)  // fp16 shadow of the updated weights (tensor-core operand of the next step): no separate cast pass
+        reinterpret_cast<uint2*>(p16)[i] = make_uint2(pack_half2(pv.x, pv.y), pack_half2(pv.z, pv.w));
     }
   }
 }
@@ -129,7 +132,7 @@ extern "C" int lav_grad_stats(const float* grad, int64_t n, float* state, void* 
 extern "C" int lav_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                               const uint8_t* group_of_block, const float* group_lr, const float* group_wd, float beta1,
                               float beta2, float eps, float max_grad_norm, float* state, float growth_factor,
-                              float backoff_factor, int growth_interval, void* stream) {
+                              float backoff_factor, int growth_interval, void* param16, void* stream) {
   LAV_REQUIRE(param && grad && exp_avg && exp_avg_sq && group_of_block && group_lr && group_wd && state,
               "lav_adamw_step: null pointer");
   LAV_REQUIRE((n % 8) == 0 && ((uintptr_t)param % 16) == 0 && ((uintptr_t)grad % 16) == 0 &&
@@ -142,7 +145,7 @@ extern "C" int lav_adamw_step(float* param, const float* grad, float* exp_avg, f
     const int64_t nb = n / 8;
     const int grid = (int)std::min<int64_t>((nb + 255) / 256, (int64_t)sm_count() * 8);
     adamw_update_kernel<<<grid, 256, 0, s>>>(param, grad, exp_avg, exp_avg_sq, nb, group_of_block, group_lr, group_wd, beta1,
-                                            beta2, eps, state);
+                                            beta2, eps, state, (__half*)param16);
     LAV_CHECK_CUDA(cudaGetLastError());
   }
   count_launch(2);

@@ -65,7 +65,11 @@ class GraphedPretrainStep:
         n0 = _lib.launch_count()
         self.graph = torch.cuda.CUDAGraph()
         agent.optzr.zero_grad(set_to_none=True)   # first prepare_grads inside the capture records one arena memset
-        ar._ver16 = None                           # ... and the first refresh16 records the fp32 -> fp16 weight cast
+        self._shadow_by_optimizer = bool(getattr(agent, "fused", False))
+        if self._shadow_by_optimizer:
+            ar.refresh16()                         # FlatAdamW keeps the fp16 shadow current: no cast inside the graph
+        else:
+            ar._ver16 = None                       # ... and the first refresh16 records the fp32 -> fp16 weight cast
         # the critical path is captured on a high-priority stream: the side-stream branches (weight gradients, default
         # priority) then only get SMs the critical-path kernels leave idle
         import os
@@ -102,6 +106,8 @@ class GraphedPretrainStep:
 
     def __call__(self, batch):
         self.load(batch)
+        if self._shadow_by_optimizer:
+            self.agent.model.arena().refresh16()   # no-op unless the weights were changed outside the optimizer
         self.graph.replay()
         return self.l_mtm, self.l_vtm
 

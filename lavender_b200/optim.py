@@ -90,12 +90,16 @@ class FlatAdamW(torch.optim.Optimizer):
         self.hyper.copy_(host, non_blocking=True)
         b1, b2 = self.param_groups[0]["betas"]
         sc = self.scaler
+        fresh16 = ar._ver16 is not None and ar._ver16 == ar._version()
         ops.grad_stats(ar.grad, sc.state)
         ops.adamw_step(ar.flat, ar.grad, self.exp_avg, self.exp_avg_sq, self.group_of_block, self.hyper[0], self.hyper[1],
                        sc.state, beta1=b1, beta2=b2, eps=self.param_groups[0]["eps"], max_grad_norm=self.max_grad_norm,
                        growth_factor=sc.growth_factor, backoff_factor=sc.backoff_factor,
-                       growth_interval=sc.growth_interval)
-        ar._ver16 = None        # weights changed through the flat buffer: the fp16 shadow must be re-cast
+                       growth_interval=sc.growth_interval, param16=ar.flat16)
+        # the kernel rewrote the fp16 shadow of every element it updated: the shadow stays valid if it was valid
+        # before (parameters without a gradient are untouched on both sides); otherwise the next forward re-casts
+        if not fresh16:
+            ar._ver16 = None
         return None
 
     def grad_norm(self):
