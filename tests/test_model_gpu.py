@@ -231,3 +231,39 @@ def test_merged_pass_and_last_token_head_equal_the_two_pass_formulation():
             if ref.norm().item() < 1e-3 or n.endswith("key.bias"):   # key.bias: exactly 0 in exact arithmetic
                 continue                                              # (softmax shift invariance) -> rounding noise
             assert _rel(g, ref) < 5e-3, (n, _rel(g, ref))
+
+
+def test_config4_large384_training_step_runs_at_full_size():
+    """BASELINE configs[3] at full size: swin_large_384_patch244_window81212 (C = 192..1536, 720-token windows) + 12-layer
+    BERT-base (sequences of 5 * 145 + 33 = 758 / 759 tokens), one train()-mode step (dropout, DropPath, loss scaling):
+    finite losses near ln(vocab), a finite non-zero gradient on every trained parameter.  Parity at this geometry is
+    covered by test_swin_window81212_at_384_vs_oracle and the L = 758 attention cases; this checks the full-size run."""
+    from lavender_b200.bert import CrossEntropyLoss
+    from lavender_b200.pretrain import LAVENDER_Pretrain_MLM, FakeTokenizer, default_args
+    torch.manual_seed(0)
+    np.random.seed(0)
+    B = 2
+    args = default_args(vis_backbone_size="large", size_img=384, size_batch=B)
+    m = LAVENDER_Pretrain_MLM(args, FakeTokenizer()).cuda().train()
+    g = torch.Generator().manual_seed(0)
+    img = torch.randn(B, 5, 3, 384, 384, generator=g).cuda()
+    txt = torch.randint(1000, 30000, (B, 33), generator=g)
+    txt[:, 0], txt[:, -2], txt[:, -1] = 101, 102, 103
+    ans = torch.full((B, 33), -1)
+    ans[:, 3], ans[:, 9] = txt[:, 3], txt[:, 9]
+    txt[:, 3] = txt[:, 9] = 103
+    out = m({"img": img, "txt": txt.cuda(), "mask": torch.ones(B, 33, dtype=torch.long).cuda(), "ans_mtm": ans.cuda()})
+    ce = CrossEntropyLoss(ignore_index=-1)
+    l1 = ce(out["out_mtm"].flatten(0, 1), out["ans_mtm"].flatten())
+    l2 = ce(out["out_vtm"].flatten(0, 1), out["ans_vtm"].flatten())
+    ((l1 + l2) * 1024.0).backward()
+    m.arena().finalize_grads()
+    torch.cuda.synchronize()
+    print("configs[3] losses", l1.item(), l2.item())
+    assert 8.0 < l1.item() < 13.0 and 8.0 < l2.item() < 13.0
+    for n, p in m.named_parameters():
+        if p.grad is None:
+            continue
+        assert torch.isfinite(p.grad).all(), n
+    w = m.enc_img.swin.layers[2].blocks[5].attn.relative_position_bias_table.grad
+    assert w is not None and w.abs().sum().item() > 0
