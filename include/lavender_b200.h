@@ -171,8 +171,11 @@ int lav_colsum_f16(const void* x16, int64_t ld, int rows, int N, float* out, flo
  * Writes O (fp16, [rows_total, ldo], head h at column h*head_dim) and lse[h][row] = log-sum-exp (fp32). */
 int lav_attn_fwd_f16(const void* qkv, int64_t ld, int64_t rows_total, int q_off, int k_off, int v_off, int head_dim,
                      int nheads, int nprob, int L, float scale, const void* bias16, int NPb,
-                     const int32_t* prob_class, int class_period, const float* key_bias, int NPk, void* out16,
-                     int64_t ldo, float* lse, const LavDropout* drop, void* stream);
+                     const int32_t* prob_class, int class_period, const float* key_bias, int NPk, int causal_from,
+                     void* out16, int64_t ldo, float* lse, const LavDropout* drop, void* stream);
+/* causal_from (-1: off): the seq2seq mask of LAVENDER_Base.get_attn_mask (model.py:208-218) without materialising
+ * [B, L, L]: keys j >= causal_from (the text part) are visible to queries i >= j only — causal among the text tokens,
+ * invisible to the video / prefix queries; keys j < causal_from follow key_bias. */
 /* drop (may be NULL): dropout of the attention probabilities (HF BertSelfAttention.dropout), element index
  * (global query row, key column, head); lse is that of the un-dropped softmax. */
 
@@ -183,7 +186,7 @@ int lav_attn_fwd_f16(const void* qkv, int64_t ld, int64_t rows_total, int q_off,
  * lav_relpos_bias_grad. */
 int lav_attn_bwd_f16(const void* qkv, int64_t ld, int64_t rows_total, int q_off, int k_off, int v_off, int head_dim,
                      int nheads, int nprob, int L, float scale, const void* bias16, int NPb,
-                     const int32_t* prob_class, int class_period, const float* key_bias, int NPk,
+                     const int32_t* prob_class, int class_period, const float* key_bias, int NPk, int causal_from,
                      const void* out16, int64_t ldo, const void* dout16, int64_t lddo, const float* lse,
                      float* delta_ws, float* dq_acc, int64_t lddq, void* dqkv16, int64_t lddqkv, void* ds16, int NPs,
                      const LavDropout* drop, void* stream);

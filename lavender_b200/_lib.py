@@ -58,10 +58,10 @@ SIGNATURES = {
     "lav_gelu_bwd_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "lav_colsum_f16": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_float, c_void_p]),
     "lav_attn_fwd_f16": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
-                                 c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64, c_void_p,
+                                 c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p,
                                  ctypes.POINTER(Dropout), c_void_p]),
     "lav_attn_bwd_f16": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
-                                 c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64, c_void_p,
+                                 c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p,
                                  c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int,
                                  ctypes.POINTER(Dropout), c_void_p]),
     "lav_relpos_bias_expand": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_float,

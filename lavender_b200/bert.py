@@ -180,8 +180,10 @@ class BertEncoder(nn.Module):
     """forward(hidden[B,L,H] fp32, attention_mask) -> dict(last_hidden_state=[B,L,H], attentions=None).
 
     attention_mask is what LAVENDER_Base.go_cross passes (model.py:239-242): HF's *extended additive* mask
-    [B,1,1,L] (0 keep / finfo.min masked), or a plain [B,L] 0/1 key mask.  [B,1,L,L] (seq2seq) masks are
-    not supported by the fused attention kernel yet and raise.
+    [B,1,1,L] (0 keep / finfo.min masked), or a plain [B,L] 0/1 key mask.  The seq2seq mask of
+    LAVENDER_Base.get_attn_mask (model.py:208-218) is passed as its structure — the key mask of the video / prefix
+    part plus `causal_from` = first text position — and applied inside the attention kernels; an arbitrary
+    materialised [B,1,L,L] mask raises.
     `output_attentions` is accepted and ignored: every caller discards the maps."""
 
     def __init__(self, config):
@@ -194,13 +196,14 @@ class BertEncoder(nn.Module):
         m = attention_mask
         if m.dim() == 4:
             if m.shape[1] != 1 or m.shape[2] != 1:
-                raise NotImplementedError("BertEncoder: [B,1,L,L] (seq2seq) attention masks are not supported yet")
+                raise NotImplementedError("BertEncoder: pass the seq2seq mask as (key mask, causal_from=first text "
+                                          "position); arbitrary materialised [B,1,L,L] masks are not supported")
             return (m.reshape(B, Lq) >= -1.0)
         if m.dim() == 2:
             return m != 0
         raise ValueError(f"BertEncoder: unsupported attention_mask shape {tuple(m.shape)}")
 
-    def forward(self, hidden_states, attention_mask=None, output_attentions=False, **unused):
+    def forward(self, hidden_states, attention_mask=None, output_attentions=False, causal_from=None, **unused):
         require_cuda(hidden_states, "BertEncoder")
         B, Lq, H = hidden_states.shape
         NPk = (Lq + 127) // 128 * 128
@@ -211,7 +214,7 @@ class BertEncoder(nn.Module):
             keep = self.key_keep_mask(attention_mask, B, Lq)
             kb[:, :Lq].masked_fill_(keep, 0.0)
         params = list(self.parameters())
-        out = _BertEncoderFn.apply(hidden_states, kb, self, *params)
+        out = _BertEncoderFn.apply(hidden_states, kb, self, -1 if causal_from is None else int(causal_from), *params)
         return {"last_hidden_state": out, "attentions": None}
 
 
@@ -226,7 +229,7 @@ def _layer_views(ar, lyr, H, grad=False):
 
 class _BertEncoderFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, kb, mod, *params):
+    def forward(ctx, x, kb, mod, causal_from, *params):
         dev = x.device
         ar = arena_of(mod)
         ar.refresh16()
@@ -252,7 +255,7 @@ class _BertEncoderFn(torch.autograd.Function):
             ctx16 = empty16(M, H, device=dev)
             lse = empty32(nh, M, device=dev)
             ops.attn_fwd(qkv16, ctx16, lse, q_off=0, k_off=H, v_off=2 * H, head_dim=hd, nheads=nh, nprob=B, L_tok=Lq,
-                         scale=1.0 / math.sqrt(hd), key_bias=kb, drop=d_att)
+                         scale=1.0 / math.sqrt(hd), key_bias=kb, drop=d_att, causal_from=causal_from)
             so = lyr.attention.output
             a_pre = empty32(M, H, device=dev)
             linear_fwd(ctx16, ar.w16(so.dense.weight), so.dense.bias, a_pre, residual=x32, drop=d_so)
@@ -274,7 +277,7 @@ class _BertEncoderFn(torch.autograd.Function):
             saved.append(dict(x16=x16, qkv16=qkv16, ctx16=ctx16, lse=lse, a_pre=a_pre, m1=m1, r1=r1, a16=a16,
                               pre16=pre16, i16=i16, o_pre=o_pre, m2=m2, r2=r2, d_att=d_att, d_so=d_so, d_oo=d_oo))
             x32, x16 = y32, y16
-        ctx.mod, ctx.saved, ctx.kb, ctx.geom = mod, saved, kb, (B, Lq, H, nh, hd)
+        ctx.mod, ctx.saved, ctx.kb, ctx.geom, ctx.causal_from = mod, saved, kb, (B, Lq, H, nh, hd), causal_from
         return x32.view(B, Lq, H)
 
     @staticmethod
@@ -314,7 +317,7 @@ class _BertEncoderFn(torch.autograd.Function):
             dqkv16 = empty16(M, 3 * H, device=dev)
             ops.attn_bwd(sv["qkv16"], sv["ctx16"], dctx16, sv["lse"], dq_acc, dqkv16, q_off=0, k_off=H, v_off=2 * H,
                          head_dim=hd, nheads=nh, nprob=B, L_tok=Lq, scale=1.0 / math.sqrt(hd), key_bias=kb,
-                         drop=sv["d_att"])
+                         drop=sv["d_att"], causal_from=ctx.causal_from)
             ops.scale_cast(dq_acc, dqkv16, rows=M, C=H)
             gw, gb = _layer_views(ar, lyr, H, grad=True)
             linear_wgrad(dqkv16, sv["x16"], gw, gb)
@@ -322,7 +325,7 @@ class _BertEncoderFn(torch.autograd.Function):
             gx = empty32(M, H, device=dev)
             linear_dgrad(dqkv16, wqkv, gx, residual=ga32)
             g = gx
-        return (g.view(B, Lq, H), None, None) + (None,) * len(list(mod.parameters()))
+        return (g.view(B, Lq, H), None, None, None) + (None,) * len(list(mod.parameters()))
 
 
 # ---------------------------------------------------------------------------------------------------------

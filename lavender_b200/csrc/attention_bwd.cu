@@ -22,6 +22,7 @@ struct AttnBwdParams {
   const __half* bias16; int NPb;
   const int32_t* prob_class; int period;
   const float* key_bias; int NPk;           // [nprob][NPk]
+  int causal_from;                          // >= 0: keys j >= causal_from visible to queries i >= j only (seq2seq mask)
   const __half* out; int64_t ldo;           // forward output O
   const __half* dout; int64_t lddo;         // dO
   const float* lse; int64_t rows_total;
@@ -242,6 +243,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             pv[4 * j + 2] += f.z * 1.4426950408889634f, pv[4 * j + 3] += f.w * 1.4426950408889634f;
           }
         }
+        if (p.causal_from >= 0 && c * 128 + j0 + 31 >= p.causal_from) {  // seq2seq mask, as in attention_flash.cu
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = c * 128 + j0 + j;
+            if (col >= p.causal_from && col > qi) pv[j] = -INFINITY;
+          }
+        }
         if (!p.drop.on) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -433,7 +441,7 @@ using namespace lav;
 extern "C" int lav_attn_bwd_f16(const void* qkv, int64_t ld, int64_t rows_total, int q_off, int k_off, int v_off,
                                 int head_dim, int nheads, int nprob, int L, float scale, const void* bias16, int NPb,
                                 const int32_t* prob_class, int class_period, const float* key_bias, int NPk,
-                                const void* out16, int64_t ldo, const void* dout16, int64_t lddo, const float* lse,
+                                int causal_from, const void* out16, int64_t ldo, const void* dout16, int64_t lddo, const float* lse,
                                 float* delta_ws, float* dq_acc, int64_t lddq, void* dqkv16, int64_t lddqkv, void* ds16, int NPs,
                                 const LavDropout* drop, void* stream) {
   LAV_REQUIRE(qkv && out16 && dout16 && lse && delta_ws && dq_acc && dqkv16, "lav_attn_bwd_f16: null pointer");
@@ -452,6 +460,7 @@ extern "C" int lav_attn_bwd_f16(const void* qkv, int64_t ld, int64_t rows_total,
   p.lddo = lddo, p.lse = lse, p.rows_total = rows_total, p.dq_acc = dq_acc, p.lddq = lddq;
   p.dqkv = (__half*)dqkv16, p.lddqkv = lddqkv, p.ds_out = (__half*)ds16, p.NPs = NPs;
   p.drop = make_drop(drop);
+  p.causal_from = causal_from;
   cudaStream_t s = (cudaStream_t)stream;
   p.delta = delta_ws;
   LAV_REQUIRE((lddq % 4) == 0 && ((uintptr_t)dq_acc % 16) == 0, "lav_attn_bwd_f16: dq_acc rows must be 16-byte aligned");

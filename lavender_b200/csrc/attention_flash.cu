@@ -25,6 +25,7 @@ struct FlashParams {
   int has_bias;
   const int32_t* prob_class; int period;
   const float* key_bias; int NPk;           // [nprob][NPk] additive (0 / -inf) or null
+  int causal_from;                          // >= 0: keys j >= causal_from are visible to queries i >= j only (seq2seq)
   __half* out; int64_t ldo;
   float* lse; int64_t rows_total;
   DropParams drop;
@@ -190,6 +191,15 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
           for (int j = 0; j < 32; ++j)
             if (j0 + j >= nvalid) v[j] = -INFINITY;
         }
+        // seq2seq mask of LAVENDER_Base.get_attn_mask (model.py:208-218): the text keys (j >= causal_from) are seen
+        // causally by the text queries and not at all by the video / prefix queries, i.e. exactly when j <= i
+        if (p.causal_from >= 0 && c * 128 + j0 + 31 >= p.causal_from) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = c * 128 + j0 + j;
+            if (col >= p.causal_from && col > qi) v[j] = -INFINITY;
+          }
+        }
       };
       mbar_wait(bars + 3, c & 1, 34);
       tc_fence_after();
@@ -318,9 +328,10 @@ static int launch_flash(const void* qkv, int64_t ld, int64_t rows_total, const v
 // called by lav_attn_fwd_f16 (attention_fwd.cu) for the shapes the one-shot kernel does not take
 int attn_fwd_flash(const void* qkv, int64_t ld, int64_t rows_total, int q_off, int k_off, int v_off, int head_dim,
                    int nheads, int nprob, int L, float scale, const void* bias16, int NPb, const int32_t* prob_class,
-                   int class_period, const float* key_bias, int NPk, void* out16, int64_t ldo, float* lse,
+                   int class_period, const float* key_bias, int NPk, int causal_from, void* out16, int64_t ldo, float* lse,
                    const LavDropout* drop, cudaStream_t s) {
   FlashParams p;
+  p.causal_from = causal_from;
   p.L = L, p.nheads = nheads, p.nprob = nprob, p.q_off = q_off, p.k_off = k_off, p.v_off = v_off, p.scale = scale;
   p.NPb = NPb, p.has_bias = bias16 != nullptr, p.prob_class = prob_class, p.period = class_period > 0 ? class_period : 1;
   p.key_bias = key_bias, p.NPk = NPk, p.out = (__half*)out16, p.ldo = ldo, p.lse = lse, p.rows_total = rows_total;

@@ -330,7 +330,7 @@ __global__ void relpos_bias_expand_kernel(const float* table, int nheads, const 
 
 int attn_fwd_flash(const void* qkv, int64_t ld, int64_t rows_total, int q_off, int k_off, int v_off, int head_dim,
                    int nheads, int nprob, int L, float scale, const void* bias16, int NPb, const int32_t* prob_class,
-                   int class_period, const float* key_bias, int NPk, void* out16, int64_t ldo, float* lse,
+                   int class_period, const float* key_bias, int NPk, int causal_from, void* out16, int64_t ldo, float* lse,
                    const LavDropout* drop, cudaStream_t s);  // attention_flash.cu
 
 }  // namespace lav
@@ -340,7 +340,8 @@ using namespace lav;
 extern "C" int lav_attn_fwd_f16(const void* qkv, int64_t ld, int64_t rows_total, int q_off, int k_off, int v_off,
                                 int head_dim, int nheads, int nprob, int L, float scale, const void* bias16, int NPb,
                                 const int32_t* prob_class, int class_period, const float* key_bias, int NPk,
-                                void* out16, int64_t ldo, float* lse, const LavDropout* drop, void* stream) {
+                                int causal_from, void* out16, int64_t ldo, float* lse, const LavDropout* drop,
+                                void* stream) {
   LAV_REQUIRE(qkv && out16, "lav_attn_fwd_f16: null pointer");
   LAV_REQUIRE(nprob > 0 && nheads > 0 && L > 0, "lav_attn_fwd_f16: empty problem");
   LAV_REQUIRE((ldo % 8) == 0 && (q_off % 8) == 0 && (k_off % 8) == 0 && (v_off % 8) == 0,
@@ -361,15 +362,15 @@ extern "C" int lav_attn_fwd_f16(const void* qkv, int64_t ld, int64_t rows_total,
     const char* e = getenv("LAV_ATTN_ONESHOT");
     oneshot64 = (e && e[0] == '1') ? 1 : 0;
   }
-  if (head_dim == 32 && L <= 256 && (!key_bias || NPk == 256)) {
+  if (causal_from < 0 && head_dim == 32 && L <= 256 && (!key_bias || NPk == 256)) {
     LAV_REQUIRE(!bias16 || NPb == 256, "lav_attn_fwd_f16: dense bias must be [*, *, 256, 256] for L <= 256");
     if (bias16) return launch_attn_fwd<32, 2, true>(qkv, ld, rows_total, p, ncls, s);
     return launch_attn_fwd<32, 2, false>(qkv, ld, rows_total, p, ncls, s);
   }
-  if (oneshot64 && head_dim == 64 && L <= 384 && !bias16 && (!key_bias || NPk == 384))
+  if (causal_from < 0 && oneshot64 && head_dim == 64 && L <= 384 && !bias16 && (!key_bias || NPk == 384))
     return launch_attn_fwd<64, 3, false>(qkv, ld, rows_total, p, ncls, s);
   return attn_fwd_flash(qkv, ld, rows_total, q_off, k_off, v_off, head_dim, nheads, nprob, L, scale, bias16, NPb,
-                        prob_class, class_period, key_bias, NPk, out16, ldo, lse, drop, s);
+                        prob_class, class_period, key_bias, NPk, causal_from, out16, ldo, lse, drop, s);
 }
 
 extern "C" int lav_relpos_bias_expand(const float* table, int nheads, const int32_t* rel_index, int L,

@@ -292,11 +292,18 @@ class LAVENDER_Base(nn.Module):
             feat = torch.cat([feat_img, feat_pretxt, feat_txt], dim=1)
         else:
             feat = torch.cat([feat_img, feat_txt], dim=1)
+        if attn_mask_type == "seq2seq":
+            # model.py:208-218 without the [B, L, L] tensor (and its per-call CPU build): every query sees
+            # the (masked) video + prefix keys, text queries see text keys causally -> key mask + first text position
+            full = mask_img if mask_pretxt is None else torch.cat([mask_img, mask_pretxt], dim=1)
+            kmask = torch.cat([full, torch.ones_like(mask_txt)], dim=1)
+            assert feat.shape[1] == kmask.shape[1], \
+                f"mask and feat must have the same length, got {feat.shape[1]} vs. {kmask.shape[1]}"
+            out = self.trsfr(feat, kmask, output_attentions=True, causal_from=full.shape[1])
+            return out["last_hidden_state"], out["attentions"]
         mask = self.get_attn_mask(mask_img, mask_txt, attn_mask_type=attn_mask_type, mask_pretxt=mask_pretxt)
         assert feat.shape[1] == mask.shape[1], \
             f"mask and feat must have the same length, got {feat.shape[1]} vs. {mask.shape[1]}"
-        if mask.dim() == 3:
-            mask = self.mask_ext(mask, mask.shape, mask.device)   # [B,1,L,L] (not supported by the kernel yet)
         out = self.trsfr(feat, mask, output_attentions=True)
         return out["last_hidden_state"], out["attentions"]
 

@@ -154,7 +154,7 @@ def colsum(x16, out, *, rows, N, alpha=1.0):
 
 
 def attn_fwd(qkv, out, lse, *, q_off, k_off, v_off, head_dim, nheads, nprob, L_tok, scale, bias16=None,
-             prob_class=None, key_bias=None, drop=None):
+             prob_class=None, key_bias=None, drop=None, causal_from=-1):
     _chk16(qkv, "qkv")
     _chk16(out, "out")
     fam = "win_attn_fwd" if head_dim == 32 else "bert_attn_fwd"
@@ -162,20 +162,20 @@ def attn_fwd(qkv, out, lse, *, q_off, k_off, v_off, head_dim, nheads, nprob, L_t
       rc = L.lib().lav_attn_fwd_f16(_p(qkv), qkv.stride(0), qkv.shape[0], q_off, k_off, v_off, head_dim, nheads, nprob,
                                   L_tok, scale, _p(bias16), bias16.shape[-1] if bias16 is not None else 0,
                                   _p(prob_class), prob_class.numel() if prob_class is not None else 1, _p(key_bias),
-                                  key_bias.shape[-1] if key_bias is not None else 0,
+                                  key_bias.shape[-1] if key_bias is not None else 0, int(causal_from),
                                   _p(out), out.stride(0), _p(lse), _drop(drop), _stream())
     L.check(rc, "lav_attn_fwd_f16")
 
 
 def attn_bwd(qkv, out, dout, lse, dq_acc, dqkv, *, q_off, k_off, v_off, head_dim, nheads, nprob, L_tok, scale,
-             bias16=None, prob_class=None, key_bias=None, ds16=None, drop=None):
+             bias16=None, prob_class=None, key_bias=None, ds16=None, drop=None, causal_from=-1):
     fam = "win_attn_bwd" if head_dim == 32 else "bert_attn_bwd"
     delta = torch.empty(nheads, qkv.shape[0], dtype=torch.float32, device=qkv.device)   # workspace: rowsum(dO * O)
     with _Timed(fam, 8.0 * L_tok * L_tok * head_dim * nheads * nprob):
       rc = L.lib().lav_attn_bwd_f16(_p(qkv), qkv.stride(0), qkv.shape[0], q_off, k_off, v_off, head_dim, nheads, nprob,
                                   L_tok, scale, _p(bias16), bias16.shape[-1] if bias16 is not None else 0,
                                   _p(prob_class), prob_class.numel() if prob_class is not None else 1,
-                                  _p(key_bias), key_bias.shape[-1] if key_bias is not None else 0,
+                                  _p(key_bias), key_bias.shape[-1] if key_bias is not None else 0, int(causal_from),
                                   _p(out), out.stride(0), _p(dout), dout.stride(0), _p(lse), _p(delta),
                                   _p(dq_acc), dq_acc.stride(0), _p(dqkv), dqkv.stride(0),
                                   _p(ds16), ds16.shape[-1] if ds16 is not None else 0, _drop(drop), _stream())

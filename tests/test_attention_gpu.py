@@ -162,3 +162,46 @@ def test_long_window_attention_fwd_bwd():
     assert (dqkv[:, C:2 * C].float() - gx[:, C:2 * C]).abs().max().item() < 1e-2 * scl
     assert (dqkv[:, 2 * C:].float() - gx[:, 2 * C:]).abs().max().item() < 1e-2 * scl
     assert (dtable - t.grad).abs().max().item() < 2e-2 * t.grad.abs().max().item()
+
+
+@pytest.mark.parametrize("Lfull,Lt", [(250, 34), (255, 80), (120, 8)])
+def test_bert_attention_seq2seq_mask(Lfull, Lt):
+    """The captioning mask of LAVENDER_Base.get_attn_mask (model.py:208-218) passed as (key mask, causal_from): every
+    query sees the kept video / prefix keys, text queries see text keys causally — vs the materialised [B, L, L] mask."""
+    from lavender_b200 import ops
+    L = Lfull + Lt
+    nseq, nheads, hd = 2, 4, 64
+    H = nheads * hd
+    g = torch.Generator().manual_seed(L)
+    qkv = (torch.randn(nseq * L, 3 * H, generator=g) * 0.8).half().cuda()
+    full = torch.ones(nseq, Lfull)
+    full[1, 7:19] = 0                                     # masked video keys (vt_mask) in sequence 1
+    NPk = (L + 127) // 128 * 128
+    key_bias = torch.full((nseq, NPk), float("-inf"))
+    key_bias[:, :L] = 0.0
+    key_bias[:, :Lfull] = torch.where(full > 0, 0.0, float("-inf"))
+    key_bias = key_bias.cuda()
+    m3 = torch.zeros(nseq, L, L)                          # model.py:208-218
+    m3[:, :, :Lfull] = full.unsqueeze(1)
+    m3[:, Lfull:, Lfull:] = torch.tril(torch.ones(Lt, Lt))
+    ext = ((1.0 - m3) * torch.finfo(torch.float32).min).cuda()
+    out = torch.zeros(nseq * L, H, device="cuda", dtype=torch.float16)
+    lse = torch.zeros(nheads, nseq * L, device="cuda")
+    scale = 1.0 / math.sqrt(hd)
+    kw = dict(q_off=0, k_off=H, v_off=2 * H, head_dim=hd, nheads=nheads, nprob=nseq, L_tok=L, scale=scale,
+              key_bias=key_bias, causal_from=Lfull)
+    ops.attn_fwd(qkv, out, lse, **kw)
+    x = qkv.float().view(nseq, L, 3, nheads, hd).permute(2, 0, 3, 1, 4).clone().requires_grad_(True)
+    s = (x[0] @ x[1].transpose(-1, -2)) * scale + ext[:, None]
+    ref = (s.softmax(-1) @ x[2]).transpose(1, 2).reshape(nseq * L, H)
+    assert (out.float() - ref).abs().max().item() < 4e-3
+    dout = (torch.randn(nseq * L, H, device="cuda") * 0.5).half()
+    ref.backward(dout.float())
+    dq_acc = torch.zeros(nseq * L, H, device="cuda")
+    dqkv = torch.zeros(nseq * L, 3 * H, device="cuda", dtype=torch.float16)
+    ops.attn_bwd(qkv, out, dout, lse, dq_acc, dqkv, **kw)
+    gx = x.grad.permute(1, 3, 0, 2, 4).reshape(nseq * L, 3 * H)
+    scl = gx.abs().max().item()
+    assert (dq_acc - gx[:, :H]).abs().max().item() < 1e-2 * scl
+    assert (dqkv[:, H:2 * H].float() - gx[:, H:2 * H]).abs().max().item() < 1e-2 * scl
+    assert (dqkv[:, 2 * H:].float() - gx[:, 2 * H:]).abs().max().item() < 1e-2 * scl

@@ -267,3 +267,26 @@ def test_config4_large384_training_step_runs_at_full_size():
         assert torch.isfinite(p.grad).all(), n
     w = m.enc_img.swin.layers[2].blocks[5].attn.relative_position_bias_table.grad
     assert w is not None and w.abs().sum().item() > 0
+
+
+def test_go_cross_seq2seq_vs_oracle_layers():
+    """LAVENDER_Base.go_cross(attn_mask_type='seq2seq') (model.py:208-243, the captioning path) against the oracle's BERT
+    layers driven with the reference's materialised [B, L, L] mask."""
+    import lavender_oracle as O
+    m, cfg, sd = _build("tiny", 2, 2, True, 5)
+    B, Lv, Lt, Hd = 2, 250, 20, 768
+    g = torch.Generator().manual_seed(9)
+    feat_img, feat_txt = torch.randn(B, Lv, Hd, generator=g), torch.randn(B, Lt, Hd, generator=g)
+    mask_img, mask_txt = torch.ones(B, Lv, dtype=torch.long), torch.ones(B, Lt, dtype=torch.long)
+    mask_img[0, 30:41] = 0
+    out, _ = m.go_cross(feat_img.cuda(), mask_img.cuda(), feat_txt.cuda(), mask_txt.cuda(), attn_mask_type="seq2seq")
+    m3 = torch.zeros(B, Lv + Lt, Lv + Lt)
+    m3[:, :, :Lv] = mask_img.unsqueeze(1).float()
+    m3[:, Lv:, Lv:] = torch.tril(torch.ones(Lt, Lt))
+    x = torch.cat([feat_img, feat_txt], dim=1)
+    with torch.no_grad():
+        for l in range(cfg.bert_layers):
+            x = O.bert_layer(sd, f"trsfr.layer.{l}.", x, O.extended_mask(m3), cfg.bert_heads)
+    err = (out.detach().cpu() - x).abs().max().item()
+    print("go_cross seq2seq max abs err", err, "ref absmax", x.abs().max().item())
+    assert err < 3e-2   # LayerNorm'ed hidden states, |x| up to ~10, fp16 operands
