@@ -255,8 +255,10 @@ def swin_forward(sd, p, x, cfg: SwinCfg, keep=None):
 # ------------------------------------------------------------------------------------------------
 # EncVideo / EncTxt / fusion BERT / MLM head
 # ------------------------------------------------------------------------------------------------
-def enc_video(sd, img, cfg: ModelCfg, keep=None):
-    """EncVideo.forward model.py:37-93 (odr=None, vt_mask=None, non-swinbert). img:[B,T,3,H,W]."""
+def enc_video(sd, img, cfg: ModelCfg, keep=None, odr=None, vt_mask=None):
+    """EncVideo.forward model.py:37-93 (non-swinbert). img:[B,T,3,H,W]; odr: per-clip frame order (model.py:72-81:
+    frame i keeps emb_len[i] only where odr[b][i] == i, else emb_odr); vt_mask [B,T,1+hw] multiplies the video key
+    mask (model.py:87-91)."""
     B, T, _, H, W = img.shape
     h, w = H // 32, W // 32
     f = swin_forward(sd, "enc_img.swin.", img.transpose(1, 2), cfg.swin, keep)  # [B,T,h,w,8C]
@@ -265,10 +267,18 @@ def enc_video(sd, img, cfg: ModelCfg, keep=None):
         f = linear(_qa(f), sd["enc_img.fc.weight"], sd["enc_img.fc.bias"])
     f = torch.cat([sd["enc_img.emb_cls"].expand(B, T, -1, -1), f], dim=2)
     f = f + sd["enc_img.emb_pos"][:, :, :1 + h * w, :]
-    f = f + sd["enc_img.emb_len"][:, :T]
+    if odr is not None:
+        rows = [torch.cat([sd["enc_img.emb_len"][:, i:i + 1] if i == int(p) else sd["enc_img.emb_odr"]
+                           for i, p in enumerate(odr[b])], dim=1) for b in range(B)]
+        f = f + torch.cat(rows, dim=0)
+    else:
+        f = f + sd["enc_img.emb_len"][:, :T]
     f = F.layer_norm(f, (cfg.hidden,), sd["enc_img.norm.weight"], sd["enc_img.norm.bias"], 1e-5)
     f = f.view(B, T * (1 + h * w), cfg.hidden)
-    return f, torch.ones(B, T * (1 + h * w), dtype=torch.long)
+    m = torch.ones(B, T, 1 + h * w, dtype=torch.long)
+    if vt_mask is not None:
+        m = m * vt_mask
+    return f, m.view(B, T * (1 + h * w))
 
 
 def bert_embeddings(sd, ids, p="enc_txt.emb_txt."):
@@ -347,7 +357,7 @@ def pretrain_forward(sd, batch, cfg: ModelCfg, negs=None, keep=None):
     B, T, _, H, W = img.shape
     Lv = (1 + (H // cfg.size_patch) * (W // cfg.size_patch)) * T
     O = min(B, cfg.vtm_batch)
-    feat_img, mask_img = enc_video(sd, img, cfg, keep)
+    feat_img, mask_img = enc_video(sd, img, cfg, keep, vt_mask=batch.get("vt_mask"))
     feat_txt = bert_embeddings(sd, txt)
     out = go_cross(sd, feat_img, mask_img, feat_txt, mask, cfg)
     out_mtm = mlm_head(sd, out[:, Lv:])

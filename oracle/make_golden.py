@@ -32,7 +32,19 @@ def sample_flat(t, n=GSAMPLES):
     return O.sample_flat(t, n).numpy()
 
 
-def run_case(name, size, layers, B, task_token=True, seed=0):
+def make_vt_mask(B, T=5, hw=49):
+    """Video key mask of the base case: clip 0 fully visible, the last clip loses frame 3 and a few patches of
+    frame 1 (EncVideo vt_mask, model.py:87-91)."""
+    m = torch.ones(B, T, 1 + hw, dtype=torch.long)
+    m[B - 1, 3, :] = 0
+    m[B - 1, 1, 5:17] = 0
+    return m
+
+
+ODR = [[0, 2, 1, 3, 4], [4, 1, 2, 3, 0], [0, 1, 2, 3, 4]]   # frame orders of the EncVideo odr golden (model.py:72-81)
+
+
+def run_case(name, size, layers, B, task_token=True, seed=0, vt_mask=False, odr=False):
     torch.manual_seed(0)
     ref = ref_shims.build_reference_model(size, layers, 224, B, task_token)
     cfg = O.ModelCfg(swin=O.SWIN[size], bert_layers=layers, enable_task_token=task_token,
@@ -45,6 +57,8 @@ def run_case(name, size, layers, B, task_token=True, seed=0):
     ref.load_state_dict(sd, strict=True)
     ref.eval()
     batch = O.make_batch(B, seed=seed)
+    if vt_mask:
+        batch["vt_mask"] = make_vt_mask(B)
 
     np.random.seed(1 + seed)
     out = ref({k: v.clone() for k, v in batch.items()})
@@ -56,6 +70,9 @@ def run_case(name, size, layers, B, task_token=True, seed=0):
         swin_out = ref.enc_img.swin(batch["img"].transpose(1, 2))  # [B,8C,T,h,w]
         feat_img, _ = ref.enc_img(batch["img"])
         feat_txt = ref.enc_txt(batch["txt"])
+        if odr:
+            f_odr, m_odr, _, _ = ref.go_feat(batch["img"], batch["txt"], batch["mask"], odr=ODR[:B],
+                                             vt_mask=batch.get("vt_mask"))
 
     gold = {
         "out_mtm_s": out["out_mtm"].detach()[..., ::VSTRIDE].numpy(),
@@ -68,6 +85,14 @@ def run_case(name, size, layers, B, task_token=True, seed=0):
         "out_mtm_absmax": np.float64(out["out_mtm"].abs().max().item()),
         "out_mtm_std": np.float64(out["out_mtm"].std().item()),
     }
+    if odr:
+        gold["feat_img_odr_s"] = f_odr[:, ::5, ::3].contiguous().numpy()
+        gold["mask_img_odr"] = m_odr.numpy()
+        with torch.no_grad():
+            fo, mo = O.enc_video(sd, batch["img"], cfg, odr=ODR[:B], vt_mask=batch.get("vt_mask"))
+        assert (fo - f_odr).abs().max().item() < 2e-4 and torch.equal(mo, m_odr)
+    if vt_mask:
+        gold["vt_mask"] = batch["vt_mask"].numpy()
     names = []
     for n, p in ref.named_parameters():
         names.append(n)
@@ -136,6 +161,13 @@ def kat_cases():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    kat_cases()
-    run_case("tiny_l2_b2", "tiny", 2, 2)
-    run_case("tiny_l1_b3_notask", "tiny", 1, 3, task_token=False, seed=3)
+    if len(sys.argv) == 1 or "kat" in sys.argv[1:]:
+        kat_cases()
+    only = sys.argv[1:]
+    if not only or "tiny" in only:
+        run_case("tiny_l2_b2", "tiny", 2, 2)
+        run_case("tiny_l1_b3_notask", "tiny", 1, 3, task_token=False, seed=3)
+    if not only or "base" in only:
+        # the benchmarked architecture (BASELINE configs[1]: swin_base + 12-layer BERT-base: EncVideo.fc, 4-32 heads,
+        # K = 128 GEMMs) at B = 2 / 2 VTM pairs per clip, with a video key mask on the last clip and an odr golden
+        run_case("base_l12_b2", "base", 12, 2, seed=5, vt_mask=True, odr=True)

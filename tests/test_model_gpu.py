@@ -113,7 +113,8 @@ def test_swin_window81212_at_384_vs_oracle():
 
 
 @pytest.mark.parametrize("name,size,layers,B,task,seed", [("tiny_l2_b2", "tiny", 2, 2, True, 0),
-                                                          ("tiny_l1_b3_notask", "tiny", 1, 3, False, 3)])
+                                                          ("tiny_l1_b3_notask", "tiny", 1, 3, False, 3),
+                                                          ("base_l12_b2", "base", 12, 2, True, 5)])
 def test_pretrain_vs_reference_golden(name, size, layers, B, task, seed):
     """Eval-mode forward + CE + backward on the seeded batch vs outputs of the UNMODIFIED reference."""
     import lavender_oracle as O
@@ -121,6 +122,8 @@ def test_pretrain_vs_reference_golden(name, size, layers, B, task, seed):
     gold = np.load(os.path.join(GOLD, name + ".npz"))
     m, cfg, sd = _build(size, layers, B, task, seed)
     batch = {k: v.cuda() for k, v in O.make_batch(B, seed=seed).items()}
+    if "vt_mask" in gold.files:   # base case: video key mask on the last clip (EncVideo vt_mask, model.py:87-91)
+        batch["vt_mask"] = torch.from_numpy(gold["vt_mask"]).cuda()
     np.random.seed(1 + seed)
     out = m(batch)
     assert torch.equal(out["ans_vtm"].cpu(), torch.from_numpy(gold["ans_vtm"]))
@@ -290,3 +293,25 @@ def test_go_cross_seq2seq_vs_oracle_layers():
     err = (out.detach().cpu() - x).abs().max().item()
     print("go_cross seq2seq max abs err", err, "ref absmax", x.abs().max().item())
     assert err < 3e-2   # LayerNorm'ed hidden states, |x| up to ~10, fp16 operands
+
+
+def test_enc_video_base_fc_odr_vt_mask_vs_reference_golden():
+    """EncVideo on the benchmarked backbone (swin_base: `fc` Linear(1024 -> 768), 4..32 heads) with a frame-order list
+    (emb_odr swap, model.py:72-81) and a video key mask (model.py:87-91) against features of the unmodified reference."""
+    gold = np.load(os.path.join(GOLD, "base_l12_b2.npz"))
+    import lavender_oracle as O
+    m, cfg, sd = _build("base", 12, 2, True, 5)
+    batch = {k: v.cuda() for k, v in O.make_batch(2, seed=5).items()}
+    odr = [[0, 2, 1, 3, 4], [4, 1, 2, 3, 0]]
+    vt = torch.from_numpy(gold["vt_mask"]).cuda()
+    with torch.no_grad():
+        f, mi, ft, _ = m.go_feat(batch["img"], batch["txt"], batch["mask"], odr=odr, vt_mask=vt)
+        f0, _ = m.enc_img(batch["img"])
+        sw = m.enc_img.swin.forward_features(batch["img"].transpose(1, 2))
+    assert torch.equal(mi.cpu(), torch.from_numpy(gold["mask_img_odr"]))
+    e_sw = (sw.cpu()[..., ::7] - torch.from_numpy(gold["swin_out_s"])).abs().max().item()
+    e_f0 = (f0.cpu()[:, ::5, ::3] - torch.from_numpy(gold["feat_img_s"])).abs().max().item()
+    e_fo = (f.cpu()[:, ::5, ::3] - torch.from_numpy(gold["feat_img_odr_s"])).abs().max().item()
+    e_ft = (ft.cpu()[..., ::3] - torch.from_numpy(gold["feat_txt_s"])).abs().max().item()
+    print(f"base features max abs err: swin {e_sw:.2e} enc_video {e_f0:.2e} enc_video(odr) {e_fo:.2e} enc_txt {e_ft:.2e}")
+    assert e_sw < 3e-2 and e_f0 < 2e-2 and e_fo < 2e-2 and e_ft < 1e-5   # LayerNorm'ed features, |x| up to ~5

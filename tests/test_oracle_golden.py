@@ -42,8 +42,12 @@ def test_window_partition_reverse_roundtrip():
     assert torch.equal(O.window_reverse(O.window_partition(x, ws), ws, 2, 5, 14, 14), x)
 
 
-@pytest.mark.parametrize("name,size,layers,B,task,seed", [("tiny_l2_b2", "tiny", 2, 2, True, 0),
-                                                          ("tiny_l1_b3_notask", "tiny", 1, 3, False, 3)])
+CASES = [("tiny_l2_b2", "tiny", 2, 2, True, 0), ("tiny_l1_b3_notask", "tiny", 1, 3, False, 3),
+         # the benchmarked architecture (swin_base + 12-layer BERT-base), vt_mask on the last clip
+         ("base_l12_b2", "base", 12, 2, True, 5)]
+
+
+@pytest.mark.parametrize("name,size,layers,B,task,seed", CASES)
 def test_oracle_reproduces_reference_outputs(name, size, layers, B, task, seed):
     gold = np.load(os.path.join(GOLD, name + ".npz"))
     cfg = O.ModelCfg(swin=O.SWIN[size], bert_layers=layers, enable_task_token=task, vtm_batch=min(B, 4))
@@ -51,6 +55,8 @@ def test_oracle_reproduces_reference_outputs(name, size, layers, B, task, seed):
     sd = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point else v) for k, v in sd.items()}
     sd["fc_mtm.predictions.decoder.bias"] = sd["fc_mtm.predictions.bias"]
     batch = O.make_batch(B, seed=seed)
+    if "vt_mask" in gold.files:
+        batch["vt_mask"] = torch.from_numpy(gold["vt_mask"])
     np.random.seed(1 + seed)
     out = O.pretrain_forward(sd, batch, cfg)
     loss, l1, l2 = O.pretrain_loss(out)
@@ -80,3 +86,16 @@ def test_feature_goldens():
     assert np.abs(sw[..., ::7].numpy() - gold["swin_out_s"]).max() < 2e-4
     assert np.abs(fi[:, ::5, ::3].numpy() - gold["feat_img_s"]).max() < 2e-4
     assert np.abs(ft[..., ::3].numpy() - gold["feat_txt_s"]).max() < 1e-5
+
+
+def test_enc_video_odr_vt_mask_golden():
+    """EncVideo with a frame-order list and a video key mask (model.py:72-91) on the base backbone (covers EncVideo.fc)."""
+    gold = np.load(os.path.join(GOLD, "base_l12_b2.npz"))
+    cfg = O.ModelCfg(swin=O.SWIN["base"], bert_layers=12, vtm_batch=2)
+    sd = O.make_state_dict(cfg, 5)
+    batch = O.make_batch(2, seed=5)
+    odr = [[0, 2, 1, 3, 4], [4, 1, 2, 3, 0]]
+    with torch.no_grad():
+        f, m = O.enc_video(sd, batch["img"], cfg, odr=odr, vt_mask=torch.from_numpy(gold["vt_mask"]))
+    assert np.abs(f[:, ::5, ::3].numpy() - gold["feat_img_odr_s"]).max() < 2e-4
+    assert np.array_equal(m.numpy(), gold["mask_img_odr"])
