@@ -146,6 +146,13 @@ int lav_layernorm_bwd(const void* dy, int64_t lddy, int dy_is_f32, const float* 
 int lav_scale_cast_f16(const float* x, int64_t ldx, const int32_t* row_map, const float* row_scale,
                        int rows_per_scale, float alpha, void* out16, int64_t ldo, int rows, int C, void* stream);
 
+/* High-precision mode (LAV_PRECISION=high; the stated parity mode): out16[r] = [hi | lo | hi] (mode 0,
+ * the A operand) or [hi | hi | lo] (mode 1, the B operand) of x[r, 0:C] with hi = fp16(x), lo = fp16(x - hi), so that
+ * one lav_gemm_f16 call over K' = 3C computes the split product Ah*Bh + Al*Bh + Ah*Bl (~2^-22 relative operand error)
+ * on the same tcgen05 kernel.  Replaces nothing in the reference: its fp32 CPU path multiplies fp32 operands directly
+ * (e.g. video_swin.py:147 nn.Linear); this restores that operand precision on the fp16 tensor-core path. */
+int lav_split3_f16(const float* x, int64_t ldx, void* out16, int64_t ldo, int rows, int C, int mode, void* stream);
+
 /* flat fp32 -> fp16 copy (per-step fp16 shadow of the fp32 master parameters; autocast's weight cast,
  * agent.py:219) */
 int lav_cast_f32_to_f16(const float* src, void* dst, int64_t n, void* stream);
@@ -173,6 +180,14 @@ int lav_attn_fwd_f16(const void* qkv, int64_t ld, int64_t rows_total, int q_off,
                      int nheads, int nprob, int L, float scale, const void* bias16, int NPb,
                      const int32_t* prob_class, int class_period, const float* key_bias, int NPk, int causal_from,
                      void* out16, int64_t ldo, float* lse, const LavDropout* drop, void* stream);
+/* Same as lav_attn_fwd_f16 with an optional fp32 copy of O (out32, [rows_total, ldo32]; may be NULL; out16 may then be
+ * NULL too) - the high-precision mode feeds the un-rounded O to the output projection (video_swin.py:168, HF
+ * BertSelfOutput.dense). */
+int lav_attn_fwd_ex(const void* qkv, int64_t ld, int64_t rows_total, int q_off, int k_off, int v_off, int head_dim,
+                    int nheads, int nprob, int L, float scale, const void* bias16, int NPb,
+                    const int32_t* prob_class, int class_period, const float* key_bias, int NPk, int causal_from,
+                    void* out16, int64_t ldo, float* out32, int64_t ldo32, float* lse, const LavDropout* drop,
+                    void* stream);
 /* causal_from (-1: off): the seq2seq mask of LAVENDER_Base.get_attn_mask (model.py:208-218) without materialising
  * [B, L, L]: keys j >= causal_from (the text part) are visible to queries i >= j only — causal among the text tokens,
  * invisible to the video / prefix queries; keys j < causal_from follow key_bias. */

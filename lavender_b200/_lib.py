@@ -64,6 +64,10 @@ SIGNATURES = {
                                  c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p,
                                  c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int,
                                  ctypes.POINTER(Dropout), c_void_p]),
+    "lav_attn_fwd_ex": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                                c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p,
+                                c_int64, c_void_p, ctypes.POINTER(Dropout), c_void_p]),
+    "lav_split3_f16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     "lav_relpos_bias_expand": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_float,
                                        c_void_p]),
     "lav_relpos_bias_grad": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),

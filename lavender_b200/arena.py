@@ -62,6 +62,7 @@ class ParamArena:
                 self.flat[o:o + p.numel()].copy_(p.data.reshape(-1))
                 p.data = self.flat[o:o + p.numel()].view(p.shape)
         self._ver16 = None
+        self._x3, self._ver_x3 = {}, None   # high-precision mode: split-fp16 [hi | hi | lo] copies of the weights
         self._grad_views = {}
         self._clean = set()
         self.on_swin_backward = None  # set by dist.GradSync: called when the video encoder's backward begins
@@ -84,6 +85,22 @@ class ParamArena:
     def w16(self, p):
         o = self.offsets[id(p)]
         return self.flat16[o:o + p.numel()].view(p.shape)
+
+    def w16x3(self, w32):
+        """High-precision mode (precision.py): the [N, 3K] fp16 split operand [hi | hi | lo] of the fp32 master weight view
+        `w32` ([N, K], a view of `flat`), cached until a parameter changes."""
+        v = self._version()
+        if v != self._ver_x3:
+            self._x3.clear()
+            self._ver_x3 = v
+        key = (w32.data_ptr(), tuple(w32.shape))
+        t = self._x3.get(key)
+        if t is None:
+            N, K = w32.shape
+            t = torch.empty(N, 3 * K, dtype=torch.float16, device=w32.device)
+            ops.split3(w32, t, rows=N, C=K, weight=True)
+            self._x3[key] = t
+        return t
 
     def span16(self, first, last, shape):
         """fp16 view covering `first`..`last` (adjacent in the arena), e.g. fused [Wq;Wk;Wv]."""

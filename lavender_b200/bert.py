@@ -22,10 +22,12 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from . import precision
 from . import _lib as L
 from .arena import arena_of
 from .dropout import rng_for
-from .functional import (F16, F32, empty16, empty32, linear_dgrad, linear_fwd, linear_wgrad, require_cuda)
+from .functional import (F16, F32, cast16, empty16, empty32, linear_dgrad, linear_fwd, linear_fwd_hp, linear_wgrad,
+                         require_cuda)
 
 NEG_INF = float("-inf")
 
@@ -247,29 +249,47 @@ class _BertEncoderFn(torch.autograd.Function):
         saved = []
         rng = rng_for(dev)
         p_hid, p_att = _drop_p(mod, c.hidden_dropout_prob), _drop_p(mod, c.attention_probs_dropout_prob)
+        hp = precision.high("bert")   # parity mode: split-fp16 linears on fp32 activations, fp32 attention output
         for lyr in mod.layer:
             d_att, d_so, d_oo = rng.spec(p_att), rng.spec(p_hid), rng.spec(p_hid)   # three dropout sites per layer
             wqkv, bqkv = _layer_views(ar, lyr, H)
+            sa = lyr.attention.self
             qkv16 = empty16(M, 3 * H, device=dev)
-            linear_fwd(x16, wqkv, bqkv, qkv16)
+            if hp:
+                linear_fwd_hp(ar, x32, ar.span32(sa.query.weight, sa.value.weight, (3 * H, H)), bqkv, qkv16)
+            else:
+                linear_fwd(x16, wqkv, bqkv, qkv16)
             ctx16 = empty16(M, H, device=dev)
+            ctx32 = empty32(M, H, device=dev) if hp else None
             lse = empty32(nh, M, device=dev)
             ops.attn_fwd(qkv16, ctx16, lse, q_off=0, k_off=H, v_off=2 * H, head_dim=hd, nheads=nh, nprob=B, L_tok=Lq,
-                         scale=1.0 / math.sqrt(hd), key_bias=kb, drop=d_att, causal_from=causal_from)
+                         scale=1.0 / math.sqrt(hd), key_bias=kb, drop=d_att, causal_from=causal_from, out32=ctx32)
             so = lyr.attention.output
             a_pre = empty32(M, H, device=dev)
-            linear_fwd(ctx16, ar.w16(so.dense.weight), so.dense.bias, a_pre, residual=x32, drop=d_so)
+            if hp:
+                linear_fwd_hp(ar, ctx32, so.dense.weight.data, so.dense.bias, a_pre, residual=x32, drop=d_so)
+            else:
+                linear_fwd(ctx16, ar.w16(so.dense.weight), so.dense.bias, a_pre, residual=x32, drop=d_so)
             a32, a16 = empty32(M, H, device=dev), empty16(M, H, device=dev)
             m1, r1 = empty32(M, device=dev), empty32(M, device=dev)
             ops.layernorm_fwd(a_pre, so.LayerNorm.weight, so.LayerNorm.bias, so.LayerNorm.eps, rows=M, C=H, out16=a16,
                               out32=a32, mean=m1, rstd=r1)
             FF = lyr.intermediate.dense.weight.shape[0]
-            pre16, i16 = empty16(M, FF, device=dev), empty16(M, FF, device=dev)
-            linear_fwd(a16, ar.w16(lyr.intermediate.dense.weight), lyr.intermediate.dense.bias, i16, act=L.ACT_GELU,
-                       aux=pre16)
+            pre16 = empty16(M, FF, device=dev)
             oo = lyr.output
             o_pre = empty32(M, H, device=dev)
-            linear_fwd(i16, ar.w16(oo.dense.weight), oo.dense.bias, o_pre, residual=a32, drop=d_oo)
+            if hp:
+                i32 = empty32(M, FF, device=dev)
+                linear_fwd_hp(ar, a32, lyr.intermediate.dense.weight.data, lyr.intermediate.dense.bias, i32,
+                              act=L.ACT_GELU, aux=pre16)
+                linear_fwd_hp(ar, i32, oo.dense.weight.data, oo.dense.bias, o_pre, residual=a32, drop=d_oo)
+                i16 = cast16(i32)
+                del i32, ctx32
+            else:
+                i16 = empty16(M, FF, device=dev)
+                linear_fwd(a16, ar.w16(lyr.intermediate.dense.weight), lyr.intermediate.dense.bias, i16, act=L.ACT_GELU,
+                           aux=pre16)
+                linear_fwd(i16, ar.w16(oo.dense.weight), oo.dense.bias, o_pre, residual=a32, drop=d_oo)
             y32, y16 = empty32(M, H, device=dev), empty16(M, H, device=dev)
             m2, r2 = empty32(M, device=dev), empty32(M, device=dev)
             ops.layernorm_fwd(o_pre, oo.LayerNorm.weight, oo.LayerNorm.bias, oo.LayerNorm.eps, rows=M, C=H, out16=y16,
@@ -378,13 +398,22 @@ class _MLMHeadFn(torch.autograd.Function):
         x16 = ops.scale_cast(x2, empty16(M, H, device=dev), rows=M, C=H)  # handles row-strided x2
         pre16, t16 = empty16(M, H, device=dev), empty16(M, H, device=dev)
         t32 = empty32(M, H, device=dev)
-        linear_fwd(x16, ar.w16(wd), bd, t32, act=L.ACT_GELU, aux=pre16)
+        hp = precision.high("head")   # parity mode: split-fp16 transform / decoder products on fp32 activations (precision.py)
+        if hp:
+            xf = x2.float() if x2.dtype != F32 else x2
+            linear_fwd_hp(ar, xf, wd.data, bd, t32, act=L.ACT_GELU, aux=pre16)
+        else:
+            linear_fwd(x16, ar.w16(wd), bd, t32, act=L.ACT_GELU, aux=pre16)
         mean, rstd = empty32(M, device=dev), empty32(M, device=dev)
         eps = mod.predictions.transform.LayerNorm.eps
-        ops.layernorm_fwd(t32, gamma, beta, eps, rows=M, C=H, out16=t16, mean=mean, rstd=rstd)
+        tn32 = empty32(M, H, device=dev) if hp else None
+        ops.layernorm_fwd(t32, gamma, beta, eps, rows=M, C=H, out16=t16, out32=tn32, mean=mean, rstd=rstd)
         Vp = (V + 7) // 8 * 8
         logits = empty32(M, Vp, device=dev)
-        linear_fwd(t16, ar.w16(wdec), bdec, logits[:, :V])
+        if hp:
+            linear_fwd_hp(ar, tn32, wdec.data, bdec, logits[:, :V])
+        else:
+            linear_fwd(t16, ar.w16(wdec), bdec, logits[:, :V])
         ctx.mod, ctx.params = mod, (wd, bd, gamma, beta, wdec, bdec)
         ctx.saved, ctx.shp = (x16, pre16, t32, mean, rstd, t16), shp
         return logits[:, :V].view(*shp[:-1], V)

@@ -14,8 +14,11 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "liblavender_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-I", os.path.join(os.path.dirname(HERE), "include")]
+# --use_fast_math only where the instruction count matters (tensor-core kernels' epilogues / softmax, the optimizer pass);
+# the HBM-bound row kernels (LayerNorm statistics, embeddings, cross-entropy log-sum-exp) use IEEE division / sqrt / exp.
+FAST_MATH = {"gemm.cu", "attention_fwd.cu", "attention_flash.cu", "attention_bwd.cu", "optim.cu"}
 
 
 def _sources():
@@ -25,6 +28,7 @@ def _sources():
 def _headers_mtime():
     hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     hs.append(os.path.join(os.path.dirname(HERE), "include", "lavender_b200.h"))
+    hs.append(os.path.abspath(__file__))   # flag changes rebuild everything
     return max(os.path.getmtime(h) for h in hs)
 
 
@@ -42,7 +46,8 @@ def build(force=False, verbose=False):
 
     def compile_one(job):
         s, o = job
-        r = subprocess.run([NVCC] + FLAGS + ["-c", s, "-o", o], capture_output=True, text=True)
+        fm = ["--use_fast_math"] if os.path.basename(s) in FAST_MATH else []
+        r = subprocess.run([NVCC] + FLAGS + fm + ["-c", s, "-o", o], capture_output=True, text=True)
         with open(o + ".log", "w") as f:
             f.write(r.stdout + r.stderr)
         if r.returncode != 0:

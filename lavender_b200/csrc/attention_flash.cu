@@ -27,6 +27,7 @@ struct FlashParams {
   const float* key_bias; int NPk;           // [nprob][NPk] additive (0 / -inf) or null
   int causal_from;                          // >= 0: keys j >= causal_from are visible to queries i >= j only (seq2seq)
   __half* out; int64_t ldo;
+  float* out32; int64_t ldo32;              // optional fp32 copy of O (high-precision mode)
   float* lse; int64_t rows_total;
   DropParams drop;
 };
@@ -280,7 +281,7 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       uint32_t o[32];
       tmem_ld_32x32(trow + Cfg::COL_O + c0, o);
       tmem_ld_wait();
-      if (valid) {
+      if (valid && p.out) {
         __half* dst = p.out + (size_t)(row0 + qi) * p.ldo + h * HD + c0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -291,6 +292,14 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
           u.w = pack_half2(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv);
           reinterpret_cast<uint4*>(dst)[j] = u;
         }
+      }
+      if (valid && p.out32) {
+        float* dst = p.out32 + (size_t)(row0 + qi) * p.ldo32 + h * HD + c0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          reinterpret_cast<float4*>(dst)[j] =
+              make_float4(__uint_as_float(o[4 * j]) * inv, __uint_as_float(o[4 * j + 1]) * inv,
+                          __uint_as_float(o[4 * j + 2]) * inv, __uint_as_float(o[4 * j + 3]) * inv);
       }
     }
   }
@@ -328,13 +337,14 @@ static int launch_flash(const void* qkv, int64_t ld, int64_t rows_total, const v
 // called by lav_attn_fwd_f16 (attention_fwd.cu) for the shapes the one-shot kernel does not take
 int attn_fwd_flash(const void* qkv, int64_t ld, int64_t rows_total, int q_off, int k_off, int v_off, int head_dim,
                    int nheads, int nprob, int L, float scale, const void* bias16, int NPb, const int32_t* prob_class,
-                   int class_period, const float* key_bias, int NPk, int causal_from, void* out16, int64_t ldo, float* lse,
-                   const LavDropout* drop, cudaStream_t s) {
+                   int class_period, const float* key_bias, int NPk, int causal_from, void* out16, int64_t ldo,
+                   float* out32, int64_t ldo32, float* lse, const LavDropout* drop, cudaStream_t s) {
   FlashParams p;
   p.causal_from = causal_from;
   p.L = L, p.nheads = nheads, p.nprob = nprob, p.q_off = q_off, p.k_off = k_off, p.v_off = v_off, p.scale = scale;
   p.NPb = NPb, p.has_bias = bias16 != nullptr, p.prob_class = prob_class, p.period = class_period > 0 ? class_period : 1;
   p.key_bias = key_bias, p.NPk = NPk, p.out = (__half*)out16, p.ldo = ldo, p.lse = lse, p.rows_total = rows_total;
+  p.out32 = out32, p.ldo32 = ldo32;
   p.drop = make_drop(drop);
   const int nblk = (L + 127) / 128;
   LAV_REQUIRE(!bias16 || NPb >= nblk * 128, "lav_attn_fwd_f16: dense bias smaller than the padded length");

@@ -30,6 +30,7 @@ struct AttnFwdParams {
   const int32_t* prob_class; int period;   // class of problem p = prob_class[p % period] (null: class 0)
   const float* key_bias;                   // [nprob][NKC*128] additive (0 / -inf) or null
   __half* out; int64_t ldo;
+  float* out32; int64_t ldo32;             // optional fp32 copy of O (high-precision mode)
   float* lse; int64_t rows_total;
   DropParams drop;                         // attention-probability dropout (BERT, train mode)
 };
@@ -257,7 +258,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       uint32_t o[32];
       tmem_ld_32x32(trow + c0, o);
       tmem_ld_wait();
-      if (valid) {
+      if (valid && p.out) {
         __half* dst = p.out + (size_t)(row0 + qi) * p.ldo + h * HD + c0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -268,6 +269,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           u.w = pack_half2(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv);
           reinterpret_cast<uint4*>(dst)[j] = u;
         }
+      }
+      if (valid && p.out32) {
+        float* dst = p.out32 + (size_t)(row0 + qi) * p.ldo32 + h * HD + c0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          reinterpret_cast<float4*>(dst)[j] =
+              make_float4(__uint_as_float(o[4 * j]) * inv, __uint_as_float(o[4 * j + 1]) * inv,
+                          __uint_as_float(o[4 * j + 2]) * inv, __uint_as_float(o[4 * j + 3]) * inv);
       }
     }
   }
@@ -330,19 +339,20 @@ __global__ void relpos_bias_expand_kernel(const float* table, int nheads, const 
 
 int attn_fwd_flash(const void* qkv, int64_t ld, int64_t rows_total, int q_off, int k_off, int v_off, int head_dim,
                    int nheads, int nprob, int L, float scale, const void* bias16, int NPb, const int32_t* prob_class,
-                   int class_period, const float* key_bias, int NPk, int causal_from, void* out16, int64_t ldo, float* lse,
-                   const LavDropout* drop, cudaStream_t s);  // attention_flash.cu
+                   int class_period, const float* key_bias, int NPk, int causal_from, void* out16, int64_t ldo,
+                   float* out32, int64_t ldo32, float* lse, const LavDropout* drop, cudaStream_t s);  // attention_flash.cu
 
 }  // namespace lav
 
 using namespace lav;
 
-extern "C" int lav_attn_fwd_f16(const void* qkv, int64_t ld, int64_t rows_total, int q_off, int k_off, int v_off,
-                                int head_dim, int nheads, int nprob, int L, float scale, const void* bias16, int NPb,
-                                const int32_t* prob_class, int class_period, const float* key_bias, int NPk,
-                                int causal_from, void* out16, int64_t ldo, float* lse, const LavDropout* drop,
-                                void* stream) {
-  LAV_REQUIRE(qkv && out16, "lav_attn_fwd_f16: null pointer");
+extern "C" int lav_attn_fwd_ex(const void* qkv, int64_t ld, int64_t rows_total, int q_off, int k_off, int v_off,
+                               int head_dim, int nheads, int nprob, int L, float scale, const void* bias16, int NPb,
+                               const int32_t* prob_class, int class_period, const float* key_bias, int NPk,
+                               int causal_from, void* out16, int64_t ldo, float* out32, int64_t ldo32, float* lse,
+                               const LavDropout* drop, void* stream) {
+  LAV_REQUIRE(qkv && (out16 || out32), "lav_attn_fwd_f16: null pointer");
+  LAV_REQUIRE(!out32 || ((ldo32 % 4) == 0 && ((uintptr_t)out32 % 16) == 0), "lav_attn_fwd_ex: out32 must be 16-byte aligned");
   LAV_REQUIRE(nprob > 0 && nheads > 0 && L > 0, "lav_attn_fwd_f16: empty problem");
   LAV_REQUIRE((ldo % 8) == 0 && (q_off % 8) == 0 && (k_off % 8) == 0 && (v_off % 8) == 0,
               "lav_attn_fwd_f16: offsets / ld must be multiples of 8");
@@ -351,6 +361,7 @@ extern "C" int lav_attn_fwd_f16(const void* qkv, int64_t ld, int64_t rows_total,
   p.q_off = q_off, p.k_off = k_off, p.v_off = v_off, p.scale = scale;
   p.bias16 = (const __half*)bias16, p.NPb = NPb, p.prob_class = prob_class, p.period = class_period > 0 ? class_period : 1;
   p.key_bias = key_bias, p.out = (__half*)out16, p.ldo = ldo, p.lse = lse, p.rows_total = rows_total;
+  p.out32 = out32, p.ldo32 = ldo32;
   p.drop = make_drop(drop);
   cudaStream_t s = (cudaStream_t)stream;
   const int ncls = 8;  // row extent of the bias tensor map: an upper bound on the classes a dense tensor holds (2^3
@@ -370,7 +381,17 @@ extern "C" int lav_attn_fwd_f16(const void* qkv, int64_t ld, int64_t rows_total,
   if (causal_from < 0 && oneshot64 && head_dim == 64 && L <= 384 && !bias16 && (!key_bias || NPk == 384))
     return launch_attn_fwd<64, 3, false>(qkv, ld, rows_total, p, ncls, s);
   return attn_fwd_flash(qkv, ld, rows_total, q_off, k_off, v_off, head_dim, nheads, nprob, L, scale, bias16, NPb,
-                        prob_class, class_period, key_bias, NPk, causal_from, out16, ldo, lse, drop, s);
+                        prob_class, class_period, key_bias, NPk, causal_from, out16, ldo, out32, ldo32, lse, drop, s);
+}
+
+extern "C" int lav_attn_fwd_f16(const void* qkv, int64_t ld, int64_t rows_total, int q_off, int k_off, int v_off,
+                                int head_dim, int nheads, int nprob, int L, float scale, const void* bias16, int NPb,
+                                const int32_t* prob_class, int class_period, const float* key_bias, int NPk,
+                                int causal_from, void* out16, int64_t ldo, float* lse, const LavDropout* drop,
+                                void* stream) {
+  LAV_REQUIRE(out16, "lav_attn_fwd_f16: null pointer");
+  return lav_attn_fwd_ex(qkv, ld, rows_total, q_off, k_off, v_off, head_dim, nheads, nprob, L, scale, bias16, NPb,
+                         prob_class, class_period, key_bias, NPk, causal_from, out16, ldo, nullptr, 0, lse, drop, stream);
 }
 
 extern "C" int lav_relpos_bias_expand(const float* table, int nheads, const int32_t* rel_index, int L,

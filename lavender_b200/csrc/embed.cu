@@ -31,7 +31,7 @@ __device__ __forceinline__ void ln_row(float4 (&v)[MAXV], int n4, int lane, int 
       float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
       ss += (a * a + b * b) + (c * c + d * d);
     }
-  const float rstd = rsqrtf(warp_sum(ss) / C + eps);
+  const float rstd = 1.0f / sqrtf(warp_sum(ss) / C + eps);
   if (lane == 0) {
     if (mean_out) *mean_out = mean;
     if (rstd_out) *rstd_out = rstd;

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(kRowThreads) ln_fwd_kernel(const LnFwdParams p
           float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
           ss += (a * a + b * b) + (c * c + d * d);
         }
-    const float rstd = rsqrtf(warp_sum(ss) / W + p.eps);
+    const float rstd = 1.0f / sqrtf(warp_sum(ss) / W + p.eps);
     if (lane == 0) {
       if (p.mean) p.mean[r] = mean;
       if (p.rstd) p.rstd[r] = rstd;
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kRowThreads) ln_fwd_reg_kernel(const LnFwdPara
         ss += (a * a + b * b) + (c * c + d * d);
       }
     }
-    const float rstd = rsqrtf(warp_sum(ss) * invC + p.eps);
+    const float rstd = 1.0f / sqrtf(warp_sum(ss) * invC + p.eps);
     if (lane == 0) {
       if (p.mean) p.mean[r] = mean;
       if (p.rstd) p.rstd[r] = rstd;
@@ -406,6 +406,28 @@ scale_cast_kernel(const float* x, int64_t ldx, const int32_t* map, const float* 
   }
 }
 
+// Split-fp16 operand of the high-precision GEMM mode (LAV_PRECISION=high): x = hi + lo, hi = fp16(x), lo = fp16(x - hi)
+// (|x - hi - lo| <= 2^-22 |x|).  out16[r] = [hi | lo | hi] (mode 0, A operand) or [hi | hi | lo] (mode 1, B operand),
+// each C wide, so that ONE fp16 GEMM over K' = 3C accumulates Ah*Bh + Al*Bh + Ah*Bl in fp32.
+__global__ void __launch_bounds__(kRowThreads)
+split3_kernel(const float* x, int64_t ldx, __half* out, int64_t ldo, int rows, int C, int mode) {
+  griddep_launch();
+  griddep_wait();
+  const int lane = threadIdx.x & 31, wpb = kRowThreads / 32;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+    const float* src = x + (int64_t)r * ldx;
+    __half* o = out + (int64_t)r * ldo;
+    for (int c = lane; c < C; c += 32) {
+      const float v = src[c];
+      const __half hi = __float2half_rn(v);
+      const __half lo = __float2half_rn(v - __half2float(hi));
+      o[c] = hi;
+      o[C + c] = mode == 0 ? lo : hi;
+      o[2 * C + c] = mode == 0 ? hi : lo;
+    }
+  }
+}
+
 // flat fp32 -> fp16 (parameter shadow copy)
 __global__ void __launch_bounds__(256) cast_flat_kernel(const float* __restrict__ src, __half* __restrict__ dst, int64_t n) {
   griddep_launch();  // the next kernel may start its prologue under this kernel's tail
@@ -595,6 +617,17 @@ extern "C" int lav_scale_cast_f16(const float* x, int64_t ldx, const int32_t* ro
   if (rows <= 0) return LAV_OK;
   LAV_CHECK_CUDA(launch_pdl(scale_cast_kernel, dim3(row_grid(rows)), dim3(kRowThreads), 0, (cudaStream_t)stream, 
       x, ldx, row_map, row_scale, rows_per_scale > 0 ? rows_per_scale : 1, alpha, (__half*)out16, ldo, rows, C));
+  LAV_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return LAV_OK;
+}
+
+extern "C" int lav_split3_f16(const float* x, int64_t ldx, void* out16, int64_t ldo, int rows, int C, int mode,
+                              void* stream) {
+  LAV_REQUIRE(x && out16 && C > 0 && ldo >= 3 * (int64_t)C && (mode == 0 || mode == 1), "lav_split3_f16: bad arguments");
+  if (rows <= 0) return LAV_OK;
+  LAV_CHECK_CUDA(launch_pdl(split3_kernel, dim3(row_grid(rows)), dim3(kRowThreads), 0, (cudaStream_t)stream, x, ldx,
+                            (__half*)out16, ldo, rows, C, mode));
   LAV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return LAV_OK;

@@ -99,7 +99,7 @@ int encode_tmap_2d(CUtensorMap* map, const void* ptr, int elt_bytes, uint64_t ro
 
 extern "C" {
 
-int lav_abi_version(void) { return 2; }
+int lav_abi_version(void) { return 3; }
 const char* lav_last_error(void) { return lav::g_err; }
 int64_t lav_launch_count(void) { return lav::g_launches.load(); }
 

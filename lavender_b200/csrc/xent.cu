@@ -10,7 +10,7 @@ constexpr int kXentThreads = 256;
 __device__ __forceinline__ void lse_combine(float& m, float& s, float m2, float s2) {
   const float mm = fmaxf(m, m2);
   if (mm == -INFINITY) { m = mm, s = 0.f; return; }
-  s = s * __expf(m - mm) + s2 * __expf(m2 - mm);
+  s = s * expf(m - mm) + s2 * expf(m2 - mm);
   m = mm;
 }
 
@@ -28,19 +28,19 @@ xent_fwd_kernel(const float* logits, int64_t ld, const int64_t* labels, int V, i
     for (int i = threadIdx.x; i < n4; i += kXentThreads) {
       float4 v = reinterpret_cast<const float4*>(x)[i];
       const float mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
-      if (mx > m) { s *= __expf(m - mx); m = mx; }
-      s += (__expf(v.x - m) + __expf(v.y - m)) + (__expf(v.z - m) + __expf(v.w - m));
+      if (mx > m) { s *= expf(m - mx); m = mx; }
+      s += (expf(v.x - m) + expf(v.y - m)) + (expf(v.z - m) + expf(v.w - m));
     }
     for (int c = (n4 << 2) + threadIdx.x; c < V; c += kXentThreads) {
       const float v = x[c];
-      if (v > m) { s *= __expf(m - v); m = v; }
-      s += __expf(v - m);
+      if (v > m) { s *= expf(m - v); m = v; }
+      s += expf(v - m);
     }
   } else {
     for (int c = threadIdx.x; c < V; c += kXentThreads) {
       const float v = x[c];
-      if (v > m) { s *= __expf(m - v); m = v; }
-      s += __expf(v - m);
+      if (v > m) { s *= expf(m - v); m = v; }
+      s += expf(v - m);
     }
   }
 #pragma unroll
@@ -80,7 +80,7 @@ xent_bwd_kernel(const float* logits, int64_t ld, const int64_t* labels, int V, i
   const float* x = logits + (int64_t)r * ld;
   for (int c = threadIdx.x; c < V; c += kXentThreads) {
     float v = 0.f;
-    if (valid) v = g * (__expf(x[c] - lse) - (c == lab ? 1.f : 0.f));
+    if (valid) v = g * (expf(x[c] - lse) - (c == lab ? 1.f : 0.f));
     if (d32) d32[(int64_t)r * ldd32 + c] = v;
     if (d16) d16[(int64_t)r * ldd16 + c] = __float2half_rn(v);
   }

@@ -8,6 +8,7 @@ import torch
 
 from . import ops
 from . import _lib as L
+from . import precision
 from . import streams
 from .arena import arena_of
 
@@ -32,6 +33,21 @@ def linear_fwd(x16, w16, bias, out, **kw):
     M, K = x16.shape
     N = w16.shape[0]
     return ops.gemm(x16, w16, out, M=M, N=N, K=K, bias=bias, **kw)
+
+
+def linear_fwd_hp(ar, x32, w32, bias, out, **kw):
+    """High-precision forward (precision.py): out = x32 @ w32.T (+ bias) as ONE tcgen05 GEMM over the split-fp16
+    operands [xh | xl | xh] . [wh | wh | wl]^T (K' = 3K); x32 [M,K] fp32, w32 [N,K] fp32 master weight view."""
+    M, K = x32.shape
+    N = w32.shape[0]
+    xs = ops.split3(x32, empty16(M, 3 * K, device=x32.device), rows=M, C=K)
+    return ops.gemm(xs, ar.w16x3(w32), out, M=M, N=N, K=3 * K, bias=bias, **kw)
+
+
+def cast16(x32):
+    """fp16 copy of an fp32 activation (what the default mode would have stored; backward operand in high-precision mode)."""
+    M, C = x32.shape
+    return ops.scale_cast(x32, empty16(M, C, device=x32.device), rows=M, C=C)
 
 
 def linear_dgrad(dy16, w16, out, **kw):
@@ -72,7 +88,10 @@ class LinearFn(torch.autograd.Function):
         M, K = x2.shape
         x16 = ops.scale_cast(x2, empty16(M, K, device=x.device), rows=M, C=K)
         y = empty32(M, weight.shape[0], device=x.device)
-        linear_fwd(x16, ar.w16(weight), bias, y)
+        if precision.high("fc"):
+            linear_fwd_hp(ar, x2.float(), weight.data, bias, y)
+        else:
+            linear_fwd(x16, ar.w16(weight), bias, y)
         ctx.mod, ctx.weight, ctx.bias, ctx.x16, ctx.shp = mod, weight, bias, x16, shp
         return y.view(*shp[:-1], weight.shape[0])
 

@@ -139,6 +139,16 @@ def scale_cast(x, out16, *, rows, C, row_map=None, row_scale=None, rows_per_scal
     return out16
 
 
+def split3(x, out16, *, rows, C, weight=False):
+    """High-precision mode operand: out16[r] = [hi | lo | hi] (activation) or [hi | hi | lo] (weight=True) of the fp32
+    rows x[r, :C] (hi = fp16(x), lo = fp16(x - hi)); out16 is [rows, >= 3C] fp16."""
+    assert x.dtype == torch.float32 and x.stride(-1) == 1 and out16.dtype == F16 and out16.stride(-1) == 1
+    with _Timed("cast"):
+        rc = L.lib().lav_split3_f16(_p(x), x.stride(0), _p(out16), out16.stride(0), rows, C, 1 if weight else 0, _stream())
+    L.check(rc, "lav_split3_f16")
+    return out16
+
+
 def cast_f16(src, dst):
     assert src.dtype == torch.float32 and dst.dtype == F16 and src.numel() == dst.numel()
     assert src.is_contiguous() and dst.is_contiguous()
@@ -154,17 +164,21 @@ def colsum(x16, out, *, rows, N, alpha=1.0):
 
 
 def attn_fwd(qkv, out, lse, *, q_off, k_off, v_off, head_dim, nheads, nprob, L_tok, scale, bias16=None,
-             prob_class=None, key_bias=None, drop=None, causal_from=-1):
+             prob_class=None, key_bias=None, drop=None, causal_from=-1, out32=None):
+    """out (fp16) and / or out32 (fp32, high-precision mode) receive O."""
     _chk16(qkv, "qkv")
-    _chk16(out, "out")
+    if out is not None:
+        _chk16(out, "out")
+    assert out32 is None or (out32.dtype == torch.float32 and out32.stride(-1) == 1)
     fam = "win_attn_fwd" if head_dim == 32 else "bert_attn_fwd"
     with _Timed(fam, 4.0 * L_tok * L_tok * head_dim * nheads * nprob):
-      rc = L.lib().lav_attn_fwd_f16(_p(qkv), qkv.stride(0), qkv.shape[0], q_off, k_off, v_off, head_dim, nheads, nprob,
-                                  L_tok, scale, _p(bias16), bias16.shape[-1] if bias16 is not None else 0,
-                                  _p(prob_class), prob_class.numel() if prob_class is not None else 1, _p(key_bias),
-                                  key_bias.shape[-1] if key_bias is not None else 0, int(causal_from),
-                                  _p(out), out.stride(0), _p(lse), _drop(drop), _stream())
-    L.check(rc, "lav_attn_fwd_f16")
+      rc = L.lib().lav_attn_fwd_ex(_p(qkv), qkv.stride(0), qkv.shape[0], q_off, k_off, v_off, head_dim, nheads, nprob,
+                                 L_tok, scale, _p(bias16), bias16.shape[-1] if bias16 is not None else 0,
+                                 _p(prob_class), prob_class.numel() if prob_class is not None else 1, _p(key_bias),
+                                 key_bias.shape[-1] if key_bias is not None else 0, int(causal_from),
+                                 _p(out), out.stride(0) if out is not None else 0,
+                                 _p(out32), out32.stride(0) if out32 is not None else 0, _p(lse), _drop(drop), _stream())
+    L.check(rc, "lav_attn_fwd_ex")
 
 
 def attn_bwd(qkv, out, dout, lse, dq_acc, dqkv, *, q_off, k_off, v_off, head_dim, nheads, nprob, L_tok, scale,

@@ -20,10 +20,12 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from . import precision
 from . import streams
 from . import _lib as L
 from .arena import arena_of
-from .functional import F16, F32, empty16, empty32, linear_dgrad, linear_fwd, linear_wgrad, require_cuda
+from .functional import (F16, F32, cast16, empty16, empty32, linear_dgrad, linear_fwd, linear_fwd_hp, linear_wgrad,
+                         require_cuda)
 
 # (embed_dim, depths, num_heads, window, patch) — the only keys get_vidswin_model reads from the mmcv config
 # files (video_swin.py:616-634): swin_tiny.py:4-17, swin_base.py:3-5, swin_large.py:3-5 and the
@@ -261,13 +263,13 @@ class SwinTransformer3D(nn.Module):
 # ---------------------------------------------------------------------------------------------------------
 # fused forward / backward over the whole backbone
 # ---------------------------------------------------------------------------------------------------------
-def _im2col(x, T):
+def _im2col(x, T, dtype=F16):
     """[B,3,T,H,W] -> fp16 [B*T*(H/4)*(W/4), 96]; column = c*32 + kt*16 + kh*4 + kw, frame d+1 is zeros for
     d = T-1 (F.pad at video_swin.py:396 + Conv3d weight order)."""
     B, Cin, _, H, W = x.shape
     xp = torch.nn.functional.pad(x, (0, 0, 0, 0, 0, 1))
     pat = xp.unfold(2, 2, 1).unfold(3, 4, 4).unfold(4, 4, 4)  # [B,3,T,h,w,2,4,4]
-    return pat.permute(0, 2, 3, 4, 1, 5, 6, 7).reshape(B * T * (H // 4) * (W // 4), Cin * 32).to(F16)
+    return pat.permute(0, 2, 3, 4, 1, 5, 6, 7).reshape(B * T * (H // 4) * (W // 4), Cin * 32).to(dtype)
 
 
 class _SwinFn(torch.autograd.Function):
@@ -282,10 +284,19 @@ class _SwinFn(torch.autograd.Function):
         saved = {"blocks": [], "merges": []}
         # ---- patch embed (K1, K2)
         pe = mod.patch_embed
-        cols16 = _im2col(x, T)
+        hp = precision.high("swin")
+        if hp:
+            cols32 = _im2col(x, T, F32)
+            cols16 = cols32.to(F16)
+        else:
+            cols16 = _im2col(x, T)
         M = cols16.shape[0]
         y = empty32(M, C, device=dev)
-        linear_fwd(cols16, ar.w16(pe.proj.weight).view(C, 96), pe.proj.bias, y)
+        if hp:
+            linear_fwd_hp(ar, cols32, pe.proj.weight.data.view(C, 96), pe.proj.bias, y)
+            del cols32
+        else:
+            linear_fwd(cols16, ar.w16(pe.proj.weight).view(C, 96), pe.proj.bias, y)
         xcur = empty32(M, C, device=dev)
         pm, pr = empty32(M, device=dev), empty32(M, device=dev)
         ops.layernorm_fwd(y, pe.norm.weight, pe.norm.bias, pe.norm.eps, rows=M, C=C, out32=xcur, mean=pm, rstd=pr)
@@ -314,11 +325,16 @@ class _SwinFn(torch.autograd.Function):
                 mmap = merge_row_map(B, D, Hc, Wc, dev)
                 M4 = M // 4
                 y16 = empty16(M4, 4 * C, device=dev)
+                y32 = empty32(M4, 4 * C, device=dev) if hp else None
                 mm, mr = empty32(M4, device=dev), empty32(M4, device=dev)
                 ops.layernorm_fwd(xcur, ds.norm.weight, ds.norm.bias, ds.norm.eps, rows=M4, C=C, G=4, row_map=mmap,
-                                  out16=y16, mean=mm, rstd=mr)
+                                  out16=y16, out32=y32, mean=mm, rstd=mr)
                 xn = empty32(M4, 2 * C, device=dev)
-                linear_fwd(y16, ar.w16(ds.reduction.weight), None, xn)
+                if hp:
+                    linear_fwd_hp(ar, y32, ds.reduction.weight.data, None, xn)
+                    del y32
+                else:
+                    linear_fwd(y16, ar.w16(ds.reduction.weight), None, xn)
                 saved["merges"].append((xcur, y16, mm, mr, mmap, M, C))
                 xcur, M, C, Hc, Wc = xn, M4, 2 * C, Hc // 2, Wc // 2
         out = empty32(M, C, device=dev)
@@ -381,29 +397,50 @@ def _block_fwd(ar, blk, x, M, C, N, NP, nprob, rmap, labels, cls_of, k1, k2, rps
     at = blk.attn
     nh = blk.num_heads
     hd = C // nh
+    hp = precision.high("swin")   # parity mode: split-fp16 linears on fp32 activations, fp32 attention output (precision.py)
     y16 = empty16(M, C, device=dev)
+    y32 = empty32(M, C, device=dev) if hp else None
     m1, r1 = empty32(M, device=dev), empty32(M, device=dev)
-    ops.layernorm_fwd(x, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps, rows=M, C=C, row_map=rmap, out16=y16,
+    ops.layernorm_fwd(x, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps, rows=M, C=C, row_map=rmap, out16=y16, out32=y32,
                       mean=m1, rstd=r1)
     qkv16 = empty16(M, 3 * C, device=dev)
-    linear_fwd(y16, ar.w16(at.qkv.weight), at.qkv.bias, qkv16)
+    if hp:
+        linear_fwd_hp(ar, y32, at.qkv.weight.data, at.qkv.bias, qkv16)
+    else:
+        linear_fwd(y16, ar.w16(at.qkv.weight), at.qkv.bias, qkv16)
     rel = _rel_index(at, N, dev)
     ncls = labels.shape[0] if labels is not None else 1
     dense = empty16(ncls, nh, NP, NP, device=dev)
     ops.relpos_bias_expand(at.relative_position_bias_table, rel, N, labels, dense, at.scale)
     o16 = empty16(M, C, device=dev)
+    o32 = empty32(M, C, device=dev) if hp else None
     lse = empty32(nh, M, device=dev)
     ops.attn_fwd(qkv16, o16, lse, q_off=0, k_off=C, v_off=2 * C, head_dim=hd, nheads=nh, nprob=nprob, L_tok=N,
-                 scale=at.scale, bias16=dense, prob_class=cls_of)
+                 scale=at.scale, bias16=dense, prob_class=cls_of, out32=o32)
     x1 = empty32(M, C, device=dev)
-    linear_fwd(o16, ar.w16(at.proj.weight), at.proj.bias, x1, residual=x, row_map=rmap, row_scale=k1, rows_per_scale=rps)
+    kw = dict(residual=x, row_map=rmap, row_scale=k1, rows_per_scale=rps)
+    if hp:
+        linear_fwd_hp(ar, o32, at.proj.weight.data, at.proj.bias, x1, **kw)
+    else:
+        linear_fwd(o16, ar.w16(at.proj.weight), at.proj.bias, x1, **kw)
     y2 = empty16(M, C, device=dev)
+    y2_32 = empty32(M, C, device=dev) if hp else None
     m2, r2 = empty32(M, device=dev), empty32(M, device=dev)
-    ops.layernorm_fwd(x1, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps, rows=M, C=C, out16=y2, mean=m2, rstd=r2)
-    a16, h16 = empty16(M, 4 * C, device=dev), empty16(M, 4 * C, device=dev)
-    linear_fwd(y2, ar.w16(blk.mlp.fc1.weight), blk.mlp.fc1.bias, h16, act=L.ACT_GELU, aux=a16)
+    ops.layernorm_fwd(x1, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps, rows=M, C=C, out16=y2, out32=y2_32, mean=m2,
+                      rstd=r2)
+    a16 = empty16(M, 4 * C, device=dev)
     x2 = empty32(M, C, device=dev)
-    linear_fwd(h16, ar.w16(blk.mlp.fc2.weight), blk.mlp.fc2.bias, x2, residual=x1, row_scale=k2, rows_per_scale=rps)
+    kw = dict(residual=x1, row_scale=k2, rows_per_scale=rps)
+    if hp:
+        h32 = empty32(M, 4 * C, device=dev)
+        linear_fwd_hp(ar, y2_32, blk.mlp.fc1.weight.data, blk.mlp.fc1.bias, h32, act=L.ACT_GELU, aux=a16)
+        linear_fwd_hp(ar, h32, blk.mlp.fc2.weight.data, blk.mlp.fc2.bias, x2, **kw)
+        h16 = cast16(h32)
+        del y32, o32, y2_32, h32
+    else:
+        h16 = empty16(M, 4 * C, device=dev)
+        linear_fwd(y2, ar.w16(blk.mlp.fc1.weight), blk.mlp.fc1.bias, h16, act=L.ACT_GELU, aux=a16)
+        linear_fwd(h16, ar.w16(blk.mlp.fc2.weight), blk.mlp.fc2.bias, x2, **kw)
     sv = dict(x=x, y16=y16, m1=m1, r1=r1, qkv16=qkv16, dense=dense, o16=o16, lse=lse, x1=x1, y2=y2, m2=m2, r2=r2,
               a16=a16, h16=h16, rmap=rmap, cls_of=cls_of, k1=k1, k2=k2, rps=rps, N=N, NP=NP, nprob=nprob, M=M, C=C,
               rel=rel)

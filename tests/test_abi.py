@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in _header_functions():
         assert hasattr(lib, name), name
     l = _lib.lib()
-    assert l.lav_abi_version() == 2
+    assert l.lav_abi_version() == 3
     assert l.lav_launch_count() == 0
 
 

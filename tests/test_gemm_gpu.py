@@ -138,3 +138,28 @@ def test_launch_count_increases():
     out = torch.zeros(128, 128, device="cuda")
     ops.gemm(a, b, out, M=128, N=128, K=64)
     assert L.launch_count() == n0 + 1
+
+
+def test_split_fp16_gemm_restores_fp32_operand_precision():
+    """High-precision mode building block: lav_split3_f16 + ONE lav_gemm_f16 over K' = 3K computes xh*wh + xl*wh + xh*wl;
+    the result must agree with the fp64 product of the fp32 operands ~1000x better than the plain fp16-operand GEMM."""
+    from lavender_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    M, N, K = 520, 392, 768
+    x = torch.randn(M, K, generator=g).cuda()
+    w = (torch.randn(N, K, generator=g) * 0.05).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    ref = (x.double() @ w.double().t() + bias.double())
+    xs = ops.split3(x, torch.empty(M, 3 * K, device="cuda", dtype=torch.float16), rows=M, C=K)
+    ws = ops.split3(w, torch.empty(N, 3 * K, device="cuda", dtype=torch.float16), rows=N, C=K, weight=True)
+    assert torch.equal(xs[:, :K], x.half()) and torch.equal(xs[:, 2 * K:], x.half()) and torch.equal(ws[:, K:2 * K], w.half())
+    assert torch.equal(xs[:, K:2 * K], (x - x.half().float()).half()) and torch.equal(ws[:, 2 * K:], (w - w.half().float()).half())
+    out = torch.empty(M, N, device="cuda")
+    ops.gemm(xs, ws, out, M=M, N=N, K=3 * K, bias=bias)
+    plain = torch.empty(M, N, device="cuda")
+    ops.gemm(x.half(), w.half(), plain, M=M, N=N, K=K, bias=bias)
+    torch.cuda.synchronize()
+    e_hp = (out.double() - ref).abs().max().item()
+    e_16 = (plain.double() - ref).abs().max().item()
+    print(f"split-fp16 GEMM max abs err {e_hp:.2e} vs plain fp16 operands {e_16:.2e} (|ref| max {ref.abs().max().item():.1f})")
+    assert e_hp < 2e-5 and e_hp * 50 < e_16
