@@ -269,7 +269,12 @@ int lav_grad_stats(const float* grad, int64_t n, float* state, void* stream);
 int lav_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                    const uint8_t* group_of_block, const float* group_lr, const float* group_wd, float beta1, float beta2,
                    float eps, float max_grad_norm, float* state, float growth_factor, float backoff_factor,
-                   int growth_interval, void* param16, void* stream);
+                   int growth_interval, void* param16, float* group_step0, float* group_bc, int ngroups,
+                   void* stream);
+/* group_step0 (fp32 [ngroups], may be NULL = all 0): number of non-skipped optimizer steps taken before the group's
+ * parameters got their first gradient (a NEGATIVE entry is replaced by the kernel with the current count on the group's
+ * first step) — torch.optim.AdamW keeps a per-parameter step that only advances when the parameter has a gradient,
+ * so late starters (emb_odr, task heads) are bias-corrected with step - step0; group_bc: fp32 [2 * ngroups] scratch. */
 /* param16 (may be NULL): f16 [n] shadow of `param`, rewritten for every updated element (the tensor-core operand copy
  * of the weights; saves the per-step lav_cast_f32_to_f16 pass over the arena). */
 

@@ -251,14 +251,20 @@ class Agent_Pretrain_MLM(Agent_Base):
         l1, l2 = self._train_step_device(dev)
         # the losses of a graphed step live in static tensors that the next replay overwrites: park this step's pair
         # in pinned host memory (async D2H + event), so `finish` may be called after later steps were enqueued
+        # (a slot is reused after 4 steps: if the host got that far ahead without reading it, wait for its copy first, so
+        #  one step's losses are never overwritten by another's while a reader may still pick them up)
         slots = self.__dict__.setdefault("_loss_slots", [])
         if not slots:
-            slots.extend((torch.empty(2, dtype=torch.float32).pin_memory(), torch.cuda.Event()) for _ in range(4))
+            slots.extend([torch.empty(2, dtype=torch.float32).pin_memory(), torch.cuda.Event(), False] for _ in range(4))
             self._loss_i = 0
-        buf, done = slots[self._loss_i % len(slots)]
+        slot = slots[self._loss_i % len(slots)]
         self._loss_i += 1
+        buf, done = slot[0], slot[1]
+        if slot[2]:
+            done.synchronize()
         buf.copy_(torch.stack([l1.detach().float(), l2.detach().float()]), non_blocking=True)
         done.record(cur)
+        slot[2] = True
         return buf, done
 
     @staticmethod

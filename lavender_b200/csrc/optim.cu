@@ -40,8 +40,12 @@ __global__ void __launch_bounds__(256) grad_stats_kernel(const float* __restrict
   }
 }
 
+// group_step0[g]: number of (non-skipped) optimizer steps taken before group g's parameters received their first
+// gradient (0 for parameters active from the start); a negative entry is filled in by this kernel on the group's first step.  torch.optim.AdamW keeps a step PER PARAMETER that only advances when the parameter has a
+// gradient, so the bias corrections of late starters (emb_odr on the first `odr` batch, task heads) use
+// step - step0.  group_bc[2g] = 1 - b1^t, group_bc[2g+1] = sqrt(1 - b2^t).
 __global__ void adamw_prepare_kernel(float* state, float max_norm, float beta1, float beta2, float growth, float backoff,
-                                     int growth_interval) {
+                                     int growth_interval, float* group_step0, float* group_bc, int ngroups) {
   const float scale = state[ST_SCALE];
   const float inv = 1.0f / scale;
   const float sumsq = state[ST_SUMSQ];
@@ -57,6 +61,12 @@ __global__ void adamw_prepare_kernel(float* state, float max_norm, float beta1, 
     state[ST_STEP] = step;
     state[ST_BC1] = 1.0f - powf(beta1, step);
     state[ST_BC2S] = sqrtf(1.0f - powf(beta2, step));
+    for (int g = 0; g < ngroups; ++g) {
+      if (group_step0 && group_step0[g] < 0.f) group_step0[g] = step - 1.0f;   // the group's first step: recorded here
+      const float t = fmaxf(1.0f, step - (group_step0 ? group_step0[g] : 0.f));
+      group_bc[2 * g] = 1.0f - powf(beta1, t);
+      group_bc[2 * g + 1] = sqrtf(1.0f - powf(beta2, t));
+    }
   }
   // GradScaler.update (torch/amp/grad_scaler.py: _amp_update_scale_)
   if (found) {
@@ -81,13 +91,14 @@ __global__ void __launch_bounds__(256)
 adamw_update_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                     int64_t nblocks8, const uint8_t* __restrict__ group_of_block, const float* __restrict__ group_lr,
                     const float* __restrict__ group_wd, float beta1, float beta2, float eps, const float* __restrict__ state,
-                    __half* __restrict__ p16) {
+                    const float* __restrict__ group_bc, __half* __restrict__ p16) {
   if (state[ST_FOUND] != 0.f) return;  // GradScaler.step: skip the update when a non-finite gradient was found
-  const float gmul = state[ST_GMUL], bc1 = state[ST_BC1], bc2s = state[ST_BC2S];
+  const float gmul = state[ST_GMUL];
   for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nblocks8; b += (int64_t)gridDim.x * blockDim.x) {
     const int grp = group_of_block[b];
     if (grp == 255) continue;  // parameter without a gradient (optimizer skips it, as torch does for p.grad is None)
     const float lr = group_lr[grp], wd = group_wd[grp];
+    const float bc1 = group_bc[2 * grp], bc2s = group_bc[2 * grp + 1];
     const float decay = 1.0f - lr * wd, step_size = lr / bc1;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -132,20 +143,23 @@ extern "C" int lav_grad_stats(const float* grad, int64_t n, float* state, void* 
 extern "C" int lav_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                               const uint8_t* group_of_block, const float* group_lr, const float* group_wd, float beta1,
                               float beta2, float eps, float max_grad_norm, float* state, float growth_factor,
-                              float backoff_factor, int growth_interval, void* param16, void* stream) {
-  LAV_REQUIRE(param && grad && exp_avg && exp_avg_sq && group_of_block && group_lr && group_wd && state,
+                              float backoff_factor, int growth_interval, void* param16, float* group_step0,
+                              float* group_bc, int ngroups, void* stream) {
+  LAV_REQUIRE(param && grad && exp_avg && exp_avg_sq && group_of_block && group_lr && group_wd && state && group_bc,
               "lav_adamw_step: null pointer");
+  LAV_REQUIRE(ngroups > 0 && ngroups < 255, "lav_adamw_step: 1..254 parameter groups");
   LAV_REQUIRE((n % 8) == 0 && ((uintptr_t)param % 16) == 0 && ((uintptr_t)grad % 16) == 0 &&
                   ((uintptr_t)exp_avg % 16) == 0 && ((uintptr_t)exp_avg_sq % 16) == 0,
               "lav_adamw_step: buffers must be 16-byte aligned and n a multiple of 8");
   cudaStream_t s = (cudaStream_t)stream;
-  adamw_prepare_kernel<<<1, 1, 0, s>>>(state, max_grad_norm, beta1, beta2, growth_factor, backoff_factor, growth_interval);
+  adamw_prepare_kernel<<<1, 1, 0, s>>>(state, max_grad_norm, beta1, beta2, growth_factor, backoff_factor, growth_interval,
+                                       group_step0, group_bc, ngroups);
   LAV_CHECK_CUDA(cudaGetLastError());
   if (n > 0) {
     const int64_t nb = n / 8;
     const int grid = (int)std::min<int64_t>((nb + 255) / 256, (int64_t)sm_count() * 8);
     adamw_update_kernel<<<grid, 256, 0, s>>>(param, grad, exp_avg, exp_avg_sq, nb, group_of_block, group_lr, group_wd, beta1,
-                                            beta2, eps, state, (__half*)param16);
+                                            beta2, eps, state, group_bc, (__half*)param16);
     LAV_CHECK_CUDA(cudaGetLastError());
   }
   count_launch(2);

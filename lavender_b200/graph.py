@@ -47,8 +47,8 @@ class GraphedPretrainStep:
         self.static.update(vtm_vid_idx=vi, vtm_txt_idx=ti, vtm_labels=lab)
         # pinned staging for the per-step VTM text indices: a ring, because the pipelined input path lets the host run
         # up to 3 steps ahead of the device (a single buffer would be refilled before its async copy has executed)
-        self._txt_idx_ring = [torch.empty(ti.shape, dtype=ti.dtype).pin_memory() for _ in range(4)]
-        self._txt_idx_i = 0
+        from .optim import PinnedRing   # each slot is guarded by an event: never refilled under a pending copy
+        self._txt_idx_ring = PinnedRing(lambda: torch.empty(ti.shape, dtype=ti.dtype).pin_memory())
         model.train()
         ar = model.arena()
         hook, ar.on_swin_backward = ar.on_swin_backward, None   # no side-stream NCCL inside the capture (see dist.py)
@@ -95,14 +95,14 @@ class GraphedPretrainStep:
             if k in self.static:
                 self.static[k].copy_(batch[k], non_blocking=True)
         negs = self.agent.model.draw_negatives(self.B, self.O)
-        host = self._txt_idx_ring[self._txt_idx_i % len(self._txt_idx_ring)]
-        self._txt_idx_i += 1
+        host = self._txt_idx_ring.next()
         ti = host.view(self.B, self.O)
         for i in range(self.B):
             ti[i, 0] = i
             for j in range(self.O - 1):
                 ti[i, 1 + j] = int(negs[i][j])
         self.static["vtm_txt_idx"].copy_(host, non_blocking=True)
+        self._txt_idx_ring.copied()
 
     def __call__(self, batch):
         self.load(batch)

@@ -12,6 +12,7 @@ random init in HF's scheme.
 """
 import json
 import os
+import warnings
 
 import torch
 import torch.nn as nn
@@ -59,11 +60,17 @@ def _hf_state_dict(name_or_path):
     return None
 
 
-def _load_prefixed(module, sd, prefixes):
+def _load_prefixed(module, sd, prefixes, what, source):
     """Copies the entries of `sd` under any of `prefixes` into `module` (HF checkpoints use `bert.` for the
-    trunk and `cls.` for the head; old ones store LayerNorm as gamma/beta)."""
+    trunk and `cls.` for the head; old ones store LayerNorm as gamma/beta).  Never silent: without a checkpoint it
+    warns that `what` keeps its random (HF-scheme) init — the reference would fetch the weights from the hub or fail
+    (model.py:100-102,152-157) —, a checkpoint that matches nothing raises, a partial match reports the missing keys."""
     if sd is None:
-        return False
+        warnings.warn(f"lavender_b200: no local HuggingFace checkpoint at {source!r} (offline: no hub access) - {what} is "
+                      f"RANDOMLY initialised, not pre-trained.  Point txt_backbone / fusion_encoder / tokenizer at a local "
+                      f"directory (utils/args.py:216-237 maps names to ./_models/huggingface_transformers/...) or load a "
+                      f"LAVENDER checkpoint with load_ckpt().", stacklevel=3)
+        return 0
     own = module.state_dict()
     picked = {}
     for k, v in sd.items():
@@ -71,14 +78,22 @@ def _load_prefixed(module, sd, prefixes):
         for p in prefixes:
             if k.startswith(p) and k[len(p):] in own and own[k[len(p):]].shape == v.shape:
                 picked[k[len(p):]] = v
+    if not picked:
+        raise RuntimeError(f"lavender_b200: the checkpoint at {source!r} has no tensor matching {what} "
+                           f"(prefixes {prefixes}); refusing to continue with random weights")
     module.load_state_dict(picked, strict=False)
-    return len(picked) > 0
+    missing = sorted(set(own) - set(picked))
+    if missing:
+        warnings.warn(f"lavender_b200: {what} loaded {len(picked)} tensors from {source!r}, {len(missing)} keep their "
+                      f"init: {missing[:6]}{' ...' if len(missing) > 6 else ''}", stacklevel=3)
+    return len(picked)
 
 
 def build_bert_embeddings(name_or_path, args=None):
     cfg = _bert_config_for(name_or_path, args)
     emb = BertEmbeddings(cfg)
-    _load_prefixed(emb, _hf_state_dict(name_or_path), ("bert.embeddings.", "embeddings."))
+    _load_prefixed(emb, _hf_state_dict(name_or_path), ("bert.embeddings.", "embeddings."), "the text embeddings",
+                   name_or_path)
     return emb, cfg
 
 
@@ -86,7 +101,7 @@ def build_bert_encoder(name_or_path, args=None, rand_init=False):
     cfg = _bert_config_for(name_or_path, args)
     enc = BertEncoder(cfg)
     if not rand_init:
-        _load_prefixed(enc, _hf_state_dict(name_or_path), ("bert.encoder.", "encoder."))
+        _load_prefixed(enc, _hf_state_dict(name_or_path), ("bert.encoder.", "encoder."), "the BERT encoder", name_or_path)
     return enc, cfg
 
 
@@ -94,13 +109,15 @@ def build_mlm_head(name_or_path, args=None):
     cfg = _bert_config_for(name_or_path, args)
     head = BertOnlyMLMHead(cfg)
     sd = _hf_state_dict(name_or_path)
-    if sd is not None:
-        _load_prefixed(head, sd, ("cls.",))
-        if "cls.predictions.decoder.weight" not in sd:  # tied checkpoints store the decoder only as word embeddings
-            for k in ("bert.embeddings.word_embeddings.weight", "embeddings.word_embeddings.weight"):
-                if k in sd and sd[k].shape == head.predictions.decoder.weight.shape:
-                    with torch.no_grad():
-                        head.predictions.decoder.weight.copy_(sd[k])
+    if sd is not None and not any(k.startswith("cls.") for k in sd):
+        sd = {**sd, **{"cls.predictions.decoder.weight": sd[k] for k in
+                       ("bert.embeddings.word_embeddings.weight", "embeddings.word_embeddings.weight") if k in sd}}
+    _load_prefixed(head, sd, ("cls.",), "the MLM head (fc_mtm)", name_or_path)
+    if sd is not None and "cls.predictions.decoder.weight" not in sd:  # tied checkpoints store the decoder only as word embeddings
+        for k in ("bert.embeddings.word_embeddings.weight", "embeddings.word_embeddings.weight"):
+            if k in sd and sd[k].shape == head.predictions.decoder.weight.shape:
+                with torch.no_grad():
+                    head.predictions.decoder.weight.copy_(sd[k])
     return head, cfg
 
 

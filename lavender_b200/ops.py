@@ -310,11 +310,17 @@ def grad_stats(grad, state):
 
 
 def adamw_step(param, grad, exp_avg, exp_avg_sq, group_of_block, group_lr, group_wd, state, *, beta1, beta2, eps,
-               max_grad_norm, growth_factor=2.0, backoff_factor=0.5, growth_interval=2000, param16=None):
+               max_grad_norm, growth_factor=2.0, backoff_factor=0.5, growth_interval=2000, param16=None,
+               group_step0=None, group_bc=None):
     n = param.numel()
     assert grad.numel() == n and exp_avg.numel() == n and exp_avg_sq.numel() == n and group_of_block.numel() * 8 == n
+    ngroups = group_lr.numel()
+    if group_bc is None:
+        group_bc = torch.empty(2 * ngroups, dtype=torch.float32, device=param.device)
+    assert group_bc.numel() >= 2 * ngroups and (group_step0 is None or group_step0.numel() >= ngroups)
     with _Timed("optimizer"):
         rc = L.lib().lav_adamw_step(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), n, _p(group_of_block), _p(group_lr),
                                     _p(group_wd), beta1, beta2, eps, max_grad_norm, _p(state), growth_factor,
-                                    backoff_factor, growth_interval, _p(param16), _stream())
+                                    backoff_factor, growth_interval, _p(param16), _p(group_step0), _p(group_bc), ngroups,
+                                    _stream())
     L.check(rc, "lav_adamw_step")

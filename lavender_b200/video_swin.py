@@ -14,6 +14,7 @@ The residual stream is fp32 token-major [B*D*H*W, C]; GEMM operands are fp16.
 Not restated: F.pad to window multiples (:211-216, :274-276) — all BASELINE shapes (224^2 / 384^2) divide.
 """
 import math
+import os
 from functools import lru_cache
 
 import torch
@@ -220,12 +221,37 @@ class SwinTransformer3D(nn.Module):
         self.num_features = int(embed_dim * 2 ** (self.num_layers - 1))
         self.norm = nn.LayerNorm(self.num_features)
 
-    def init_weights(self, pretrained=None):
-        """video_swin.py:535-568 with pretrained=None: trunc_normal(0.02) Linear weights, zero biases, unit LN."""
-        if pretrained or isinstance(self.pretrained, str):
-            raise NotImplementedError("2-D checkpoint inflation (video_swin.py:482-533) is not part of the hot path; "
-                                      "load a converted state_dict instead")
+    def inflate_weights(self):
+        """video_swin.py:482-533: 2-D Swin checkpoint (`{'model': state_dict}`) -> 3-D: the patch-embed kernel is repeated
+        over the temporal patch axis and divided by it, every [(2Wh-1)(2Ww-1), nH] relative-position table is (bicubically
+        resized if the 2-D window differs, then) repeated 2*Wd-1 times; index / mask buffers are always re-created."""
+        checkpoint = torch.load(self.pretrained, map_location="cpu")
+        state_dict = dict(checkpoint["model"])
+        for k in [k for k in state_dict if "relative_position_index" in k or "attn_mask" in k]:
+            del state_dict[k]
+        w = state_dict["patch_embed.proj.weight"]
+        state_dict["patch_embed.proj.weight"] = w.unsqueeze(2).repeat(1, 1, self.patch_size[0], 1, 1) / self.patch_size[0]
+        own = self.state_dict()
+        wd, wh, ww = self.window_size
+        for k in [k for k in state_dict if "relative_position_bias_table" in k]:
+            tab = state_dict[k]
+            L1, nH1 = tab.shape
+            nH2 = own[k].shape[1]
+            L2 = (2 * wh - 1) * (2 * ww - 1)
+            if nH1 != nH2:
+                print(f"Error in loading {k}, passing")
+            elif L1 != L2:
+                S1 = int(L1 ** 0.5)
+                tab = torch.nn.functional.interpolate(tab.permute(1, 0).view(1, nH1, S1, S1), size=(2 * wh - 1, 2 * ww - 1),
+                                                      mode="bicubic").view(nH2, L2).permute(1, 0)
+            state_dict[k] = tab.repeat(2 * wd - 1, 1)
+        msg = self.load_state_dict(state_dict, strict=False)
+        print(msg)
+        print(f"=> loaded successfully '{self.pretrained}'")
 
+    def init_weights(self, pretrained=None):
+        """video_swin.py:535-568: trunc_normal(0.02) Linear weights, zero biases, unit LayerNorm; with a checkpoint path
+        (`pretrained` or self.pretrained) the 2-D weights are inflated (pretrained2d) or a 3-D state dict is loaded."""
         def _init(m):
             if isinstance(m, nn.Linear):
                 trunc_normal_(m.weight, std=.02)
@@ -234,7 +260,20 @@ class SwinTransformer3D(nn.Module):
             elif isinstance(m, nn.LayerNorm):
                 nn.init.constant_(m.bias, 0)
                 nn.init.constant_(m.weight, 1.0)
-        self.apply(_init)
+        if pretrained:
+            self.pretrained = pretrained
+        if isinstance(self.pretrained, str):
+            self.apply(_init)
+            print(f"load model from: {self.pretrained}")
+            if self.pretrained2d:
+                self.inflate_weights()
+            else:   # directly load a 3-D model (the reference goes through mmcv's load_checkpoint, strict=False)
+                missing, unexpected = self.load_state_dict(load_checkpoint_3d(self.pretrained), strict=False)
+                print(f"Missing keys: {missing}\nUnexpected keys: {unexpected}")
+        elif self.pretrained is None:
+            self.apply(_init)
+        else:
+            raise TypeError("pretrained must be a str or None")
 
     # -----------------------------------------------------------------------------------------------------
     def forward_features(self, x, keep=None):
@@ -531,13 +570,49 @@ def get_vidswin_model(args):
     if key not in SWIN_VARIANTS:
         raise ValueError(f"unsupported video swin variant {key}")
     init = getattr(args, "vis_backbone_init", "random")
+    model_path = None
     if init != "random":
-        # 3-D Kinetics / 2-D ImageNet checkpoints are files under ./_models (video_swin.py:576-593) that are
-        # not available offline; weights come from LAVENDER_Base.load_ckpt / load_state_dict instead.
-        print(f"video swin: vis_backbone_init={init!r} needs ./_models checkpoints; using random init")
-    args.vis_backbone_pretrained_weight = None
-    m = SwinTransformer3D(pretrained=None, pretrained2d=True, patch_size=(2, 4, 4), in_chans=3, mlp_ratio=4.,
+        model_path = vidswin_checkpoint_path(args)
+        if not os.path.isfile(model_path):
+            # the reference dies in torch.load here (video_swin.py:636-639 / :494); starting a "pre-trained" run from random
+            # weights silently would be a results bug, so this raises as well (utils/args.py:195-196 already forces
+            # vis_backbone_init = "random" whenever --path_ckpt is given)
+            raise FileNotFoundError(f"vis_backbone_init={init!r} needs {model_path} (relative to the working directory); "
+                                    f"use vis_backbone_init='random' (or --path_ckpt) to train from scratch")
+    pretrained2d = model_path if init == "2d" else None
+    args.vis_backbone_pretrained_weight = model_path
+    print("video swin random initialized" if init == "random" else
+          f"video swin with pre-trained {init} (model path): {model_path}")
+    m = SwinTransformer3D(pretrained=pretrained2d, pretrained2d=True, patch_size=(2, 4, 4), in_chans=3, mlp_ratio=4.,
                           qkv_bias=True, qk_scale=None, drop_rate=0., attn_drop_rate=0., drop_path_rate=0.2,
                           patch_norm=True, frozen_stages=-1, use_checkpoint=False, **SWIN_VARIANTS[key])
-    m.init_weights()
+    if init == "3d" and model_path is not None:
+        missing, unexpected = m.load_state_dict(load_checkpoint_3d(model_path), strict=False)
+        print(f"Missing keys in loaded video_swin_transformerr: {missing}")
+        print(f"Unexpected keys in loaded video_swin_transformer: {unexpected}")
+    else:
+        m.init_weights()
     return m
+
+
+def vidswin_checkpoint_path(args):
+    """./_models/... path rules of video_swin.py:572-593 (CWD-relative)."""
+    size, init = args.vis_backbone_size, getattr(args, "vis_backbone_init", "random")
+    kin = getattr(args, "kinetics", 400)
+    if int(args.size_img) == 384:
+        if init == "2d":
+            return f"./_models/swin_transformer/swin_{size}_patch4_window12_384_22k.pth"
+        return f"./_models/video_swin_transformer/swin_{size}_384_patch244_window81212_kinetics{kin}_22k.pth"
+    if size != "tiny":
+        if init == "2d":
+            return f"./_models/swin_transformer/swin_{size}_patch4_window7_224_22k.pth"
+        return f"./_models/video_swin_transformer/swin_{size}_patch244_window877_kinetics{kin}_22k.pth"
+    if init == "2d":
+        return f"./_models/swin_transformer/swin_{size}_patch4_window7_224.pth"
+    return "./_models/video_swin_transformer/swin_tiny_patch244_window877_kinetics400_1k.pth"
+
+
+def load_checkpoint_3d(model_path):
+    """video_swin.py:647-654: `{'state_dict': ...}` with the `backbone.` prefix stripped."""
+    sd = torch.load(model_path, map_location="cpu")["state_dict"]
+    return {k.replace("backbone.", ""): v for k, v in sd.items()}

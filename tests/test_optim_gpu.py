@@ -69,3 +69,55 @@ def test_flat_adamw_matches_torch():
             assert torch.allclose(p, q, rtol=2e-5, atol=5e-6), (it, n, (p - q).abs().max().item())
     assert sc_m.get_scale() != 1024.0            # the scale moved (back-off at the inf step, growth afterwards)
     assert torch.equal(ref.unused, mine.unused)  # parameter without gradient: untouched by both
+
+
+class ToyLate(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.a = torch.nn.Linear(19, 24)
+        self.late = torch.nn.Parameter(torch.randn(24) * 0.1)   # like emb_odr: first gradient arrives at step 3
+        self.use_late = False
+
+    def forward(self, x):
+        h = torch.tanh(self.a(x))
+        return h * (1.0 + self.late) if self.use_late else h
+
+
+def test_flat_adamw_late_parameter_uses_its_own_step_and_state_roundtrip():
+    """torch.optim.AdamW keeps a step count PER PARAMETER: a parameter that gets its first gradient at step 3 is
+    bias-corrected with t = 1 there, not with the global step.  Also: state_dict -> load_state_dict
+    into a fresh optimizer continues identically (exact resume)."""
+    from lavender_b200.arena import ParamArena
+    from lavender_b200.optim import DeviceGradScaler, FlatAdamW
+    torch.manual_seed(1)
+    ref = ToyLate().cuda()
+    mine = copy.deepcopy(ref)
+    ar = ParamArena(mine)
+    lr, wd, eps = 1e-2, 1e-2, 1e-5
+    opt_r = torch.optim.AdamW([{"params": list(ref.parameters())}], lr=lr, betas=(0.9, 0.98), weight_decay=wd, eps=eps)
+    sc_m = DeviceGradScaler("cuda", init_scale=256.0)
+    opt_m = FlatAdamW([{"params": list(mine.parameters())}], ar, sc_m, lr=lr, betas=(0.9, 0.98), eps=eps, weight_decay=wd)
+    g = torch.Generator(device="cuda").manual_seed(2)
+
+    def one_step(it, opt_mine, scaler):
+        x = torch.randn(8, 19, device="cuda", generator=g)
+        ref.use_late = mine.use_late = it >= 3
+        opt_r.zero_grad(set_to_none=True)
+        ref(x).pow(2).mean().backward()
+        opt_r.step()
+        scaler.scale(mine(x).pow(2).mean()).backward()
+        ar.finalize_grads()
+        scaler.step(opt_mine)
+        opt_mine.zero_grad()
+        torch.cuda.synchronize()
+        for (n, p), (_, q) in zip(ref.named_parameters(), mine.named_parameters()):
+            assert torch.allclose(p, q, rtol=2e-5, atol=5e-6), (it, n, (p - q).abs().max().item())
+
+    for it in range(6):
+        one_step(it, opt_m, sc_m)
+    sd = opt_m.state_dict()
+    sc2 = DeviceGradScaler("cuda", init_scale=1.0)
+    opt2 = FlatAdamW([{"params": list(mine.parameters())}], ar, sc2, lr=lr, betas=(0.9, 0.98), eps=eps, weight_decay=wd)
+    opt2.load_state_dict(sd)
+    for it in range(6, 9):
+        one_step(it, opt2, sc2)
