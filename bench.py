@@ -271,6 +271,18 @@ def run_native(a):
     ms_e2e, _, last_e2e, per_step_e2e = timed(step_e2e, a.steps)
     samples = sampler.stop() if sampler is not None else []
 
+    # ---- data-parallel consistency: after all the steps above every rank must hold bit-identical weights
+    dp = None
+    if world > 1:
+        ar_ = model.arena()
+        ref_w = ar_.flat.clone()
+        dist.broadcast(ref_w, src=0)
+        diff = (ref_w - ar_.flat).abs().max().reshape(1)
+        dist.all_reduce(diff, op=dist.ReduceOp.MAX)
+        dp = {"weight_max_abs_diff_vs_rank0": float(diff.item()), "ranks": world,
+              "after_steps": int(agent.global_step)}
+        del ref_w
+
     # ---- one extra instrumented step: per-kernel-family device time (CUDA events around every C-ABI call)
     phase("instrumented step")
     fams = {}
@@ -363,16 +375,95 @@ def run_native(a):
         "per_step_ms": per_step, "per_step_ms_e2e": per_step_e2e,
         "instrumented_step_ms": round(step_ms_prof, 3), "kernel_ms_sum": round(kern_total, 3),
     }
+    out["roofline"]["traffic"], out["roofline"]["traffic_source"] = committed_traffic()
+    wa = committed_window_attention_profile()
+    if wa is not None:
+        out["window_attention"] = wa
+    if world > 1:
+        out["dp_check"] = dp
+    if not a.no_gpu_baseline and world == 1:
+        phase("PyTorch-eager fp16-autocast baseline on the same GPU")
+        try:
+            out["gpu_torch_baseline"] = gpu_torch_baseline(B, steps=5, warmup=2)
+            out["gpu_torch_baseline"]["native_speedup"] = round(out["value"] / out["gpu_torch_baseline"]["value"], 2)
+        except Exception as e:   # a baseline must never take the headline down
+            out["gpu_torch_baseline"] = {"error": repr(e)[:300]}
     if not a.no_cpu_baseline and world == 1:
-        out["cpu_baseline"] = cpu_oracle_baseline(steps=1, warmup=0)
+        phase("CPU baseline (oracle port on the host cores)")
+        out["cpu_baseline"] = cpu_oracle_baseline(steps=3, warmup=1, B=4, budget_s=60.0)
     _emit(json.dumps(out))
 
 
 # ---------------------------------------------------------------------------------------------------------
+def committed_traffic():
+    """roofline.traffic: measured DRAM bytes per launch of the dominant kernel family, from the committed ncu capture
+    (profiles/r2_gemm_dram.json, written by tools/ncu_dram_summary.py from `ncu --metrics dram__bytes_read.sum,
+    dram__bytes_write.sum -k regex:gemm_f16` over one training step).  ncu cannot run inside a timed bench."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r2_gemm_dram.json")))
+        return d["dram_bytes_per_launch"], (f"profiles/r2_gemm_dram.json: {d['launches']} gemm_f16 launches of one step, "
+                                           f"algorithmic bytes/launch {d.get('algorithmic_bytes_per_launch')}")
+    except Exception:
+        return None, "no committed ncu DRAM capture"
+
+
+def committed_window_attention_profile():
+    """BASELINE metric's '% tensor-pipe' for the WindowAttention3D kernels (qkv GEMM + attention + proj GEMM, stage 2,
+    B = 8), from the committed `ncu --set full` summaries under profiles/ (a profiler cannot run inside the timed bench)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r2_window_attention_ncu.json")))
+    except Exception:
+        return None
+
+
+def gpu_torch_baseline(B, steps, warmup):
+    """The reference's ACTUAL GPU path as a baseline (never the product): the pinned PyTorch restatement of the model
+    (oracle/lavender_oracle.py == the reference's modules, tests/test_oracle_golden.py) run on the same B200 in eager
+    mode under torch.autocast(float16) as agent.py:219 / main_pretrain_mlm.py:150 do - cuBLAS GEMMs + ATen kernels +
+    autograd, the materialised [B_, nh, N, N] attention tensors included -, fwd + 2x CE + backward, configs[1] shapes."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import lavender_oracle as O
+    cfg = O.ModelCfg(swin=O.SWIN["base"], bert_layers=12, vtm_batch=4)
+    sd = O.make_state_dict(cfg, 0)
+    sd = {k: (v.cuda().requires_grad_(True) if v.dtype.is_floating_point else v.cuda()) for k, v in sd.items()}
+    sd["fc_mtm.predictions.decoder.bias"] = sd["fc_mtm.predictions.bias"]
+    batch = {k: v.cuda() for k, v in O.make_batch(B, seed=0).items()}
+    nblk = sum(cfg.swin.depths)
+    kp = (1.0 - torch.linspace(0, 0.2, nblk).view(-1, 1, 1)).cuda()
+    scaler = torch.amp.GradScaler("cuda")
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    for it in range(warmup + steps):
+        if it == warmup:
+            torch.cuda.synchronize()
+            ev[0].record()
+        keep = torch.floor(kp + torch.rand(nblk, 2, B, device="cuda")) / kp
+        np.random.seed(it)
+        with torch.autocast("cuda", dtype=torch.float16):
+            out = O.pretrain_forward(sd, batch, cfg, keep=keep)
+            loss, _, _ = O.pretrain_loss({k: (v.float() if torch.is_tensor(v) and v.is_floating_point() else v)
+                                          for k, v in out.items()})
+        scaler.scale(loss).backward()
+        for v in sd.values():
+            if v.dtype.is_floating_point:
+                v.grad = None
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / steps
+    peak = torch.cuda.max_memory_allocated() / 2 ** 30
+    del sd, batch
+    torch.cuda.empty_cache()
+    return {"value": round(B / (ms * 1e-3), 2), "unit": "clips/s", "ms_per_step": round(ms, 2), "steps": steps,
+            "warmup": warmup, "kind": "PyTorch eager, torch.autocast(float16), cuBLAS/ATen + autograd (the reference's GPU "
+            "path restated by the pinned oracle); fwd + 2xCE + bwd, no optimizer step; same B200, same shapes",
+            "peak_mem_gib": round(peak, 1)}
+
+
 def cpu_oracle_baseline(steps, warmup, B=4, budget_s=240.0):
     """Times the CPU oracle (a port: the pure-Python reference cannot travel to the GPU box) on a bounded sample of
-    the same workload: swin_base + 12-layer BERT, B clips (B=4 keeps the per-clip work of configs[1]: 4 VTM pairs
-    per clip), fwd + CE + bwd, fp32, all host threads."""
+    the same workload: swin_base + 12-layer BERT, B clips (4 VTM pairs per clip as in configs[1]), fwd + CE + bwd,
+    fp32, all host threads; `warmup` untimed steps first, then up to `steps` timed ones within `budget_s`."""
     import numpy as np
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -404,13 +495,14 @@ def cpu_oracle_baseline(steps, warmup, B=4, budget_s=240.0):
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
-        budget_s -= dt
+            budget_s -= dt
         if it >= warmup and budget_s < dt:   # keep the whole run within a few minutes on slow hosts
             break
     tot = sum(times)
     return {"value": round(B * len(times) / tot, 4), "unit": "clips/s", "cores": cores, "kind": "port",
             "sample": f"{len(times)} step(s) of B={B} clips (configs[1] shapes, 4 VTM pairs/clip), fwd+CE+bwd fp32, "
                       f"torch {torch.__version__} CPU, {cores} threads, {warmup} warm-up",
+            "sample_batch": B,
             "s_per_step": round(tot / len(times), 2)}
 
 
@@ -423,20 +515,110 @@ def run_reference(a):
     if rank != 0:
         return
     steps = max(1, a.steps)
-    warm = min(a.warmup, 1)
-    cb = cpu_oracle_baseline(steps=steps, warmup=warm)
-    B = 4
+    warm = max(1, min(a.warmup, 3))
+    B = PER_GPU_BATCH   # the native arm's per-GPU batch: same config (8 clips, 4 VTM pairs per clip)
+    cb = cpu_oracle_baseline(steps=steps, warmup=warm, B=B, budget_s=200.0)
     fwd = fwd_flops_per_clip("base", 12, B=PER_GPU_BATCH)
     out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "clips/s", "n_gpus": a.gpus,
            "steps": len_steps(cb), "warmup": warm, "ms_per_step": round(cb["s_per_step"] * 1e3, 1), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (same generator as the CUDA arm)",
-           "config": {"workload": WORKLOAD, "sample_batch": B,
+           "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B, "sample_batch": B,
                       "note": "the reference is pure Python/PyTorch and is not present on the GPU box; this arm times "
                               "the CPU oracle that is pinned against it (tests/test_oracle_golden.py)",
                       "algorithmic_gflop_per_clip_fwd_bwd": round(3 * fwd / 1e9, 1)},
            "cpu_baseline": cb,
            "e2e": {"value": cb["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     _emit(json.dumps(out))
+
+
+def run_check_dp(a):
+    """`--check-dp` (torchrun, N >= 2): the data-parallel path against a single process.
+      1. N ranks x B clips: eval-mode forward + 2x CE + scaled backward + GradSync (NCCL all-reduce, mean over ranks);
+         rank 0 then runs ONE process on the concatenated N*B clips with the same VTM negatives and the loss
+         (1/N) sum_r [CE_mtm(rank r rows) + CE_vtm(rank r rows)] (DDP semantics: mean of the per-rank means) and compares
+         the full flat gradient: relative L2 error and max-abs.
+      2. 3 optimizer steps in train() mode (dropout / DropPath on, per-rank data): max |w_rank0 - w_rankN| must be 0."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from lavender_b200 import dist as D
+    from lavender_b200.agent import Agent_Pretrain_MLM
+    from lavender_b200.pretrain import LAVENDER_Pretrain_MLM, FakeTokenizer, default_args
+    world, rank, local = D.get_world_size(), D.get_rank(), D.get_local_rank()
+    assert world > 1, "--check-dp needs torchrun with >= 2 ranks"
+    B = 4   # per rank: min(B, 4) = 4 VTM pairs per clip on every rank and in the concatenated run
+    args = default_args(vis_backbone_size="base", size_batch=B, seed=0, max_iter=100000, cuda_graph=False)
+    torch.cuda.set_device(local)
+    D.dist_init(args, distributed=True)
+    torch.manual_seed(0)
+    model = LAVENDER_Pretrain_MLM(args, FakeTokenizer())
+    for cfg in (model.trsfr.config, model.enc_txt.emb_txt.config):
+        cfg.lav_eval_dropout = True
+    model.cuda()
+    agent = Agent_Pretrain_MLM(args, model)
+    agent.prepare_dist_model()
+    ar = model.arena()
+    O = min(B, model.vtm_batch)
+
+    def rank_batch(r):
+        b = make_host_batch(B, seed=100 + r, pin=False)
+        torch.manual_seed(900 + r)
+        b.update(agent.masking(b["txt"], b["mask"], 0.15))
+        np.random.seed(500 + r)
+        return b, model.draw_negatives(B, O)
+
+    def losses(out, lo, hi, rows_v):
+        l1 = agent.loss_func(out["out_mtm"][lo:hi].flatten(0, 1), out["ans_mtm"][lo:hi].flatten())
+        l2 = agent.loss_func(out["out_vtm"][rows_v[0]:rows_v[1]].flatten(0, 1), out["ans_vtm"][rows_v[0]:rows_v[1]].flatten())
+        return l1 + l2
+
+    model.eval()
+    scale = 1024.0
+    mine, negs = rank_batch(rank)
+    dev = {k: v.cuda() for k, v in mine.items()}
+    dev["vtm_negatives"] = negs
+    agent.optzr.zero_grad(set_to_none=True)
+    out = model(dev)
+    (losses(out, 0, B, (0, B * O)) * scale).backward()
+    agent.grad_sync.finish()
+    g_dp = ar.grad.clone() / scale
+    torch.cuda.synchronize()
+    res = {}
+    if rank == 0:
+        allb = [rank_batch(r) for r in range(world)]
+        cat = {k: torch.cat([b[k] for b, _ in allb]).cuda() for k in ("img", "txt", "mask", "ans_mtm")}
+        cat["vtm_negatives"] = [np.asarray(n) + r * B for r, (_, ng) in enumerate(allb) for n in ng]
+        agent.optzr.zero_grad(set_to_none=True)
+        out = model(cat)
+        tot = sum(losses(out, r * B, (r + 1) * B, (r * B * O, (r + 1) * B * O)) for r in range(world)) / world
+        (tot * scale).backward()
+        ar.finalize_grads()
+        g_1 = ar.grad.clone() / scale
+        torch.cuda.synchronize()
+        res["grad_rel_l2_err"] = float(((g_dp - g_1).norm() / g_1.norm()).item())
+        res["grad_max_abs_err"] = float((g_dp - g_1).abs().max().item())
+        res["grad_norm"] = float(g_1.norm().item())
+        del out, tot, g_1, cat
+    del g_dp
+    torch.cuda.empty_cache()
+    dist.barrier()
+    # ---- 3 real training steps, per-rank data: weights must stay bit-identical across ranks
+    model.train()
+    for cfg in (model.trsfr.config, model.enc_txt.emb_txt.config):
+        cfg.lav_eval_dropout = False
+    for it in range(3):
+        b, _ = rank_batch(rank * 10 + it)
+        agent.step(agent.prepare_batch(b), True)
+    ref_w = ar.flat.clone()
+    dist.broadcast(ref_w, src=0)
+    diff = (ref_w - ar.flat).abs().max().reshape(1)
+    dist.all_reduce(diff, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        res.update({"check_dp": True, "n_gpus": world, "per_rank_batch": B, "weight_max_abs_diff_after_3_steps": float(diff.item()),
+                    "pass": bool(res["grad_rel_l2_err"] <= 1e-4 and diff.item() == 0.0),
+                    "note": "gradients: N-rank all-reduced mean vs ONE process on the concatenated batch (fp16 operands, fp32 "
+                            "accumulation: the two differ only by summation order); tolerance 1e-4 relative L2"})
+        _emit(json.dumps(res))
 
 
 def main():
@@ -449,6 +631,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the PyTorch-eager fp16-autocast leg")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--quick", action="store_true", help="resident steps only (for ncu runs)")
     ap.add_argument("--no-pipeline", action="store_true", help="e2e leg without the prefetch pipeline (serial H2D)")
@@ -456,6 +639,8 @@ def main():
                     help="one eager step between cudaProfilerStart/Stop (ncu --profile-from-start off)")
     ap.add_argument("--eval-dropout", action="store_true",
                     help="identity BERT dropout (default: active p=0.1 dropout as in the reference's train() step)")
+    ap.add_argument("--check-dp", action="store_true",
+                    help="N-rank gradients vs one process on the concatenated batch + weight equality after 3 steps")
     a = ap.parse_args()
     # stdout carries exactly ONE JSON line: libraries that write to fd 1 (NCCL prints its version banner there) are
     # routed to stderr; the result line goes to the saved descriptor
@@ -466,6 +651,8 @@ def main():
     _emit = lambda line: os.write(real_stdout, (line + "\n").encode())
     if a.impl == "reference":
         run_reference(a)
+    elif a.check_dp:
+        run_check_dp(a)
     else:
         run_native(a)
 

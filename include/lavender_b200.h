@@ -225,10 +225,11 @@ int lav_bert_embed_ln_fwd(const int64_t* ids, const int64_t* pos_ids, const int6
                           int vocab, int max_pos, int n_types, const float* word, const float* pos, const float* type,
                           const float* gamma, const float* beta, float eps, float* sum32, float* y32, float* mean,
                           float* rstd, void* stream);
-/* d{word,pos,type}[index[r]] += dsum32[r]  (autograd of the three nn.Embedding lookups; fp32 atomics) */
+/* d{word,pos,type}[index[r]] += dsum32[r]  (autograd of the three nn.Embedding lookups; fp32 atomics).  Rows whose id
+ * equals padding_idx (HF: word_embeddings has padding_idx = pad_token_id = 0; pass -1 for none) add nothing to dword. */
 int lav_bert_embed_bwd(const float* dsum32, const int64_t* ids, const int64_t* pos_ids, const int64_t* type_ids,
                        int rows, int Lt, int C, int vocab, int max_pos, int n_types, float* dword, float* dpos,
-                       float* dtype, void* stream);
+                       float* dtype, int padding_idx, void* stream);
 
 /* EncVideo.forward token assembly, model.py:69-85: row (b,t,s), s in [0, 1+hw):
  *   sum32 = (s == 0 ? emb_cls : feat[(b*T+t)*hw + s-1]) + emb_pos[s] + (odr_swap[b*T+t] ? emb_odr : emb_len[t])

@@ -174,7 +174,9 @@ class _BertEmbedFn(torch.autograd.Function):
             g2 = ops.dropout_f32(g2, empty32(rows, H, device=gy.device), ctx.drop)
         d = empty32(rows, H, device=gy.device)
         ops.layernorm_bwd(g2, s32, gamma, mean, rstd, rows=rows, C=H, dx32=d, dgamma=ar.g(gamma), dbeta=ar.g(beta))
-        ops.bert_embed_bwd(d, ids1, ps1, tt1, ar.g(word), ar.g(pos), ar.g(typ), Lt=ctx.Lt)
+        pad = ctx.mod.word_embeddings.padding_idx
+        ops.bert_embed_bwd(d, ids1, ps1, tt1, ar.g(word), ar.g(pos), ar.g(typ), Lt=ctx.Lt,
+                           padding_idx=-1 if pad is None else pad)
         return (None,) * 9
 
 

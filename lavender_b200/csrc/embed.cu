@@ -95,7 +95,8 @@ __global__ void __launch_bounds__(kEmbThreads) bert_embed_ln_fwd_kernel(const Be
 // d{word,pos,type}[index[r]] += d[r]   (fp32 atomics; a few hundred rows per step)
 __global__ void __launch_bounds__(kEmbThreads)
 bert_embed_bwd_kernel(const float* d, const int64_t* ids, const int64_t* pos_ids, const int64_t* type_ids, int rows,
-                      int Lt, int C, int vocab, int max_pos, int n_types, float* dword, float* dpos, float* dtype) {
+                      int Lt, int C, int vocab, int max_pos, int n_types, float* dword, float* dpos, float* dtype,
+                      int padding_idx) {
   const int lane = threadIdx.x & 31;
   for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += gridDim.x * 8) {
     int64_t w = min(max(ids[r], (int64_t)0), (int64_t)vocab - 1);
@@ -105,7 +106,7 @@ bert_embed_bwd_kernel(const float* d, const int64_t* ids, const int64_t* pos_ids
     tt = min(max(tt, (int64_t)0), (int64_t)n_types - 1);
     for (int c = lane; c < C; c += 32) {
       const float g = d[(int64_t)r * C + c];
-      if (dword) atomicAdd(dword + w * C + c, g);
+      if (dword && w != padding_idx) atomicAdd(dword + w * C + c, g);   // nn.Embedding(padding_idx): the pad row gets no gradient
       if (dpos) atomicAdd(dpos + ps * C + c, g);
       if (dtype) atomicAdd(dtype + tt * C + c, g);
     }
@@ -213,11 +214,11 @@ extern "C" int lav_bert_embed_ln_fwd(const int64_t* ids, const int64_t* pos_ids,
 
 extern "C" int lav_bert_embed_bwd(const float* dsum32, const int64_t* ids, const int64_t* pos_ids,
                                   const int64_t* type_ids, int rows, int Lt, int C, int vocab, int max_pos, int n_types,
-                                  float* dword, float* dpos, float* dtype, void* stream) {
+                                  float* dword, float* dpos, float* dtype, int padding_idx, void* stream) {
   LAV_REQUIRE(dsum32 && ids && Lt > 0, "lav_bert_embed_bwd: null pointer");
   if (rows <= 0) return LAV_OK;
   bert_embed_bwd_kernel<<<emb_grid(rows), kEmbThreads, 0, (cudaStream_t)stream>>>(dsum32, ids, pos_ids, type_ids, rows, Lt, C,
-                                                                                 vocab, max_pos, n_types, dword, dpos, dtype);
+                                                                                 vocab, max_pos, n_types, dword, dpos, dtype, padding_idx);
   LAV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return LAV_OK;

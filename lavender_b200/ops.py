@@ -9,6 +9,7 @@ import torch
 from . import _lib as L
 
 F16 = torch.float16
+_CHECK_IDS = __import__("os").environ.get("LAV_CHECK_IDS", "0") == "1"
 
 # Optional per-call timing (bench.py's roofline leg): when PROFILE is a list, every wrapper brackets its C-ABI call
 # with CUDA events on the launching stream and appends (family, start_event, end_event, algorithmic_flops).
@@ -245,6 +246,9 @@ def bert_embed_ln_fwd(ids, pos_ids, type_ids, word, pos, typ, gamma, beta, eps, 
     rows, C = ids.numel(), word.shape[1]
     for t in (ids, pos_ids, type_ids):
         assert t is None or (t.dtype == torch.int64 and t.is_contiguous() and t.numel() == rows)
+    check_ids(ids, word.shape[0], "word_embeddings")
+    check_ids(pos_ids, pos.shape[0], "position_embeddings")
+    check_ids(type_ids, typ.shape[0], "token_type_embeddings")
     with _Timed("embed"):
         rc = L.lib().lav_bert_embed_ln_fwd(_p(ids), _p(pos_ids), _p(type_ids), rows, Lt, C, word.shape[0], pos.shape[0],
                                            typ.shape[0], _p(word), _p(pos), _p(typ), _p(gamma), _p(beta), eps, _p(sum32),
@@ -252,12 +256,22 @@ def bert_embed_ln_fwd(ids, pos_ids, type_ids, word, pos, typ, gamma, beta, eps, 
     L.check(rc, "lav_bert_embed_ln_fwd")
 
 
-def bert_embed_bwd(dsum32, ids, pos_ids, type_ids, dword, dpos, dtyp, *, Lt):
+def check_ids(ids, n, what):
+    """torch's nn.Embedding raises on out-of-range indices; the kernels clamp (no device-side assert).  LAV_CHECK_IDS=1
+    validates on the host (one sync per call; off by default on the hot path, on in the tests)."""
+    if _CHECK_IDS and ids is not None and ids.numel():
+        lo, hi = int(ids.min()), int(ids.max())
+        if lo < 0 or hi >= n:
+            raise IndexError(f"{what}: index out of range [{lo}, {hi}] for an embedding of {n} rows")
+
+
+def bert_embed_bwd(dsum32, ids, pos_ids, type_ids, dword, dpos, dtyp, *, Lt, padding_idx=-1):
     rows, C = ids.numel(), dsum32.shape[-1]
     assert dsum32.is_contiguous() and dsum32.dtype == torch.float32
     with _Timed("embed"):
         rc = L.lib().lav_bert_embed_bwd(_p(dsum32), _p(ids), _p(pos_ids), _p(type_ids), rows, Lt, C, dword.shape[0],
-                                        dpos.shape[0], dtyp.shape[0], _p(dword), _p(dpos), _p(dtyp), _stream())
+                                        dpos.shape[0], dtyp.shape[0], _p(dword), _p(dpos), _p(dtyp), int(padding_idx),
+                                        _stream())
     L.check(rc, "lav_bert_embed_bwd")
 
 

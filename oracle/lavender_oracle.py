@@ -166,10 +166,11 @@ def window_attention(sd, p, x, mask, num_heads, window_cfg):
     qkv = _qa(qkv.reshape(B_, N, 3, num_heads, hd).permute(2, 0, 3, 1, 4))
     q, k, v = qkv[0] * hd ** -0.5, qkv[1], qkv[2]
     attn = bmm(q, k.transpose(-2, -1))
-    idx = relative_position_index(tuple(window_cfg))[:N, :N].reshape(-1)
+    idx = relative_position_index(tuple(window_cfg))[:N, :N].reshape(-1).to(x.device)
     bias = sd[p + "relative_position_bias_table"][idx].reshape(N, N, -1).permute(2, 0, 1)
     attn = attn + bias.unsqueeze(0)
     if mask is not None:
+        mask = mask.to(x.device)
         nW = mask.shape[0]
         attn = attn.view(B_ // nW, nW, num_heads, N, N) + mask.unsqueeze(1).unsqueeze(0)
         attn = attn.view(-1, num_heads, N, N)
@@ -275,7 +276,7 @@ def enc_video(sd, img, cfg: ModelCfg, keep=None, odr=None, vt_mask=None):
         f = f + sd["enc_img.emb_len"][:, :T]
     f = F.layer_norm(f, (cfg.hidden,), sd["enc_img.norm.weight"], sd["enc_img.norm.bias"], 1e-5)
     f = f.view(B, T * (1 + h * w), cfg.hidden)
-    m = torch.ones(B, T, 1 + h * w, dtype=torch.long)
+    m = torch.ones(B, T, 1 + h * w, dtype=torch.long, device=img.device)
     if vt_mask is not None:
         m = m * vt_mask
     return f, m.view(B, T * (1 + h * w))
@@ -364,16 +365,16 @@ def pretrain_forward(sd, batch, cfg: ModelCfg, negs=None, keep=None):
     if negs is None:
         negs = draw_negatives(B, O)
     pairs = vtm_pairs(B, O, negs)
-    vi = torch.tensor([p[0] for p in pairs])
-    ti = torch.tensor([p[1] for p in pairs])
+    vi = torch.tensor([p[0] for p in pairs], device=img.device)
+    ti = torch.tensor([p[1] for p in pairs], device=img.device)
     ft, mt, tt = feat_txt[ti], mask[ti], txt[ti]
     if cfg.enable_task_token:  # model.py:248-265,292-306: emb_task[0] row prefixed, mask 1, txt id 0
         n = len(pairs)
         ft = torch.cat([sd["emb_task"][0].view(1, 1, -1).expand(n, -1, -1), ft], dim=1)
-        mt = torch.cat([torch.ones(n, 1, dtype=mt.dtype), mt], dim=1)
-        tt = torch.cat([torch.zeros(n, 1, dtype=tt.dtype), tt], dim=1)
+        mt = torch.cat([torch.ones(n, 1, dtype=mt.dtype, device=mt.device), mt], dim=1)
+        tt = torch.cat([torch.zeros(n, 1, dtype=tt.dtype, device=tt.device), tt], dim=1)
     ans_vtm = torch.full_like(tt, -1)
-    ans_vtm[:, -1] = torch.tensor([cfg.true_id if p[2] else cfg.false_id for p in pairs])
+    ans_vtm[:, -1] = torch.tensor([cfg.true_id if p[2] else cfg.false_id for p in pairs], device=tt.device)
     out = go_cross(sd, feat_img[vi], mask_img[vi], ft, mt, cfg)
     out_vtm = mlm_head(sd, out[:, Lv:])
     return {"out_mtm": out_mtm, "out_vtm": out_vtm, "ans_mtm": batch.get("ans_mtm"), "ans_vtm": ans_vtm}
