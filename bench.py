@@ -179,7 +179,7 @@ def run_native(a):
                 agent.graphs = GraphCache(agent)
                 g = agent.graphs.get(dev_batch)
             l1, l2 = g(dev_batch)
-            agent.backward_step(None, graphed=True)
+            agent.backward_step(None, graphed="synced" if g.sync_in_graph else True)
             return l1, l2
         return step_eager()
 

@@ -174,7 +174,9 @@ class Agent_Base:
         which also zeroes the gradient arena at its start, so neither backward nor zero_grad happens here."""
         if not graphed:
             self.scaler.scale(loss).backward()
-        if self.grad_sync is not None:
+        if graphed and self.grad_sync is not None and graphed == "synced":
+            pass                            # the gradient all-reduce was captured inside the replayed graph (graph.py)
+        elif self.grad_sync is not None:
             self.grad_sync.finish()
         elif hasattr(self.model, "arena"):
             self.model.arena().finalize_grads()
@@ -218,8 +220,9 @@ class Agent_Pretrain_MLM(Agent_Base):
             if self.graphs is None:
                 from .graph import GraphCache
                 self.graphs = GraphCache(self)
-            ls_mtm, ls_vtm = self.graphs.get(batch)(batch)
-            self.backward_step(None, graphed=True)
+            g = self.graphs.get(batch)
+            ls_mtm, ls_vtm = g(batch)
+            self.backward_step(None, graphed="synced" if g.sync_in_graph else True)
             return ls_mtm, ls_vtm
         out = self.forward_step(batch)
         out_mtm, out_vtm, ans_mtm, ans_vtm = out["out_mtm"], out["out_vtm"], out["ans_mtm"], out["ans_vtm"]
@@ -306,7 +309,27 @@ class Agent_Pretrain_MLM(Agent_Base):
         sel = draw & ~special
         ans[sel] = txt[sel]
         txt[sel] = self.mask_token_id
-        return {"txt": txt, "mask": mask, "ans_mtm": ans}
+        out = {"txt": txt, "mask": mask, "ans_mtm": ans}
+        rows = self.labelled_rows(ans)
+        if rows is not None:
+            out["mtm_rows"] = rows
+        return out
+
+    def labelled_rows(self, ans, capacity=None):
+        """fixed-capacity list of the flat indices (b * Lt + t) of the labelled MLM rows, padded with the
+        index of an unlabelled row (its label is -1, so it adds nothing to the loss).  Capacity = one 128-row GEMM tile
+        (or B*Lt when smaller); returns None when the batch has more labelled rows (the model then computes full logits).
+        `LAV_MLM_LABELLED_ONLY=0` disables it."""
+        if os.environ.get("LAV_MLM_LABELLED_ONLY", "1") == "0":
+            return None
+        flat = ans.reshape(-1)
+        cap = capacity or min(128, flat.numel())
+        idx = (flat != -1).nonzero().reshape(-1)
+        un = (flat == -1).nonzero().reshape(-1)
+        if idx.numel() > cap or un.numel() == 0:
+            return None
+        pad = un[:1].expand(cap - idx.numel())
+        return torch.cat([idx, pad]).contiguous()
 
     def go_dl(self, ep, dl, is_train):
         self.model.train(is_train)

@@ -66,6 +66,7 @@ class ParamArena:
         self._grad_views = {}
         self._clean = set()
         self.on_swin_backward = None  # set by dist.GradSync: called when the video encoder's backward begins
+        self.on_swin_stage = None     # ... and when that backward enters stage s (3, 2, 1, 0)
 
     # ---- validity / shadow ------------------------------------------------------------------------
     def valid(self):

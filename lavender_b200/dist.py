@@ -3,9 +3,11 @@
 Replaces utils/dist.py (process-group bootstrap + control-plane helpers, same function names) and the
 DDP / DeepSpeed ZeRO-1 wrap of agent.py:252-265 + utils/deepspeed.py.  The forward/backward of LAVENDER shards by
 batch with no data-path exchange; the only collective is ONE all-reduce of the flat fp32 gradient
-arena per step (`GradSync`), issued in two pieces so the first overlaps the Video-Swin backward:
-  piece 1  fusion BERT + MLM head gradients   - final once autograd reaches the video encoder's backward
-  piece 2  everything else (Swin, embeddings) - after backward
+arena per step (`GradSync`), issued in three pieces so that all but ~2 % of it overlaps the Video-Swin backward:
+  early  fusion BERT + MLM head + text embeddings + EncVideo parameters - final once autograd reaches the Swin backward
+  mid    Swin stages 2-3                                                 - final when the backward enters stage 1
+  late   Swin stages 0-1, patch embed, the rest                          - after backward (the only exposed part)
+In CUDA-graph mode the collectives are captured inside the step's graph as parallel branches (graph.py).
 NCCL picks NVLS (in-switch reduction) or ring on the NVSwitch domain; nothing here depends on the link count.
 The same code runs on the `gloo` backend with CPU tensors, which is how the CPU tests cover world_size 2.
 """
@@ -142,19 +144,29 @@ def iter_tqdm(item):
 # ---------------------------------------------------------------------------------------------------------
 class GradSync:
     """Averages the flat gradient buffer of a ParamArena across ranks (DDP semantics: mean over ranks,
-    agent.py:261-265).  `early_prefixes` name the parameter groups whose gradients are final before the video
-    encoder's backward starts; their (contiguous) arena ranges are reduced on a side stream by `start_early()`,
-    which the Swin backward calls through `arena.on_swin_backward`."""
+    agent.py:261-265) in three pieces, each issued on a communication side stream as soon as its gradients are final, so
+    that only the last (small) one is exposed:
+      early  fusion BERT + MLM head + text embeddings + EncVideo's own parameters - final when autograd reaches the video
+             encoder's backward (`arena.on_swin_backward`, called by _SwinFn.backward);      ~134 M parameters (base)
+      mid    Swin stages 2-3 + the final Swin norm - final when the backward enters stage 1
+             (`arena.on_swin_stage`);                                                        ~83 M parameters
+      late   everything else (Swin stages 0-1, patch embed, emb_task ...) after backward;       ~4 M parameters
+    The spans are contiguous arena ranges.  Under CUDA-graph capture (graph.py) the side-stream collectives become
+    parallel branches of the captured step; `finish()` joins them."""
 
-    def __init__(self, arena, group=None, early_prefixes=("trsfr.", "fc_mtm.")):
+    def __init__(self, arena, group=None,
+                 early_prefixes=("trsfr.", "fc_mtm.", "enc_txt.", "enc_img.fc.", "enc_img.norm.", "enc_img.emb_"),
+                 mid_prefixes=("enc_img.swin.layers.2.", "enc_img.swin.layers.3.", "enc_img.swin.norm.")):
         self.arena, self.group = arena, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.early = self._ranges(early_prefixes)
-        self.late = self._complement(self.early)
-        self._early_done = False
+        self.mid = self._ranges(mid_prefixes)
+        self.late = self._complement(self.early + self.mid)
+        self._early_done = self._mid_done = False
         self._stream = None
         self._event = None
         arena.on_swin_backward = self.start_early
+        arena.on_swin_stage = self.on_stage
 
     def _ranges(self, prefixes):
         a = self.arena
@@ -189,10 +201,9 @@ class GradSync:
                 dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
                 t.div_(self.world)
 
-    def start_early(self):
-        """Called when the Swin backward begins: BERT + head gradients are complete -> reduce them concurrently."""
-        if self.world < 2 or self._early_done or not self.early:
-            return
+    def _side(self, spans):
+        """Reduce `spans` on the communication stream, ordered after everything enqueued on the current stream so far
+        (incl. the weight-gradient side stream, joined by finalize_grads)."""
         self.arena.finalize_grads()
         if self.arena.grad.is_cuda:
             if self._stream is None:
@@ -201,25 +212,38 @@ class GradSync:
             cur = torch.cuda.current_stream()
             self._stream.wait_stream(cur)
             with torch.cuda.stream(self._stream):
-                self._reduce(self.early)
+                self._reduce(spans)
                 self._event.record(self._stream)
         else:
-            self._reduce(self.early)
+            self._reduce(spans)
+
+    def start_early(self):
+        """Called when the Swin backward begins: BERT / head / text-embedding gradients are complete."""
+        if self.world < 2 or self._early_done or not self.early:
+            return
+        self._side(self.early)
         self._early_done = True
+
+    def on_stage(self, s):
+        """Called by the Swin backward when it enters stage `s` (3, 2, 1, 0): at s == 1 stages 2-3 are complete."""
+        if self.world < 2 or self._mid_done or not self.mid or s != 1:
+            return
+        self._side(self.mid)
+        self._mid_done = True
 
     def finish(self):
         """After backward: reduce what is left and join the side stream.  Returns the number of elements reduced."""
         self.arena.finalize_grads()
         if self.world < 2:
-            self._early_done = False
+            self._early_done = self._mid_done = False
             return 0
-        if self._early_done:
-            if self._event is not None:
-                torch.cuda.current_stream().wait_event(self._event)
-            self._reduce(self.late)
-        else:
-            self._reduce([(0, self.arena.total)])
-        self._early_done = False
+        rest = list(self.late) + ([] if self._early_done else list(self.early)) + ([] if self._mid_done else list(self.mid))
+        if self._event is not None and (self._early_done or self._mid_done):
+            torch.cuda.current_stream().wait_event(self._event)
+        if not (self._early_done or self._mid_done):
+            rest = [(0, self.arena.total)]
+        self._reduce(sorted(rest))
+        self._early_done = self._mid_done = False
         return self.arena.total
 
 

@@ -22,7 +22,7 @@ import torch
 
 from .dropout import rng_for
 
-_STATIC_KEYS = ("img", "txt", "mask", "ans_mtm", "vt_mask")
+_STATIC_KEYS = ("img", "txt", "mask", "ans_mtm", "vt_mask", "mtm_rows")
 
 
 def batch_signature(batch):
@@ -51,7 +51,14 @@ class GraphedPretrainStep:
         self._txt_idx_ring = PinnedRing(lambda: torch.empty(ti.shape, dtype=ti.dtype).pin_memory())
         model.train()
         ar = model.arena()
-        hook, ar.on_swin_backward = ar.on_swin_backward, None   # no side-stream NCCL inside the capture (see dist.py)
+        # Data parallel: the gradient all-reduce is captured INSIDE the step's graph (LAV_GRAPH_NCCL=0: after the replay,
+        # un-overlapped, as in round 1).  GradSync's pieces run on a side stream forked from the capture stream when the
+        # Swin backward starts / enters stage 1, i.e. as parallel branches of the graph, joined by finish() below.
+        import os as _os
+        self.sync_in_graph = agent.grad_sync is not None and _os.environ.get("LAV_GRAPH_NCCL", "1") != "0"
+        hooks = (ar.on_swin_backward, ar.on_swin_stage)
+        if not self.sync_in_graph:
+            ar.on_swin_backward = ar.on_swin_stage = None
         # eager warm-up on a side stream (lazy kernel attribute setup, index-map caches, allocator)
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
@@ -77,7 +84,7 @@ class GraphedPretrainStep:
         with torch.cuda.graph(self.graph, stream=cap):
             self.l_mtm, self.l_vtm = self._fwd_bwd()
         self.native_launches = _lib.launch_count() - n0   # kernels of the C-ABI library inside one replay
-        ar.on_swin_backward = hook
+        ar.on_swin_backward, ar.on_swin_stage = hooks
 
     def _fwd_bwd(self):
         ag = self.agent
@@ -86,7 +93,10 @@ class GraphedPretrainStep:
         l1 = ag.loss_func(out["out_mtm"].flatten(0, out["out_mtm"].dim() - 2), out["ans_mtm"].flatten())
         l2 = ag.loss_func(out["out_vtm"].flatten(0, out["out_vtm"].dim() - 2), out["ans_vtm"].flatten())
         ag.scaler.scale(l1 + l2).backward()
-        ag.model.arena().finalize_grads()
+        if self.sync_in_graph:
+            ag.grad_sync.finish()          # joins the overlapped pieces, reduces the rest: all inside the capture
+        else:
+            ag.model.arena().finalize_grads()
         return l1.detach(), l2.detach()
 
     def load(self, batch):

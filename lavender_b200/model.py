@@ -321,7 +321,11 @@ class LAVENDER_Base(nn.Module):
         mask = self.get_attn_mask(mask_img, mask_txt, attn_mask_type=attn_mask_type, mask_pretxt=mask_pretxt)
         assert feat.shape[1] == mask.shape[1], \
             f"mask and feat must have the same length, got {feat.shape[1]} vs. {mask.shape[1]}"
-        out = self.trsfr(feat, mask, output_attentions=True)
+        # config.is_decoder (set by LAVENDER_Captioning(is_decoder=True), model_for_captioning.py:43, on the config object the
+        # reference's mask_ext = bert.get_extended_attention_mask reads): HF turns a 2-D padding mask into padding AND a
+        # causal mask over the whole sequence -> key mask + causal_from = 0 in the attention kernels.
+        causal = 0 if getattr(self.config, "is_decoder", False) else None
+        out = self.trsfr(feat, mask, output_attentions=True, causal_from=causal)
         return out["last_hidden_state"], out["attentions"]
 
     # ---- task token / prompt prefix (model.py:245-306) -------------------------------------------------

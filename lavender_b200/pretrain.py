@@ -87,8 +87,20 @@ class LAVENDER_Pretrain_MLM(LAVENDER_Base):
         feat = torch.cat([torch.cat([feat_img, pad_f, feat_txt], dim=1), torch.cat([feat_img[vi], p_feat], dim=1)], dim=0)
         amask = torch.cat([torch.cat([mask_img, pad_m, mask_txt], dim=1), torch.cat([mask_img[vi], p_mask], dim=1)], dim=0)
         out = self.trsfr(feat, amask, output_attentions=True)["last_hidden_state"]
-        out_mtm = self.fc_mtm(out[:B, Lv + d:])   # (two head calls: one merged logits tensor would make autograd
-        #                                            materialise two zero-padded [rows, vocab] gradients and add them)
+        ans_mtm = batch["ans_mtm"]
+        rows = batch["mtm_rows"]
+        if self.training and rows is not None:
+            # the 30522-wide head only on the MLM rows that carry a label (ans != -1, ~15 % of B*Lt;
+            # main_pretrain_mlm.py:158-160 ignores the rest).  `mtm_rows` is a fixed-capacity list of flat row indices
+            # (b*Lt + t) built on the host by Agent_Pretrain_MLM.masking next to ans_mtm (padding entries point at an
+            # unlabelled row), so the gather has a static shape and the step stays CUDA-graph capturable; loss and
+            # gradients are identical because unlabelled rows contribute nothing to the cross-entropy.
+            h = out[:B, Lv + d:].reshape(B * Lt, Hh)
+            out_mtm = self.fc_mtm(h.index_select(0, rows)).unsqueeze(0)          # [1, capacity, vocab]
+            ans_mtm = ans_mtm.reshape(-1).index_select(0, rows).unsqueeze(0)     # [1, capacity] (-1 on padding)
+        else:
+            out_mtm = self.fc_mtm(out[:B, Lv + d:])   # (two head calls: one merged logits tensor would make autograd
+            #                                            materialise two zero-padded [rows, vocab] gradients and add them)
         if self.training and self.vtm_last_token_only:
             # in training only the last text position of a VTM sequence carries a label (ans_vtm is -1
             # elsewhere, main_pretrain_mlm.py:103-105), so the 30522-wide head runs on those B*O rows instead of
@@ -98,7 +110,7 @@ class LAVENDER_Pretrain_MLM(LAVENDER_Base):
             ans_vtm = ans_vtm[:, -1:]
         else:
             out_vtm = self.fc_mtm(out[B:, Lv:])
-        return {"out_vtm": out_vtm, "out_mtm": out_mtm, "ans_vtm": ans_vtm, "ans_mtm": batch["ans_mtm"]}
+        return {"out_vtm": out_vtm, "out_mtm": out_mtm, "ans_vtm": ans_vtm, "ans_mtm": ans_mtm}
 
 
 class FakeTokenizer:

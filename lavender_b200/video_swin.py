@@ -405,6 +405,8 @@ class _SwinFn(torch.autograd.Function):
         ds_ws = {}
         for s in range(mod.num_layers - 1, -1, -1):
             layer = mod.layers[s]
+            if ar.on_swin_stage is not None:
+                ar.on_swin_stage(s)   # data parallel: the gradients of the deeper stages are final -> reduce them now
             if layer.downsample is not None:
                 ds = layer.downsample
                 xprev, y16, mm, mr, mmap, Mp, Cp = saved["merges"][s]

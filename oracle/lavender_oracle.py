@@ -327,6 +327,145 @@ def go_cross(sd, feat_img, mask_img, feat_txt, mask_txt, cfg: ModelCfg):
     return x
 
 
+def seq2seq_mask(mask_img, Lt, n_pre=0):
+    """LAVENDER_Base.get_attn_mask model.py:194-221 (attn_mask_type='seq2seq'): [B, L, L] with L = Lv + n_pre + Lt;
+    every query sees the (masked) video + prefix keys, the Lt text queries see the text keys causally (the text padding
+    mask is NOT applied: model.py:213-214 builds the triangle from ones)."""
+    B, Lv = mask_img.shape
+    full = torch.cat([mask_img, torch.ones(B, n_pre, dtype=mask_img.dtype, device=mask_img.device)], dim=1)
+    Lf, L = Lv + n_pre, Lv + n_pre + Lt
+    m = torch.zeros(B, L, L, dtype=torch.long, device=mask_img.device)
+    m[:, :, :Lf] = full.unsqueeze(1)
+    m[:, Lf:, Lf:] = torch.tril(torch.ones(Lt, Lt, dtype=torch.long, device=mask_img.device))
+    return m
+
+
+def go_cross_masked(sd, feat, mask, cfg: ModelCfg, decoder=False):
+    """go_cross on an already concatenated sequence with a [B, L] or [B, L, L] 0/1 mask.  decoder=True restates HF's
+    get_extended_attention_mask for config.is_decoder (model_for_captioning.py:43 sets it on the shared config): a 2-D
+    padding mask is AND-ed with a causal mask over the whole sequence."""
+    if decoder and mask.dim() == 2:
+        L = mask.shape[1]
+        mask = torch.tril(torch.ones(L, L, dtype=mask.dtype, device=mask.device)).unsqueeze(0) * mask.unsqueeze(1)
+    ext = extended_mask(mask)
+    x = feat
+    for l in range(cfg.bert_layers):
+        x = bert_layer(sd, f"trsfr.layer.{l}.", x, ext, cfg.bert_heads)
+    return x
+
+
+TASK_TOK2ID = {"vtm": 0, "mc": 1, "oe": 2, "cap": 3}   # main_pretrain_mlm.py:51, model_for_captioning.py:48
+
+
+def add_task_token(sd, cfg: ModelCfg, txt_like, mask_txt, feat_txt, task_name):
+    """prepro_txt_inputs with enable_task_token (model.py:248-306): prefix (id 0, mask 1, emb_task[task]) on batched rows."""
+    if not cfg.enable_task_token:
+        return txt_like, mask_txt, feat_txt
+    n = feat_txt.shape[0]
+    e = sd["emb_task"][TASK_TOK2ID[task_name]].view(1, 1, -1).expand(n, -1, -1)
+    z = torch.zeros(n, 1, dtype=txt_like.dtype, device=txt_like.device)
+    o = torch.ones(n, 1, dtype=mask_txt.dtype, device=mask_txt.device)
+    return torch.cat([z, txt_like], 1), torch.cat([o, mask_txt], 1), torch.cat([e, feat_txt], 1)
+
+
+def multitask_forward(sd, batch, cfg: ModelCfg, task, task_name, decoder=False):
+    """LAVENDER_Multi_Task.forward main_multi_task_mlm.py:82-225 and LAVENDER_Captioning.encode_forward
+    model_for_captioning.py:61-93 (task-token prefix, no prompt).  Returns (logits, labels)."""
+    img = batch["img"]
+    B, T, _, H, W = img.shape
+    Lv = (1 + (H // 32) * (W // 32)) * T
+    n_pre = 1 if cfg.enable_task_token else 0
+    if "captioning" in task:
+        feat_img, mask_img = enc_video(sd, img, cfg)
+        feat_txt = bert_embeddings(sd, batch["txt"])
+        ans, _, feat_txt = add_task_token(sd, cfg, batch["ans_mtm"], batch["mask"], feat_txt, "cap")
+        ans = ans.clone()
+        ans[:, :n_pre] = -1
+        m = seq2seq_mask(mask_img, batch["txt"].shape[1], n_pre)
+        out = go_cross_masked(sd, torch.cat([feat_img, feat_txt], 1), m, cfg)
+        return mlm_head(sd, out[:, Lv:]), ans
+    if "retrieval" in task:
+        txt, mask, vid = batch["txt"], batch["mask"], batch["vid"]
+        feat_img, mask_img = enc_video(sd, img, cfg)
+        feat_txt = bert_embeddings(sd, txt)
+        vi = torch.arange(B).repeat_interleave(B)
+        ti = torch.arange(B).repeat(B)
+        t, mt, ft = add_task_token(sd, cfg, txt[ti], mask[ti], feat_txt[ti], task_name)
+        ans = torch.full_like(t, -1)
+        same = torch.tensor([vid[int(i)] == vid[int(j)] for i, j in zip(vi, ti)])
+        ans[:, -1] = torch.where(same, torch.tensor(cfg.true_id), torch.tensor(cfg.false_id))
+        out = go_cross_masked(sd, torch.cat([feat_img[vi], ft], 1), torch.cat([mask_img[vi], mt], 1), cfg, decoder)
+        return mlm_head(sd, out[:, Lv:]), ans
+    if "qamc" in task and "lsmdc-mc" in task:
+        txt, mask, ans = batch["txt"], batch["mask"], batch["mask_ans"]
+        O_ = txt.shape[1]
+        feat_img, mask_img = enc_video(sd, img, cfg)
+        feat_txt = bert_embeddings(sd, txt.flatten(0, 1))
+        vi = torch.arange(B).repeat_interleave(O_)
+        a, mt, ft = add_task_token(sd, cfg, ans.flatten(0, 1), mask.flatten(0, 1), feat_txt, task_name)
+        a = a.clone()
+        a[:, :n_pre] = -1
+        out = go_cross_masked(sd, torch.cat([feat_img[vi], ft], 1), torch.cat([mask_img[vi], mt], 1), cfg, decoder)
+        return mlm_head(sd, out[:, Lv:]), a.view(B, O_, -1)
+    # qamc / qaoe
+    txt, mask, ans = batch["txt"], batch["mask"], batch["mask_ans"]
+    feat_img, mask_img = enc_video(sd, img, cfg)
+    feat_txt = bert_embeddings(sd, txt)
+    a, mt, ft = add_task_token(sd, cfg, ans, mask, feat_txt, task_name)
+    a = a.clone()
+    a[:, :n_pre] = -1
+    out = go_cross_masked(sd, torch.cat([feat_img, ft], 1), torch.cat([mask_img, mt], 1), cfg, decoder)
+    return mlm_head(sd, out[:, Lv:]), a
+
+
+def make_multitask_batch(task, B, seed=0, X=25, O_=5, vocab=30522):
+    """Seeded synthetic batches with the keys the multi-task forwards read (main_multi_task_mlm.py:108-225,
+    model_for_captioning.py:61-70): padded captions / questions, a [MASK] answer slot for QA, duplicate video ids for
+    retrieval, BERT-style masked caption tokens for captioning."""
+    g = torch.Generator().manual_seed(7000 + seed)
+    img = torch.randn(B, 5, 3, 224, 224, generator=g)
+
+    def sent(n, X):
+        t = torch.randint(1000, min(30000, vocab), (n, X), generator=g)
+        m = torch.ones(n, X, dtype=torch.long)
+        t[:, 0] = 101
+        for r in range(n):
+            ln = int(torch.randint(X // 2, X, (1,), generator=g))   # [CLS] w.. [SEP] pad..
+            t[r, ln - 1] = 102
+            t[r, ln:] = 0
+            m[r, ln:] = 0
+        return t, m
+    if "captioning" in task:
+        txt, mask = sent(B, X)
+        ans = torch.full((B, X), -1, dtype=torch.long)
+        sel = (torch.rand(B, X, generator=g) < 0.3) & (mask == 1) & (txt != 101)
+        sel[:, 2] = True
+        ans[sel] = txt[sel]
+        txt[sel] = 103
+        return {"img": img, "txt": txt, "mask": mask, "ans_mtm": ans}
+    if "retrieval" in task:
+        txt, mask = sent(B, X)
+        txt[:, -1], mask[:, -1] = 103, 1            # appended [MASK] answer slot (Dataset_Retrieval_MLM)
+        vid = list(range(B))
+        if B > 2:
+            vid[-1] = vid[0]                        # two captions of the same video: both pairs are positives
+        return {"img": img, "txt": txt, "mask": mask, "vid": vid}
+    if "qamc" in task and "lsmdc-mc" in task:
+        txt, mask = sent(B * O_, X)
+        txt[:, -1], mask[:, -1] = 103, 1
+        ans = torch.full((B * O_, X), -1, dtype=torch.long)
+        gt = torch.randint(0, O_, (B,), generator=g)
+        for b in range(B):
+            for o in range(O_):
+                ans[b * O_ + o, -1] = 2995 if int(gt[b]) == o else 6270
+        return {"img": img, "txt": txt.view(B, O_, X), "mask": mask.view(B, O_, X), "mask_ans": ans.view(B, O_, X)}
+    txt, mask = sent(B, X)
+    txt[:, -1], mask[:, -1] = 103, 1
+    ans = torch.full((B, X), -1, dtype=torch.long)
+    ans[:, -1] = torch.randint(1000, 5000, (B,), generator=g)
+    return {"img": img, "txt": txt, "mask": mask, "mask_ans": ans}
+
+
 def mlm_head(sd, x, p="fc_mtm.predictions."):
     """HF BertOnlyMLMHead (main_pretrain_mlm.py:46-48,69,115); decoder.bias aliases predictions.bias."""
     t = gelu(linear(_qa(x), sd[p + "transform.dense.weight"], sd[p + "transform.dense.bias"]))

@@ -129,6 +129,66 @@ def run_case(name, size, layers, B, task_token=True, seed=0, vt_mask=False, odr=
     print(f"[{name}] wrote {len(gold)} arrays, {sz / 1e6:.2f} MB; loss mtm {ls_mtm.item():.5f} vtm {ls_vtm.item():.5f}")
 
 
+MT_TASKS = (("msrvtt-retrieval", "vtm", dict(B=3, X=25)), ("msvd-qaoe", "oe", dict(B=2, X=30)),
+            ("tgif-qamc", "mc", dict(B=2, X=40)), ("lsmdc-mc-qamc", "vtm", dict(B=2, X=25, O_=5)),
+            ("msrvtt-captioning", "cap", dict(B=2, X=20)))
+
+
+def run_multitask_case(name="mt_tiny_l2", size="tiny", layers=2, seed=11):
+    """BASELINE configs[4]: the five forward variants of the reference's own LAVENDER_Multi_Task
+    (main_multi_task_mlm.py:82-225, model_for_captioning.py:61-93) with the task-token prefix, eval mode, CE(ignore -1)
+    loss + backward; per task: sub-sampled logits, labels, loss, a few gradient norms."""
+    torch.manual_seed(0)
+    ref = ref_shims.build_reference_multitask(size, layers, 224, 4, True)
+    cfg = O.ModelCfg(swin=O.SWIN[size], bert_layers=layers, enable_task_token=True)
+    sd = O.make_state_dict(cfg, seed)
+    ref.load_state_dict(sd, strict=True)
+    ref.eval()
+    gold = {}
+    ce = torch.nn.CrossEntropyLoss(ignore_index=-1)
+    probe = ["emb_task", "trsfr.layer.1.attention.self.query.weight", "fc_mtm.predictions.decoder.weight",
+             "enc_img.swin.layers.2.blocks.3.attn.qkv.weight", "enc_txt.emb_txt.word_embeddings.weight"]
+    for ti, (task, tname, kw) in enumerate(MT_TASKS):
+        batch = O.make_multitask_batch(task, seed=seed + ti, **kw)
+        b = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()}
+        b.update(task=task, task_name=tname)
+        ref.zero_grad()
+        out = ref(b)
+        logits, ans = out["out"], out["ans"]
+        loss = ce(logits.flatten(0, logits.dim() - 2), ans.flatten())
+        loss.backward()
+        with torch.no_grad():
+            lo, an = O.multitask_forward(sd, batch, cfg, task, tname)
+        err = (lo - logits).abs().max().item()
+        assert err < 2e-4 and torch.equal(an, ans), (task, err)
+        print(f"[{name}/{task}] restatement vs reference logits {err:.2e}; logits {tuple(logits.shape)} loss {loss.item():.5f}")
+        gold[f"{task}/out_s"] = logits.detach()[..., ::VSTRIDE].numpy()
+        gold[f"{task}/ans"] = ans.numpy()
+        gold[f"{task}/loss"] = np.float64(loss.item())
+        named = dict(ref.named_parameters())
+        for n in probe:
+            g = named[n].grad
+            gold[f"{task}/gn/{n}"] = np.float64(0.0 if g is None else g.double().norm().item())
+    # the constructor-default is_decoder=True quirk: "full" masks become causal (one task is enough to pin it)
+    torch.manual_seed(0)
+    refd = ref_shims.build_reference_multitask(size, layers, 224, 4, True, is_decoder=True)
+    refd.load_state_dict(sd, strict=True)
+    refd.eval()
+    task, tname, kw = MT_TASKS[1]
+    batch = O.make_multitask_batch(task, seed=seed + 1, **kw)
+    b = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()}
+    b.update(task=task, task_name=tname)
+    with torch.no_grad():
+        outd = refd(b)
+        lo, an = O.multitask_forward(sd, batch, cfg, task, tname, decoder=True)
+    err = (lo - outd["out"]).abs().max().item()
+    assert err < 2e-4 and torch.equal(an, outd["ans"]), err
+    print(f"[{name}/{task} is_decoder=True] restatement vs reference logits {err:.2e}")
+    gold[f"{task}/decoder/out_s"] = outd["out"].detach()[..., ::VSTRIDE].numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **gold)
+    print(f"[{name}] wrote {len(gold)} arrays, {os.path.getsize(os.path.join(OUT, name + '.npz')) / 1e6:.2f} MB")
+
+
 def kat_cases():
     """Known-answer properties T1-T3 of SURVEY §4, evaluated with the reference's own functions and stored
     as small integer/float fixtures (window partition order, rel-pos index, shift mask)."""
@@ -167,6 +227,8 @@ if __name__ == "__main__":
     if not only or "tiny" in only:
         run_case("tiny_l2_b2", "tiny", 2, 2)
         run_case("tiny_l1_b3_notask", "tiny", 1, 3, task_token=False, seed=3)
+    if not only or "multitask" in only:
+        run_multitask_case()
     if not only or "base" in only:
         # the benchmarked architecture (BASELINE configs[1]: swin_base + 12-layer BERT-base: EncVideo.fc, 4-32 heads,
         # K = 128 GEMMs) at B = 2 / 2 VTM pairs per clip, with a video key mask on the last clip and an odr golden

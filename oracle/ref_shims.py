@@ -158,3 +158,64 @@ def build_reference_model(size="tiny", num_bert_layers=2, size_img=224, size_bat
 
     m.trsfr.forward = _enc_forward
     return m
+
+
+def install_multitask():
+    """Extra shims of SURVEY §8c-8 for main_multi_task_mlm.py: absent `evalcap`, the TSV writer helpers (their real
+    module drags in utils/qd_common.py), `dataset.TsvCompositeDataset`, and the alias for the reference's own broken
+    import (main_multi_task_mlm.py:13 asks for Dataset_QAOE_LSMDC_TSV, main_qaoe_mlm_lsmdc_fib.py:12 defines
+    Dataset_QAOE_MLM_LSMDC)."""
+    install(int(os.environ.get("LAV_NUM_BERT_LAYERS", "2")))
+    if "evalcap" not in sys.modules:
+        _stub("evalcap")
+        _stub("evalcap.utils_caption_evaluate", evaluate_on_coco_caption=lambda *a, **k: {})
+        _stub("utils.tsv_file_ops", tsv_writer=lambda *a, **k: None, reorder_tsv_keys=lambda *a, **k: None)
+        sys.modules["dataset"].TsvCompositeDataset = object
+    cwd = os.getcwd()
+    os.chdir(REF_ROOT)
+    try:
+        import main_qaoe_mlm_lsmdc_fib as fib
+        if not hasattr(fib, "Dataset_QAOE_LSMDC_TSV"):
+            fib.Dataset_QAOE_LSMDC_TSV = fib.Dataset_QAOE_MLM_LSMDC
+        import main_multi_task_mlm  # noqa: F401
+    finally:
+        os.chdir(cwd)
+
+
+def build_reference_multitask(size="tiny", num_bert_layers=2, size_img=224, size_batch=2, enable_task_token=True,
+                              is_decoder=False):
+    """The reference's own LAVENDER_Multi_Task (main_multi_task_mlm.py:77-225), random init, constructed as the script
+    does (main_multi_task_mlm.py:502-504: is_decoder = getattr(args, 'is_decoder', False) -> False; the constructor's own
+    default True would make HF's get_extended_attention_mask turn every 2-D "full" mask into a CAUSAL one)."""
+    install(num_bert_layers)
+    os.environ["LAV_NUM_BERT_LAYERS"] = str(num_bert_layers)
+    install_multitask()
+    cwd = os.getcwd()
+    os.chdir(REF_ROOT)
+    try:
+        import main_multi_task_mlm as mt
+        import visbackbone.video_swin as vs
+        import model as ref_model
+        window = (8, 12, 12) if size_img == 384 else (8, 7, 7)
+
+        def get_vidswin_model(args):
+            m = vs.SwinTransformer3D(pretrained=None, patch_size=(2, 4, 4), window_size=window,
+                                     drop_path_rate=0.2, patch_norm=True, **SWIN_SIZES[args.vis_backbone_size])
+            m.init_weights()
+            return m
+
+        ref_model.get_vidswin_model = get_vidswin_model
+        args = default_args(size, size_img, size_batch, enable_task_token)
+        m = mt.LAVENDER_Multi_Task(args, FakeTokenizer(), is_decoder=is_decoder)
+    finally:
+        os.chdir(cwd)
+    _ext = m.mask_ext
+    m.mask_ext = lambda mask, shape, device=None: _ext(mask, shape)
+    _fw = m.trsfr.forward
+
+    def _enc_forward(feat, mask, output_attentions=False, **kw):
+        o = _fw(feat, mask, **kw)
+        return {"last_hidden_state": o[0] if isinstance(o, tuple) else o.last_hidden_state, "attentions": None}
+
+    m.trsfr.forward = _enc_forward
+    return m

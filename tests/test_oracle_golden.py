@@ -99,3 +99,29 @@ def test_enc_video_odr_vt_mask_golden():
         f, m = O.enc_video(sd, batch["img"], cfg, odr=odr, vt_mask=torch.from_numpy(gold["vt_mask"]))
     assert np.abs(f[:, ::5, ::3].numpy() - gold["feat_img_odr_s"]).max() < 2e-4
     assert np.array_equal(m.numpy(), gold["mask_img_odr"])
+
+
+MT_TASKS = (("msrvtt-retrieval", "vtm", dict(B=3, X=25)), ("msvd-qaoe", "oe", dict(B=2, X=30)),
+            ("tgif-qamc", "mc", dict(B=2, X=40)), ("lsmdc-mc-qamc", "vtm", dict(B=2, X=25, O_=5)),
+            ("msrvtt-captioning", "cap", dict(B=2, X=20)))
+
+
+def test_oracle_multitask_forwards_reproduce_reference():
+    """BASELINE configs[4]: the five LAVENDER_Multi_Task forward variants (retrieval B^2, QA-OE, QA-MC, QA-MC as
+    retrieval, seq2seq captioning) against outputs of the unmodified reference (oracle/make_golden.py multitask)."""
+    gold = np.load(os.path.join(GOLD, "mt_tiny_l2.npz"))
+    cfg = O.ModelCfg(swin=O.SWIN["tiny"], bert_layers=2, enable_task_token=True)
+    sd = O.make_state_dict(cfg, 11)
+    ce = torch.nn.CrossEntropyLoss(ignore_index=-1)
+    for ti, (task, tname, kw) in enumerate(MT_TASKS):
+        batch = O.make_multitask_batch(task, seed=11 + ti, **kw)
+        with torch.no_grad():
+            lo, an = O.multitask_forward(sd, batch, cfg, task, tname)
+        assert np.array_equal(an.numpy(), gold[f"{task}/ans"]), task
+        assert np.abs(lo[..., ::61].numpy() - gold[f"{task}/out_s"]).max() < 2e-4, task
+        loss = ce(lo.flatten(0, lo.dim() - 2), an.flatten())
+        assert abs(loss.item() - float(gold[f"{task}/loss"])) < 1e-4, task
+    batch = O.make_multitask_batch("msvd-qaoe", seed=12, B=2, X=30)
+    with torch.no_grad():
+        lo, _ = O.multitask_forward(sd, batch, cfg, "msvd-qaoe", "oe", decoder=True)
+    assert np.abs(lo[..., ::61].numpy() - gold["msvd-qaoe/decoder/out_s"]).max() < 2e-4
