@@ -177,167 +177,6 @@ __device__ __forceinline__ void store_aux_phase(const GemmParams& p, const float
   }
 }
 
-// Body of the 8 epilogue warps (two warpgroups, one per TMEM accumulator stage), specialised at compile time on the
-// activation, on whether a global input is prefetched (PRE: residual rows) and on the store mode: the epilogue is
-// instruction-issue bound for the short-K GEMMs of the Swin stages, so unused paths must not cost instructions.
-template <int BN, int NCTA, int ACT, int PRE, int STORE, bool DROP = false>
-__device__ __forceinline__ void epilogue_warps(const GemmParams& p, float* epi_stage, uint64_t* tmem_full,
-                                               uint64_t* tmem_empty, uint32_t tmem_base, int warp, int lane, int total,
-                                               int stream_id, int nstreams, int rank) {
-  const int wg = (warp - 4) >> 2;
-  const int q = warp & 3;  // TMEM lane quarter this warp may access
-  float* stg = epi_stage + (warp - 4) * (kEpiWarpBytes / 4);
-  const int rr = lane >> 3, cg = lane & 7;  // this lane's row-within-group / 4-column group in the store phase
-  const LavGemmEpilogue& e = p.epi;
-  constexpr bool use_res = PRE == 1;
-  constexpr bool use_auxin = ACT == LAV_ACT_GELU_BWD;
-  constexpr bool use_pre = use_res || use_auxin;
-  DropKey dkey{};
-  if (DROP) dkey = drop_key(p.drop);
-  int iter = 0;
-  for (int item = stream_id; item < total; item += nstreams, ++iter) {
-    const int as = iter & 1;  // accumulator stage; BOTH warpgroups drain every tile (even / odd 32-column chunks)
-    const TileCoord t = decode_tile(p, item);
-    const int row_base = (t.m_blk * NCTA + rank) * BM + q * 32;
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
-    const int nchunks = min(BN / 32, (p.N - t.n_blk * BN + 31) / 32);
-    // output rows of this lane's 8 store-phase rows (row map resolved once per tile)
-    int orow[8];
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int row = row_base + it * 4 + rr;
-      orow[it] = row < p.M ? (e.row_map ? __ldg(e.row_map + row) : row) : -1;
-    }
-    // Prefetch of the chunk's global INPUT (residual rows, or the GELU pre-activation for GELU_BWD) into registers,
-    // one chunk ahead: chunk 0 is requested before the accumulator is ready, so the latency hides under the MMAs.
-    auto prefetch = [&](uint4(&dst)[8], int c) {
-      const int col = t.n_blk * BN + c * 32 + 4 * cg;
-      const int nv = p.N - col;
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        dst[it] = make_uint4(0u, 0u, 0u, 0u);
-        if (orow[it] < 0 || nv <= 0) continue;
-        if (use_res) {
-          const float* rs = e.residual + (size_t)orow[it] * e.ldres + col;
-          if (nv >= 4 && (e.ldres & 3) == 0) dst[it] = *reinterpret_cast<const uint4*>(rs);
-          else {
-            dst[it].x = __float_as_uint(rs[0]);
-            if (nv > 1) dst[it].y = __float_as_uint(rs[1]);
-            if (nv > 2) dst[it].z = __float_as_uint(rs[2]);
-            if (nv > 3) dst[it].w = __float_as_uint(rs[3]);
-          }
-        } else if (use_auxin) {
-          const __half* x = reinterpret_cast<const __half*>(e.aux) + (size_t)(row_base + it * 4 + rr) * e.ldaux + col;
-          if (nv >= 4 && (e.ldaux & 3) == 0) {
-            const uint2 u = *reinterpret_cast<const uint2*>(x);
-            dst[it].x = u.x, dst[it].y = u.y;
-          } else {
-            const __half z = __float2half_rn(0.f);
-            __half2 h0 = __halves2half2(x[0], nv > 1 ? x[1] : z), h1 = __halves2half2(nv > 2 ? x[2] : z, nv > 3 ? x[3] : z);
-            dst[it].x = *reinterpret_cast<uint32_t*>(&h0), dst[it].y = *reinterpret_cast<uint32_t*>(&h1);
-          }
-        }
-      }
-    };
-    uint4 cur[8], nxt[8];
-    if (use_pre && wg < nchunks) prefetch(cur, wg);
-    mbar_wait(tmem_full + as, (iter >> 1) & 1, 4);
-    tc_fence_after();
-    if (GemmCfg<BN, NCTA>::BIAS_COLS > 0 && p.bias_grad != nullptr && t.n_blk == 0 && wg == 0) {
-      // column 0 of the 128 x 16 side accumulator = row sums of A over this tile's k range
-      uint32_t bsum;
-      tmem_ld_32x1(tmem_base + ((uint32_t)(q * 32) << 16) + 2 * BN + as * 16, bsum);
-      tmem_ld_wait();
-      const int brow = row_base + lane;
-      if (brow < p.M) atomicAdd(p.bias_grad + brow, __uint_as_float(bsum) * e.alpha);
-    }
-    if ((p.debug & 1) || wg >= nchunks) {  // (a warpgroup without a chunk of a narrow tile just releases the stage)
-      tc_fence_before();
-      if (NCTA == 2) mbar_arrive_cluster(tmem_empty + as, 0);
-      else mbar_arrive(tmem_empty + as);
-      continue;
-    }
-#pragma unroll 1
-    for (int c = wg; c < nchunks; c += 2) {
-      const int col0 = t.n_blk * BN + c * 32;
-      const int col = col0 + 4 * cg;  // this lane's columns in the transposed (store) phases
-      uint32_t acc[32];
-      tmem_ld_32x32(taddr + c * 32, acc);
-      if (use_pre && c + 2 < nchunks) prefetch(nxt, c + 2);
-      tmem_ld_wait();
-      if (c + 2 >= nchunks) {  // accumulator fully read: hand the TMEM stage back to the MMA warp early
-        tc_fence_before();
-        if (NCTA == 2) mbar_arrive_cluster(tmem_empty + as, 0);  // the leader's MMA warp waits for both CTAs
-        else mbar_arrive(tmem_empty + as);
-      }
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * e.alpha;
-      if (e.bias) {
-        if (col0 + 32 <= p.N) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col0) + j);
-            v[4 * j] += b.x, v[4 * j + 1] += b.y, v[4 * j + 2] += b.z, v[4 * j + 3] += b.w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N) v[j] += __ldg(e.bias + col0 + j);
-        }
-      }
-      if (ACT == LAV_ACT_GELU) {
-        if (e.aux) {
-          stage_rows(stg, lane, v);
-          __syncwarp();
-          store_aux_phase(p, stg, row_base, col, rr, cg);
-          __syncwarp();
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-      } else if (use_auxin) {
-        // pre-activation: (store-layout registers) -> smem -> (row-layout registers)
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&cur[it].x));
-          const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&cur[it].y));
-          *reinterpret_cast<float4*>(stg + (it * 4 + rr) * kEpiStride + 4 * cg) = make_float4(f0.x, f0.y, f1.x, f1.y);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 x = *reinterpret_cast<const float4*>(stg + lane * kEpiStride + 4 * j);
-          v[4 * j] *= gelu_erf_grad(x.x), v[4 * j + 1] *= gelu_erf_grad(x.y);
-          v[4 * j + 2] *= gelu_erf_grad(x.z), v[4 * j + 3] *= gelu_erf_grad(x.w);
-        }
-        __syncwarp();
-      }
-      if (DROP) {  // BertSelfOutput / BertOutput .dropout on (dense + bias), element index (GEMM row, column)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t m = drop_keep8(dkey, p.drop.thresh, (uint32_t)(row_base + lane), (uint32_t)((col0 >> 3) + j), 0u);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) v[8 * j + q] = ((m >> q) & 1u) ? v[8 * j + q] * p.drop.inv_keep : 0.f;
-        }
-      }
-      if (e.row_scale) {
-        const int row = min(row_base + lane, p.M - 1);
-        const float sc = __ldg(e.row_scale + row / e.rows_per_scale);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] *= sc;
-      }
-      stage_rows(stg, lane, v);
-      __syncwarp();
-      store_phase<STORE>(p, stg, orow, cur, use_res, col, rr, cg);
-      __syncwarp();
-      if (use_pre) {
-#pragma unroll
-        for (int it = 0; it < 8; ++it) cur[it] = nxt[it];
-      }
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // TMA-store epilogue for the plain outputs (fp16 activations of qkv / fc1 / dgrad GEMMs, fp32 logits): the thread
 // that owns accumulator row r packs 32 columns into its row of a swizzled shared-memory tile and ONE lane hands the
@@ -375,20 +214,31 @@ __device__ __forceinline__ void stage_and_store(const CUtensorMap* tm, uint8_t* 
   ++nb;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// The two epilogues (TMA-store path for plain outputs, register path for scatter / residual / accumulation), both
+// software-pipelined.  profiles/r1d_gemm_sweep.md: for K <= 1024 the kernels are bound by the accumulator drain, and in
+// round 1 a warp spent ~2000 clk per 32 x 32 chunk in a serial chain  tcgen05.ld -> wait -> bias (8 broadcast LDG at L2
+// latency: the L1 is carved down to nothing by the 227 KB of shared memory) -> math -> stores.  Here the tcgen05.ld (and
+// the GELU' input) of the warp's NEXT chunk is issued before the math of the current one, so its latency hides under
+// math + stores; the TMEM stage is released one chunk earlier; the bias arrives as ONE coalesced load per lane per
+// chunk, issued before the accumulator is even ready, and is broadcast with shuffles; the epilogue warpgroups take the
+// registers the producer / MMA warps do not need (setmaxnreg), so two accumulator chunks fit without spills.
+// ---------------------------------------------------------------------------------------------------------
 template <int BN, int NCTA, int ACT, bool F32>
-__device__ __forceinline__ void epilogue_warps_tma(const GemmParams& p, const CUtensorMap* tmOut, const CUtensorMap* tmAux,
-                                                   float* epi_stage, uint64_t* tmem_full, uint64_t* tmem_empty,
-                                                   uint32_t tmem_base, int warp, int lane, int total, int stream_id,
-                                                   int nstreams, int rank) {
+__device__ __forceinline__ void epilogue_warps_tma2(const GemmParams& p, const CUtensorMap* tmOut, const CUtensorMap* tmAux,
+                                                    float* epi_stage, uint64_t* tmem_full, uint64_t* tmem_empty,
+                                                    uint32_t tmem_base, int warp, int lane, int total, int stream_id,
+                                                    int nstreams, int rank) {
   const int wg = (warp - 4) >> 2;
   const int q = warp & 3;
   uint8_t* buf = reinterpret_cast<uint8_t*>(epi_stage) + (warp - 4) * kEpiWarpBytes;
   const LavGemmEpilogue& e = p.epi;
   const bool aux_out = ACT == LAV_ACT_GELU && e.aux != nullptr;
+  constexpr int KMAX = (BN / 32 + 1) / 2;  // chunks one warpgroup drains per tile
   uint32_t nb = 0;
   int iter = 0;
   for (int item = stream_id; item < total; item += nstreams, ++iter) {
-    const int as = iter & 1;  // accumulator stage; BOTH warpgroups drain every tile (even / odd 32-column chunks)
+    const int as = iter & 1;
     const TileCoord t = decode_tile(p, item);
     const int row_base = (t.m_blk * NCTA + rank) * BM + q * 32;
     const bool rows_valid = row_base < p.M;
@@ -396,6 +246,25 @@ __device__ __forceinline__ void epilogue_warps_tma(const GemmParams& p, const CU
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
     const int n0 = t.n_blk * BN;
     const int nchunks = min(BN / 32, (p.N - n0 + 31) / 32);
+    // bias of this warp's chunks: lane j holds column (chunk, j); requested while the MMAs of the tile still run
+    float bl[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int col = n0 + (wg + 2 * k) * 32 + lane;
+      bl[k] = (e.bias && wg + 2 * k < nchunks && col < p.N) ? __ldg(e.bias + col) : 0.f;
+    }
+    auto load_aux = [&](uint4(&ax)[4], int c) {
+      const int col0 = n0 + c * 32;
+      const __half* xa = reinterpret_cast<const __half*>(e.aux) + (size_t)min(row, p.M - 1) * e.ldaux + col0;
+      if (col0 + 32 <= p.N && (e.ldaux & 7) == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ax[j] = __ldg(reinterpret_cast<const uint4*>(xa) + j);
+      } else {
+        __half* h = reinterpret_cast<__half*>(ax);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) h[j] = col0 + j < p.N ? xa[j] : __float2half_rn(0.f);
+      }
+    };
     mbar_wait(tmem_full + as, (iter >> 1) & 1, 4);
     tc_fence_after();
     if ((p.debug & 1) || wg >= nchunks) {  // (a warpgroup without a chunk of a narrow tile just releases the stage)
@@ -404,32 +273,17 @@ __device__ __forceinline__ void epilogue_warps_tma(const GemmParams& p, const CU
       else mbar_arrive(tmem_empty + as);
       continue;
     }
-#pragma unroll 1
-    for (int c = wg; c < nchunks; c += 2) {
+    uint32_t accA[32], accB[32];
+    uint4 axA[4], axB[4];
+    tmem_ld_32x32(taddr + wg * 32, accA);
+    if (ACT == LAV_ACT_GELU_BWD) load_aux(axA, wg);
+    auto step = [&](uint32_t(&cur)[32], uint4(&axc)[4], uint32_t(&nxt)[32], uint4(&axn)[4], int c, float bias_lane) {
       const int col0 = n0 + c * 32;
-      const bool full = col0 + 32 <= p.N;
-      uint32_t acc[32];
-      tmem_ld_32x32(taddr + c * 32, acc);
-      // global inputs of this chunk are requested while the TMEM load is in flight
-      float4 bv[8];
-      if (e.bias && full) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) bv[j] = __ldg(reinterpret_cast<const float4*>(e.bias + col0) + j);
-      }
-      uint4 ax[4];
-      if (ACT == LAV_ACT_GELU_BWD) {
-        const __half* xa = reinterpret_cast<const __half*>(e.aux) + (size_t)min(row, p.M - 1) * e.ldaux + col0;
-        if (full && (e.ldaux & 7) == 0) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) ax[j] = __ldg(reinterpret_cast<const uint4*>(xa) + j);
-        } else {
-          __half* h = reinterpret_cast<__half*>(ax);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) h[j] = col0 + j < p.N ? xa[j] : __float2half_rn(0.f);
-        }
-      }
       tmem_ld_wait();
-      if (c + 2 >= nchunks) {  // this warpgroup's last chunk is read: hand its share of the TMEM stage back early
+      if (c + 2 < nchunks) {  // next chunk's accumulator (and GELU' input) in flight under this chunk's math + stores
+        tmem_ld_32x32(taddr + (c + 2) * 32, nxt);
+        if (ACT == LAV_ACT_GELU_BWD) load_aux(axn, c + 2);
+      } else {                // the whole accumulator has been read: hand the TMEM stage back to the MMA warp
         tc_fence_before();
         if (NCTA == 2) mbar_arrive_cluster(tmem_empty + as, 0);
         else mbar_arrive(tmem_empty + as);
@@ -437,28 +291,21 @@ __device__ __forceinline__ void epilogue_warps_tma(const GemmParams& p, const CU
       float v[32];
       if (e.alpha != 1.0f) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * e.alpha;
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(cur[j]) * e.alpha;
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(cur[j]);
       }
       if (e.bias) {
-        if (full) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            v[4 * j] += bv[j].x, v[4 * j + 1] += bv[j].y, v[4 * j + 2] += bv[j].z, v[4 * j + 3] += bv[j].w;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N) v[j] += __ldg(e.bias + col0 + j);
-        }
+        for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bias_lane, j);
       }
       if (ACT == LAV_ACT_GELU) {
         if (aux_out) stage_and_store<false>(tmAux, buf, nb, lane, v, col0, row_base, rows_valid);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
       } else if (ACT == LAV_ACT_GELU_BWD) {
-        const __half2* h2 = reinterpret_cast<const __half2*>(ax);
+        const __half2* h2 = reinterpret_cast<const __half2*>(axc);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float2 x = __half22float2(h2[j]);
@@ -466,9 +313,174 @@ __device__ __forceinline__ void epilogue_warps_tma(const GemmParams& p, const CU
         }
       }
       stage_and_store<F32>(tmOut, buf, nb, lane, v, col0, row_base, rows_valid);
+    };
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int c = wg + 2 * k;
+      if (c >= nchunks) break;
+      if (k & 1) step(accB, axB, accA, axA, c, bl[k]);
+      else step(accA, axA, accB, axB, c, bl[k]);
     }
   }
   if (lane == 0) tma_store_wait_all();  // smem must outlive the reads; the writes complete before the grid does
+}
+
+// register-path epilogue (row map / residual / DropPath / dropout / accumulation), software-pipelined like the above
+template <int BN, int NCTA, int ACT, int PRE, int STORE, bool DROP = false>
+__device__ __forceinline__ void epilogue_warps2(const GemmParams& p, float* epi_stage, uint64_t* tmem_full,
+                                                uint64_t* tmem_empty, uint32_t tmem_base, int warp, int lane, int total,
+                                                int stream_id, int nstreams, int rank) {
+  const int wg = (warp - 4) >> 2;
+  const int q = warp & 3;
+  float* stg = epi_stage + (warp - 4) * (kEpiWarpBytes / 4);
+  const int rr = lane >> 3, cg = lane & 7;
+  const LavGemmEpilogue& e = p.epi;
+  constexpr bool use_res = PRE == 1;
+  constexpr bool use_auxin = ACT == LAV_ACT_GELU_BWD;
+  constexpr bool use_pre = use_res || use_auxin;
+  constexpr int KMAX = (BN / 32 + 1) / 2;
+  DropKey dkey{};
+  if (DROP) dkey = drop_key(p.drop);
+  int iter = 0;
+  for (int item = stream_id; item < total; item += nstreams, ++iter) {
+    const int as = iter & 1;
+    const TileCoord t = decode_tile(p, item);
+    const int row_base = (t.m_blk * NCTA + rank) * BM + q * 32;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+    const int n0 = t.n_blk * BN;
+    const int nchunks = min(BN / 32, (p.N - n0 + 31) / 32);
+    int orow[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = row_base + it * 4 + rr;
+      orow[it] = row < p.M ? (e.row_map ? __ldg(e.row_map + row) : row) : -1;
+    }
+    float bl[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int col = n0 + (wg + 2 * k) * 32 + lane;
+      bl[k] = (e.bias && wg + 2 * k < nchunks && col < p.N) ? __ldg(e.bias + col) : 0.f;
+    }
+    float rsc = 1.0f;
+    if (e.row_scale) rsc = __ldg(e.row_scale + min(row_base + lane, p.M - 1) / e.rows_per_scale);
+    // global INPUT of a chunk (residual rows in the store layout, or the GELU pre-activation), requested at the top of the
+    // chunk's step: its latency hides under the chunk's own math and staging
+    auto prefetch = [&](uint4(&dst)[8], int c) {
+      const int col = n0 + c * 32 + 4 * cg;
+      const int nv = p.N - col;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        dst[it] = make_uint4(0u, 0u, 0u, 0u);
+        if (orow[it] < 0 || nv <= 0) continue;
+        if (use_res) {
+          const float* rs = e.residual + (size_t)orow[it] * e.ldres + col;
+          if (nv >= 4 && (e.ldres & 3) == 0) dst[it] = *reinterpret_cast<const uint4*>(rs);
+          else {
+            dst[it].x = __float_as_uint(rs[0]);
+            if (nv > 1) dst[it].y = __float_as_uint(rs[1]);
+            if (nv > 2) dst[it].z = __float_as_uint(rs[2]);
+            if (nv > 3) dst[it].w = __float_as_uint(rs[3]);
+          }
+        } else if (use_auxin) {
+          const __half* x = reinterpret_cast<const __half*>(e.aux) + (size_t)(row_base + it * 4 + rr) * e.ldaux + col;
+          if (nv >= 4 && (e.ldaux & 3) == 0) {
+            const uint2 u = *reinterpret_cast<const uint2*>(x);
+            dst[it].x = u.x, dst[it].y = u.y;
+          } else {
+            const __half z = __float2half_rn(0.f);
+            __half2 h0 = __halves2half2(x[0], nv > 1 ? x[1] : z), h1 = __halves2half2(nv > 2 ? x[2] : z, nv > 3 ? x[3] : z);
+            dst[it].x = *reinterpret_cast<uint32_t*>(&h0), dst[it].y = *reinterpret_cast<uint32_t*>(&h1);
+          }
+        }
+      }
+    };
+    mbar_wait(tmem_full + as, (iter >> 1) & 1, 4);
+    tc_fence_after();
+    if (GemmCfg<BN, NCTA>::BIAS_COLS > 0 && p.bias_grad != nullptr && t.n_blk == 0 && wg == 0) {
+      uint32_t bsum;
+      tmem_ld_32x1(tmem_base + ((uint32_t)(q * 32) << 16) + 2 * BN + as * 16, bsum);
+      tmem_ld_wait();
+      const int brow = row_base + lane;
+      if (brow < p.M) atomicAdd(p.bias_grad + brow, __uint_as_float(bsum) * e.alpha);
+    }
+    if ((p.debug & 1) || wg >= nchunks) {
+      tc_fence_before();
+      if (NCTA == 2) mbar_arrive_cluster(tmem_empty + as, 0);
+      else mbar_arrive(tmem_empty + as);
+      continue;
+    }
+    uint32_t accA[32], accB[32];
+    tmem_ld_32x32(taddr + wg * 32, accA);
+    auto step = [&](uint32_t(&cur)[32], uint32_t(&nxt)[32], int c, float bias_lane) {
+      const int col0 = n0 + c * 32;
+      const int col = col0 + 4 * cg;
+      uint4 pre[8];
+      if (use_pre) prefetch(pre, c);
+      tmem_ld_wait();
+      if (c + 2 < nchunks) {
+        tmem_ld_32x32(taddr + (c + 2) * 32, nxt);
+      } else {
+        tc_fence_before();
+        if (NCTA == 2) mbar_arrive_cluster(tmem_empty + as, 0);
+        else mbar_arrive(tmem_empty + as);
+      }
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(cur[j]) * e.alpha;
+      if (e.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bias_lane, j);
+      }
+      if (ACT == LAV_ACT_GELU) {
+        if (e.aux) {
+          stage_rows(stg, lane, v);
+          __syncwarp();
+          store_aux_phase(p, stg, row_base, col, rr, cg);
+          __syncwarp();
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+      } else if (use_auxin) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&pre[it].x));
+          const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&pre[it].y));
+          *reinterpret_cast<float4*>(stg + (it * 4 + rr) * kEpiStride + 4 * cg) = make_float4(f0.x, f0.y, f1.x, f1.y);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 x = *reinterpret_cast<const float4*>(stg + lane * kEpiStride + 4 * j);
+          v[4 * j] *= gelu_erf_grad(x.x), v[4 * j + 1] *= gelu_erf_grad(x.y);
+          v[4 * j + 2] *= gelu_erf_grad(x.z), v[4 * j + 3] *= gelu_erf_grad(x.w);
+        }
+        __syncwarp();
+      }
+      if (DROP) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t m = drop_keep8(dkey, p.drop.thresh, (uint32_t)(row_base + lane), (uint32_t)((col0 >> 3) + j), 0u);
+#pragma unroll
+          for (int qq = 0; qq < 8; ++qq) v[8 * j + qq] = ((m >> qq) & 1u) ? v[8 * j + qq] * p.drop.inv_keep : 0.f;
+        }
+      }
+      if (e.row_scale) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= rsc;
+      }
+      stage_rows(stg, lane, v);
+      __syncwarp();
+      store_phase<STORE>(p, stg, orow, pre, use_res, col, rr, cg);
+      __syncwarp();
+    };
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int c = wg + 2 * k;
+      if (c >= nchunks) break;
+      if (k & 1) step(accB, accA, c, bl[k]);
+      else step(accA, accB, c, bl[k]);
+    }
+  }
 }
 
 template <int BN, int AMAJ, int BMAJ, int NCTA>
@@ -525,6 +537,10 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Register re-partition (168 per thread at launch: 384 threads x 168 = 63 K of the 64 K registers): warps 0-3 (TMA
+  // producer, MMA issuer, allocator: a few dozen live values) hand theirs to the two epilogue warpgroups, which hold two
+  // in-flight 32-column accumulator chunks + prefetched epilogue inputs.  128 x 72 + 256 x 216 = 64 512 registers.
+  // (issued at the top of the two role branches below: after a join ptxas would assume the smaller budget for everyone)
   // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) touches no global data and
   // may overlap the tail of the previous kernel; from here on operands / outputs of earlier kernels are accessed.
   griddep_launch();
@@ -532,6 +548,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   const int total = p.m_blocks * p.n_blocks * p.splits;
 
+  if (warp < 4) {
+  // (setmaxnreg re-partitioning made ptxas spill kilobytes in the epilogue branch on this toolchain: not used)
   if (warp == 0) {
     // ------------------------------------------------ TMA producer (one lane; in a pair, both CTAs run one)
     if (lane == 0) {
@@ -619,42 +637,57 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
     }
-  } else if (warp >= 4) {
-    // ------------------------------------------------ epilogue: warpgroup g drains accumulator stage g
+  }
+  } else {
+    // ------------------------------------------------ epilogue: both warpgroups drain every accumulator stage
     const LavGemmEpilogue& e = p.epi;
     const int st = e.out_dtype == LAV_OUT_F16 ? ST_F16
                    : e.accumulate != LAV_ACCUMULATE ? ST_F32 : (p.splits > 1 ? ST_F32_RED : ST_F32_RMW);
     const int pre = e.residual != nullptr ? 1 : 0;
-#define LAV_EPI(A, P, S)                                                                                       \
-  epilogue_warps<BN, NCTA, A, P, S>(p, epi_stage, tmem_full, tmem_empty, tmem_base, warp, lane, total, stream_id, \
-                                    nstreams, rank)
-#define LAV_EPI_TMA(A, F)                                                                                        \
-  epilogue_warps_tma<BN, NCTA, A, F>(p, &tmOut, &tmAux, epi_stage, tmem_full, tmem_empty, tmem_base, warp, lane, total, \
-                                     stream_id, nstreams, rank)
-    if (p.tma_store) {
-      if (e.act == LAV_ACT_GELU) LAV_EPI_TMA(LAV_ACT_GELU, false);
-      else if (e.act == LAV_ACT_GELU_BWD) LAV_EPI_TMA(LAV_ACT_GELU_BWD, false);
-      else if (st == ST_F16) LAV_EPI_TMA(LAV_ACT_NONE, false);
-      else LAV_EPI_TMA(LAV_ACT_NONE, true);
-    } else if (e.act == LAV_ACT_GELU) {
-      if (st == ST_F16 && !pre) LAV_EPI(LAV_ACT_GELU, 0, ST_F16);
-      else LAV_EPI(LAV_ACT_GELU, 0, ST_F32);               // host restricts GELU to {f16, f32 store} without residual
-    } else if (e.act == LAV_ACT_GELU_BWD) {
-      if (st == ST_F16) LAV_EPI(LAV_ACT_GELU_BWD, 0, ST_F16);
-      else LAV_EPI(LAV_ACT_GELU_BWD, 0, ST_F32);
-    } else if (!pre) {
-      if (st == ST_F16) LAV_EPI(LAV_ACT_NONE, 0, ST_F16);
-      else if (st == ST_F32) LAV_EPI(LAV_ACT_NONE, 0, ST_F32);
-      else if (st == ST_F32_RED) LAV_EPI(LAV_ACT_NONE, 0, ST_F32_RED);
-      else LAV_EPI(LAV_ACT_NONE, 0, ST_F32_RMW);
-    } else if (p.drop.on) {  // host restricts dropout to (no activation, residual, fp32 store)
-      epilogue_warps<BN, NCTA, LAV_ACT_NONE, 1, ST_F32, true>(p, epi_stage, tmem_full, tmem_empty, tmem_base, warp, lane,
-                                                              total, stream_id, nstreams, rank);
+#define LAV_EPI(A, P, S)                                                                                          \
+  epilogue_warps2<BN, NCTA, A, P, S>(p, epi_stage, tmem_full, tmem_empty, tmem_base, warp, lane, total, stream_id,   \
+                                     nstreams, rank)
+#define LAV_EPI_TMA(A, F)                                                                                          \
+  epilogue_warps_tma2<BN, NCTA, A, F>(p, &tmOut, &tmAux, epi_stage, tmem_full, tmem_empty, tmem_base, warp, lane,  \
+                                      total, stream_id, nstreams, rank)
+    // Only the (operand layout, epilogue) combinations the hot path uses are instantiated (epilogue_supported() on the
+    // host rejects the others): forward (K,K): bias / GELU / residual / scatter / dropout; dgrad (K,MN): plain, GELU',
+    // residual; wgrad (MN,MN): fp32 store / accumulate.
+    if constexpr (AMAJ == LAV_MAJOR_MN) {
+      if (st == ST_F32_RED) LAV_EPI(LAV_ACT_NONE, 0, ST_F32_RED);
+      else if (st == ST_F32_RMW) LAV_EPI(LAV_ACT_NONE, 0, ST_F32_RMW);
+      else LAV_EPI(LAV_ACT_NONE, 0, ST_F32);
+    } else if constexpr (BMAJ == LAV_MAJOR_MN) {
+      if (p.tma_store) {
+        if (e.act == LAV_ACT_GELU_BWD) LAV_EPI_TMA(LAV_ACT_GELU_BWD, false);
+        else if (st == ST_F16) LAV_EPI_TMA(LAV_ACT_NONE, false);
+        else LAV_EPI_TMA(LAV_ACT_NONE, true);
+      } else if (e.act == LAV_ACT_GELU_BWD) {
+        if (st == ST_F16) LAV_EPI(LAV_ACT_GELU_BWD, 0, ST_F16);
+        else LAV_EPI(LAV_ACT_GELU_BWD, 0, ST_F32);
+      } else if (!pre) {
+        if (st == ST_F16) LAV_EPI(LAV_ACT_NONE, 0, ST_F16);
+        else LAV_EPI(LAV_ACT_NONE, 0, ST_F32);
+      } else {
+        LAV_EPI(LAV_ACT_NONE, 1, ST_F32);
+      }
     } else {
-      if (st == ST_F16) LAV_EPI(LAV_ACT_NONE, 1, ST_F16);
-      else if (st == ST_F32) LAV_EPI(LAV_ACT_NONE, 1, ST_F32);
-      else if (st == ST_F32_RED) LAV_EPI(LAV_ACT_NONE, 1, ST_F32_RED);
-      else LAV_EPI(LAV_ACT_NONE, 1, ST_F32_RMW);
+      if (p.tma_store) {
+        if (e.act == LAV_ACT_GELU) LAV_EPI_TMA(LAV_ACT_GELU, false);
+        else if (st == ST_F16) LAV_EPI_TMA(LAV_ACT_NONE, false);
+        else LAV_EPI_TMA(LAV_ACT_NONE, true);
+      } else if (e.act == LAV_ACT_GELU) {
+        if (st == ST_F16) LAV_EPI(LAV_ACT_GELU, 0, ST_F16);
+        else LAV_EPI(LAV_ACT_GELU, 0, ST_F32);
+      } else if (!pre) {
+        if (st == ST_F16) LAV_EPI(LAV_ACT_NONE, 0, ST_F16);
+        else LAV_EPI(LAV_ACT_NONE, 0, ST_F32);
+      } else if (p.drop.on) {  // host restricts dropout to (no activation, residual, fp32 store)
+        epilogue_warps2<BN, NCTA, LAV_ACT_NONE, 1, ST_F32, true>(p, epi_stage, tmem_full, tmem_empty, tmem_base, warp, lane,
+                                                                 total, stream_id, nstreams, rank);
+      } else {
+        LAV_EPI(LAV_ACT_NONE, 1, ST_F32);
+      }
     }
 #undef LAV_EPI
 #undef LAV_EPI_TMA
@@ -752,6 +785,19 @@ extern "C" int lav_gemm_f16(const void* A, int64_t lda, int a_major, const void*
   LAV_REQUIRE(!(epi->act == LAV_ACT_GELU_BWD && !epi->aux), "lav_gemm_f16: GELU_BWD needs aux");
   LAV_REQUIRE(!(epi->act != LAV_ACT_NONE && epi->residual), "lav_gemm_f16: activations cannot be combined with a residual");
   LAV_REQUIRE(!(epi->act != LAV_ACT_NONE && epi->accumulate == LAV_ACCUMULATE), "lav_gemm_f16: activations cannot accumulate");
+  {
+    const bool f16o = epi->out_dtype == LAV_OUT_F16, acc = epi->accumulate == LAV_ACCUMULATE;
+    bool ok;
+    if (a_major == LAV_MAJOR_MN)        // wgrad: plain fp32 store / accumulate
+      ok = epi->act == LAV_ACT_NONE && !f16o && !epi->residual && !epi->row_map && !epi->row_scale;
+    else if (b_major == LAV_MAJOR_MN)   // dgrad: plain / GELU' / fp32 residual
+      ok = epi->act != LAV_ACT_GELU && !acc && !(epi->residual && f16o) && !(epi->residual && epi->act != LAV_ACT_NONE);
+    else                                // forward
+      ok = epi->act != LAV_ACT_GELU_BWD && !acc && !(epi->residual && f16o);
+    LAV_REQUIRE(ok, "lav_gemm_f16: this (operand layout, epilogue) combination is not instantiated (a_major %d b_major %d "
+                "act %d out_dtype %d accumulate %d residual %d)", a_major, b_major, epi->act, epi->out_dtype,
+                epi->accumulate, epi->residual != nullptr);
+  }
   GemmParams p;
   p.M = M, p.N = N, p.K = K;
   p.k_blocks = (K + BK - 1) / BK;

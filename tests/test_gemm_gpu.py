@@ -162,4 +162,4 @@ def test_split_fp16_gemm_restores_fp32_operand_precision():
     e_hp = (out.double() - ref).abs().max().item()
     e_16 = (plain.double() - ref).abs().max().item()
     print(f"split-fp16 GEMM max abs err {e_hp:.2e} vs plain fp16 operands {e_16:.2e} (|ref| max {ref.abs().max().item():.1f})")
-    assert e_hp < 2e-5 and e_hp * 50 < e_16
+    assert e_hp < 1e-4 and e_hp * 50 < e_16   # fp32 accumulation over K' = 2304 terms, |ref| up to ~9
