@@ -17,8 +17,13 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 fp16 = one 128-byte swizzle atom
 constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = 128 + kEpiWarps * 32;
-constexpr int kEpiStride = 36;  // floats per staged accumulator row: 16-byte aligned, conflict-free for 128-bit access
-constexpr int kEpiWarpBytes = 8192;  // >= 32 * kEpiStride * 4; four 2 KB (fp16) or two 4 KB (fp32) TMA-store buffers
+// Per-warp epilogue staging: ONE 32 x 32 fp32 chunk (4 KB), 16-byte slots XOR-swizzled by the row so that both the row
+// writes (thread = row) and the transposed reads (8 lanes per row) are conflict-free without padding; the TMA-store path
+// uses it as two 2 KB fp16 buffers / one 4 KB fp32 buffer.  Kept small on purpose: with 64 KB of staging the 128 x 256
+// tile had only 3 operand stages (3 x 48 KB in flight against ~0.8 us of TMA latency + 0.27 us of MMA per k-block made
+// the main loop feed-bound at 0.37 us per k-block, profiles/r2_gemm_ablation.md); 32 KB buys the 4th stage.
+constexpr int kEpiWarpBytes = 4096;
+__device__ __forceinline__ int epi_slot(int row, int slot) { return row * 32 + ((slot ^ (row & 7)) << 2); }  // float index
 
 // Persistent work streams: one CTA per SM, or one CTA pair per TPC.  The pair path (LAV_GEMM_PAIR=1) is correct and
 // wins on large square problems (8192^3: 1342 vs 1150 TFLOP/s) but not on the hot path's shapes, whose cost is the
@@ -45,8 +50,8 @@ struct GemmCfg {
   static constexpr int EPI_BYTES = kEpiWarps * kEpiWarpBytes;  // per-warp staging: transposes / TMA-store buffers
   static constexpr int BAR_BYTES = 1024;  // mbarriers + TMEM slot in [0, 256), the all-ones operand tile in [256, 768)
   static constexpr int STAGES_MAX = (232448 - 1024 - BAR_BYTES - EPI_BYTES) / STAGE_BYTES;
-  static constexpr int STAGES_CAP = NCTA == 2 ? 8 : 6;
-  static constexpr int STAGES = STAGES_MAX > STAGES_CAP ? STAGES_CAP : STAGES_MAX;  // 1-CTA: 3 / 5 / 6 for BN = 256 / 128 / 64
+  static constexpr int STAGES_CAP = 8;
+  static constexpr int STAGES = STAGES_MAX > STAGES_CAP ? STAGES_CAP : STAGES_MAX;  // 1-CTA: 4 / 4 / 6 / 8 for BN = 256 / 192 / 128 / 64
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
   static constexpr int BIAS_COLS = (BN <= 192 && NCTA == 1) ? 32 : 0;         // 2 x 16 columns: fused bias gradient
   static constexpr int TMEM_COLS = 2 * BN + BIAS_COLS;                        // 2 accumulator stages
@@ -91,7 +96,7 @@ __device__ __forceinline__ void red_add_v4(float* p, float4 v) {
 __device__ __forceinline__ void stage_rows(float* stg, int lane, const float (&v)[32]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j)
-    *reinterpret_cast<float4*>(stg + lane * kEpiStride + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    *reinterpret_cast<float4*>(stg + epi_slot(lane, j)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 }
 
 enum { ST_F32 = 0, ST_F32_RMW = 1, ST_F32_RED = 2, ST_F16 = 3 };
@@ -109,7 +114,7 @@ __device__ __forceinline__ void store_phase(const GemmParams& p, const float* st
   for (int it = 0; it < 8; ++it) {
     const int r = it * 4 + rr;
     if (orow[it] < 0) continue;
-    float4 a = *reinterpret_cast<const float4*>(stg + r * kEpiStride + 4 * cg);
+    float4 a = *reinterpret_cast<const float4*>(stg + epi_slot(r, cg));
     if (use_res) {
       a.x += __uint_as_float(res[it].x), a.y += __uint_as_float(res[it].y);
       a.z += __uint_as_float(res[it].z), a.w += __uint_as_float(res[it].w);
@@ -165,7 +170,7 @@ __device__ __forceinline__ void store_aux_phase(const GemmParams& p, const float
     const int r = it * 4 + rr;
     const int row = row_base + r;
     if (row >= p.M) continue;
-    const float4 a = *reinterpret_cast<const float4*>(stg + r * kEpiStride + 4 * cg);
+    const float4 a = *reinterpret_cast<const float4*>(stg + epi_slot(r, cg));
     __half* o = reinterpret_cast<__half*>(e.aux) + (size_t)row * e.ldaux + col;
     if (vec) *reinterpret_cast<uint2*>(o) = make_uint2(pack_half2(a.x, a.y), pack_half2(a.z, a.w));
     else {
@@ -185,11 +190,12 @@ __device__ __forceinline__ void store_aux_phase(const GemmParams& p, const float
 // ---------------------------------------------------------------------------------------------------------
 template <bool F32>
 __device__ __forceinline__ void stage_and_store(const CUtensorMap* tm, uint8_t* buf, uint32_t& nb, int lane,
-                                                const float (&v)[32], int col0, int row0, bool rows_valid) {
+                                                const float (&v)[32], int col0, int row0, bool rows_valid, int dbg = 0) {
   constexpr int ROWB = F32 ? 128 : 64;
   constexpr int BUFB = 32 * ROWB;
   constexpr int NB = kEpiWarpBytes / BUFB;
   uint8_t* b = buf + (nb % NB) * BUFB;
+  if (dbg & 16) return;                          // (profiling) no staging, no store
   if (lane == 0) tma_store_wait_read<NB - 1>();  // the store that last used this buffer has drained it
   __syncwarp();
   if (F32) {
@@ -205,10 +211,10 @@ __device__ __forceinline__ void stage_and_store(const CUtensorMap* tm, uint8_t* 
           make_uint4(pack_half2(v[8 * j], v[8 * j + 1]), pack_half2(v[8 * j + 2], v[8 * j + 3]),
                      pack_half2(v[8 * j + 4], v[8 * j + 5]), pack_half2(v[8 * j + 6], v[8 * j + 7]));
   }
-  fence_proxy_async_smem();
+  if (!(dbg & 8)) fence_proxy_async_smem();      // (profiling bit 8: no proxy fence)
   __syncwarp();
   if (lane == 0) {
-    if (rows_valid) tma_store_2d(tm, b, col0, row0);
+    if (rows_valid && !(dbg & 4)) tma_store_2d(tm, b, col0, row0);   // (profiling bit 4: no TMA store)
     tma_store_commit();
   }
   ++nb;
@@ -296,12 +302,12 @@ __device__ __forceinline__ void epilogue_warps_tma2(const GemmParams& p, const C
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(cur[j]);
       }
-      if (e.bias) {
+      if (e.bias && !(p.debug & 32)) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bias_lane, j);
       }
       if (ACT == LAV_ACT_GELU) {
-        if (aux_out) stage_and_store<false>(tmAux, buf, nb, lane, v, col0, row_base, rows_valid);
+        if (aux_out) stage_and_store<false>(tmAux, buf, nb, lane, v, col0, row_base, rows_valid, p.debug);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
       } else if (ACT == LAV_ACT_GELU_BWD) {
@@ -312,7 +318,7 @@ __device__ __forceinline__ void epilogue_warps_tma2(const GemmParams& p, const C
           v[2 * j] *= gelu_erf_grad(x.x), v[2 * j + 1] *= gelu_erf_grad(x.y);
         }
       }
-      stage_and_store<F32>(tmOut, buf, nb, lane, v, col0, row_base, rows_valid);
+      stage_and_store<F32>(tmOut, buf, nb, lane, v, col0, row_base, rows_valid, p.debug);
     };
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
@@ -325,48 +331,43 @@ __device__ __forceinline__ void epilogue_warps_tma2(const GemmParams& p, const C
   if (lane == 0) tma_store_wait_all();  // smem must outlive the reads; the writes complete before the grid does
 }
 
-// register-path epilogue (row map / residual / DropPath / dropout / accumulation), software-pipelined like the above
+// register-path epilogue (row map / residual / DropPath / dropout / accumulation): one accumulator chunk in registers,
+// the chunk's global input (residual rows / GELU pre-activation) prefetched one chunk ahead
+// Body of the 8 epilogue warps (two warpgroups, one per TMEM accumulator stage), specialised at compile time on the
+// activation, on whether a global input is prefetched (PRE: residual rows) and on the store mode: the epilogue is
+// instruction-issue bound for the short-K GEMMs of the Swin stages, so unused paths must not cost instructions.
 template <int BN, int NCTA, int ACT, int PRE, int STORE, bool DROP = false>
-__device__ __forceinline__ void epilogue_warps2(const GemmParams& p, float* epi_stage, uint64_t* tmem_full,
-                                                uint64_t* tmem_empty, uint32_t tmem_base, int warp, int lane, int total,
-                                                int stream_id, int nstreams, int rank) {
+__device__ __forceinline__ void epilogue_warps(const GemmParams& p, float* epi_stage, uint64_t* tmem_full,
+                                               uint64_t* tmem_empty, uint32_t tmem_base, int warp, int lane, int total,
+                                               int stream_id, int nstreams, int rank) {
   const int wg = (warp - 4) >> 2;
-  const int q = warp & 3;
+  const int q = warp & 3;  // TMEM lane quarter this warp may access
   float* stg = epi_stage + (warp - 4) * (kEpiWarpBytes / 4);
-  const int rr = lane >> 3, cg = lane & 7;
+  const int rr = lane >> 3, cg = lane & 7;  // this lane's row-within-group / 4-column group in the store phase
   const LavGemmEpilogue& e = p.epi;
   constexpr bool use_res = PRE == 1;
   constexpr bool use_auxin = ACT == LAV_ACT_GELU_BWD;
   constexpr bool use_pre = use_res || use_auxin;
-  constexpr int KMAX = (BN / 32 + 1) / 2;
   DropKey dkey{};
   if (DROP) dkey = drop_key(p.drop);
   int iter = 0;
   for (int item = stream_id; item < total; item += nstreams, ++iter) {
-    const int as = iter & 1;
+    const int as = iter & 1;  // accumulator stage; BOTH warpgroups drain every tile (even / odd 32-column chunks)
     const TileCoord t = decode_tile(p, item);
     const int row_base = (t.m_blk * NCTA + rank) * BM + q * 32;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
-    const int n0 = t.n_blk * BN;
-    const int nchunks = min(BN / 32, (p.N - n0 + 31) / 32);
+    const int nchunks = min(BN / 32, (p.N - t.n_blk * BN + 31) / 32);
+    // output rows of this lane's 8 store-phase rows (row map resolved once per tile)
     int orow[8];
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int row = row_base + it * 4 + rr;
       orow[it] = row < p.M ? (e.row_map ? __ldg(e.row_map + row) : row) : -1;
     }
-    float bl[KMAX];
-#pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      const int col = n0 + (wg + 2 * k) * 32 + lane;
-      bl[k] = (e.bias && wg + 2 * k < nchunks && col < p.N) ? __ldg(e.bias + col) : 0.f;
-    }
-    float rsc = 1.0f;
-    if (e.row_scale) rsc = __ldg(e.row_scale + min(row_base + lane, p.M - 1) / e.rows_per_scale);
-    // global INPUT of a chunk (residual rows in the store layout, or the GELU pre-activation), requested at the top of the
-    // chunk's step: its latency hides under the chunk's own math and staging
+    // Prefetch of the chunk's global INPUT (residual rows, or the GELU pre-activation for GELU_BWD) into registers,
+    // one chunk ahead: chunk 0 is requested before the accumulator is ready, so the latency hides under the MMAs.
     auto prefetch = [&](uint4(&dst)[8], int c) {
-      const int col = n0 + c * 32 + 4 * cg;
+      const int col = t.n_blk * BN + c * 32 + 4 * cg;
       const int nv = p.N - col;
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
@@ -394,42 +395,52 @@ __device__ __forceinline__ void epilogue_warps2(const GemmParams& p, float* epi_
         }
       }
     };
+    uint4 cur[8], nxt[8];
+    if (use_pre && wg < nchunks) prefetch(cur, wg);
     mbar_wait(tmem_full + as, (iter >> 1) & 1, 4);
     tc_fence_after();
     if (GemmCfg<BN, NCTA>::BIAS_COLS > 0 && p.bias_grad != nullptr && t.n_blk == 0 && wg == 0) {
+      // column 0 of the 128 x 16 side accumulator = row sums of A over this tile's k range
       uint32_t bsum;
       tmem_ld_32x1(tmem_base + ((uint32_t)(q * 32) << 16) + 2 * BN + as * 16, bsum);
       tmem_ld_wait();
       const int brow = row_base + lane;
       if (brow < p.M) atomicAdd(p.bias_grad + brow, __uint_as_float(bsum) * e.alpha);
     }
-    if ((p.debug & 1) || wg >= nchunks) {
+    if ((p.debug & 1) || wg >= nchunks) {  // (a warpgroup without a chunk of a narrow tile just releases the stage)
       tc_fence_before();
       if (NCTA == 2) mbar_arrive_cluster(tmem_empty + as, 0);
       else mbar_arrive(tmem_empty + as);
       continue;
     }
-    uint32_t accA[32], accB[32];
-    tmem_ld_32x32(taddr + wg * 32, accA);
-    auto step = [&](uint32_t(&cur)[32], uint32_t(&nxt)[32], int c, float bias_lane) {
-      const int col0 = n0 + c * 32;
-      const int col = col0 + 4 * cg;
-      uint4 pre[8];
-      if (use_pre) prefetch(pre, c);
+#pragma unroll 1
+    for (int c = wg; c < nchunks; c += 2) {
+      const int col0 = t.n_blk * BN + c * 32;
+      const int col = col0 + 4 * cg;  // this lane's columns in the transposed (store) phases
+      uint32_t acc[32];
+      tmem_ld_32x32(taddr + c * 32, acc);
+      if (use_pre && c + 2 < nchunks) prefetch(nxt, c + 2);
       tmem_ld_wait();
-      if (c + 2 < nchunks) {
-        tmem_ld_32x32(taddr + (c + 2) * 32, nxt);
-      } else {
+      if (c + 2 >= nchunks) {  // accumulator fully read: hand the TMEM stage back to the MMA warp early
         tc_fence_before();
-        if (NCTA == 2) mbar_arrive_cluster(tmem_empty + as, 0);
+        if (NCTA == 2) mbar_arrive_cluster(tmem_empty + as, 0);  // the leader's MMA warp waits for both CTAs
         else mbar_arrive(tmem_empty + as);
       }
       float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(cur[j]) * e.alpha;
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * e.alpha;
       if (e.bias) {
+        if (col0 + 32 <= p.N) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bias_lane, j);
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col0) + j);
+            v[4 * j] += b.x, v[4 * j + 1] += b.y, v[4 * j + 2] += b.z, v[4 * j + 3] += b.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) v[j] += __ldg(e.bias + col0 + j);
+        }
       }
       if (ACT == LAV_ACT_GELU) {
         if (e.aux) {
@@ -441,47 +452,48 @@ __device__ __forceinline__ void epilogue_warps2(const GemmParams& p, float* epi_
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
       } else if (use_auxin) {
+        // pre-activation: (store-layout registers) -> smem -> (row-layout registers)
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
-          const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&pre[it].x));
-          const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&pre[it].y));
-          *reinterpret_cast<float4*>(stg + (it * 4 + rr) * kEpiStride + 4 * cg) = make_float4(f0.x, f0.y, f1.x, f1.y);
+          const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&cur[it].x));
+          const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&cur[it].y));
+          *reinterpret_cast<float4*>(stg + epi_slot(it * 4 + rr, cg)) = make_float4(f0.x, f0.y, f1.x, f1.y);
         }
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 x = *reinterpret_cast<const float4*>(stg + lane * kEpiStride + 4 * j);
+          const float4 x = *reinterpret_cast<const float4*>(stg + epi_slot(lane, j));
           v[4 * j] *= gelu_erf_grad(x.x), v[4 * j + 1] *= gelu_erf_grad(x.y);
           v[4 * j + 2] *= gelu_erf_grad(x.z), v[4 * j + 3] *= gelu_erf_grad(x.w);
         }
         __syncwarp();
       }
-      if (DROP) {
+      if (DROP) {  // BertSelfOutput / BertOutput .dropout on (dense + bias), element index (GEMM row, column)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint32_t m = drop_keep8(dkey, p.drop.thresh, (uint32_t)(row_base + lane), (uint32_t)((col0 >> 3) + j), 0u);
 #pragma unroll
-          for (int qq = 0; qq < 8; ++qq) v[8 * j + qq] = ((m >> qq) & 1u) ? v[8 * j + qq] * p.drop.inv_keep : 0.f;
+          for (int q = 0; q < 8; ++q) v[8 * j + q] = ((m >> q) & 1u) ? v[8 * j + q] * p.drop.inv_keep : 0.f;
         }
       }
       if (e.row_scale) {
+        const int row = min(row_base + lane, p.M - 1);
+        const float sc = __ldg(e.row_scale + row / e.rows_per_scale);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] *= rsc;
+        for (int j = 0; j < 32; ++j) v[j] *= sc;
       }
       stage_rows(stg, lane, v);
       __syncwarp();
-      store_phase<STORE>(p, stg, orow, pre, use_res, col, rr, cg);
+      store_phase<STORE>(p, stg, orow, cur, use_res, col, rr, cg);
       __syncwarp();
-    };
+      if (use_pre) {
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      const int c = wg + 2 * k;
-      if (c >= nchunks) break;
-      if (k & 1) step(accB, accA, c, bl[k]);
-      else step(accA, accB, c, bl[k]);
+        for (int it = 0; it < 8; ++it) cur[it] = nxt[it];
+      }
     }
   }
 }
+
 
 template <int BN, int AMAJ, int BMAJ, int NCTA>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -645,8 +657,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                    : e.accumulate != LAV_ACCUMULATE ? ST_F32 : (p.splits > 1 ? ST_F32_RED : ST_F32_RMW);
     const int pre = e.residual != nullptr ? 1 : 0;
 #define LAV_EPI(A, P, S)                                                                                          \
-  epilogue_warps2<BN, NCTA, A, P, S>(p, epi_stage, tmem_full, tmem_empty, tmem_base, warp, lane, total, stream_id,   \
-                                     nstreams, rank)
+  epilogue_warps<BN, NCTA, A, P, S>(p, epi_stage, tmem_full, tmem_empty, tmem_base, warp, lane, total, stream_id,    \
+                                    nstreams, rank)
 #define LAV_EPI_TMA(A, F)                                                                                          \
   epilogue_warps_tma2<BN, NCTA, A, F>(p, &tmOut, &tmAux, epi_stage, tmem_full, tmem_empty, tmem_base, warp, lane,  \
                                       total, stream_id, nstreams, rank)
@@ -683,8 +695,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (st == ST_F16) LAV_EPI(LAV_ACT_NONE, 0, ST_F16);
         else LAV_EPI(LAV_ACT_NONE, 0, ST_F32);
       } else if (p.drop.on) {  // host restricts dropout to (no activation, residual, fp32 store)
-        epilogue_warps2<BN, NCTA, LAV_ACT_NONE, 1, ST_F32, true>(p, epi_stage, tmem_full, tmem_empty, tmem_base, warp, lane,
-                                                                 total, stream_id, nstreams, rank);
+        epilogue_warps<BN, NCTA, LAV_ACT_NONE, 1, ST_F32, true>(p, epi_stage, tmem_full, tmem_empty, tmem_base, warp, lane,
+                                                                total, stream_id, nstreams, rank);
       } else {
         LAV_EPI(LAV_ACT_NONE, 1, ST_F32);
       }
