@@ -28,6 +28,13 @@ WORKLOAD = "configs[1]: swin_base_patch244_window877 + 12-layer BERT-base fusion
            "5x224x224 frames, 33 text tokens, MLM + VTM(4 pairs/clip) fwd+bwd+AdamW"
 METRIC = "clips/sec (5x224x224, seq=32) pretrain fwd+bwd"
 PER_GPU_BATCH = 8
+# --workload: the headline is configs[1] (= configs[2] per GPU); config4 / multitask are extra measured lines
+WORKLOADS = {
+    "configs1": dict(size="base", img=224, B=8, win=(8, 7, 7), text=WORKLOAD, metric=METRIC),
+    "config4": dict(size="large", img=384, B=4, win=(8, 12, 12), metric="clips/sec (5x384x384, seq=32) pretrain fwd+bwd",
+                    text="configs[3]: swin_large_384_patch244_window81212 + 12-layer BERT-base + MLM head, 4 clips/GPU, "
+                         "5x384x384 frames (720-token windows, 758-token fusion sequences), MLM + VTM fwd+bwd+AdamW"),
+}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -116,10 +123,10 @@ def summarize_clocks(samples):
 _emit = print
 
 
-def make_host_batch(B, seed, pin):
+def make_host_batch(B, seed, pin, H=224):
     import torch
     g = torch.Generator().manual_seed(1000 + seed)
-    img = torch.randn(B, 5, 3, 224, 224, generator=g)
+    img = torch.randn(B, 5, 3, H, H, generator=g)
     txt = torch.randint(1000, 30000, (B, 33), generator=g)
     txt[:, 0], txt[:, -2], txt[:, -1] = 101, 102, 103
     mask = torch.ones(B, 33, dtype=torch.long)
@@ -143,7 +150,8 @@ def run_native(a):
         raise SystemExit("bench.py: no CUDA device - the native path has no CPU fallback (use --impl reference)")
     world, rank, local = D.get_world_size(), D.get_rank(), D.get_local_rank()
     assert world == a.gpus or world == 1, f"--gpus {a.gpus} but WORLD_SIZE={world}"
-    args = default_args(vis_backbone_size="base", size_batch=PER_GPU_BATCH, seed=0, max_iter=100000,
+    wl = WORKLOADS[a.workload]
+    args = default_args(vis_backbone_size=wl["size"], size_img=wl["img"], size_batch=wl["B"], seed=0, max_iter=100000,
                         cuda_graph=not a.no_graph)
     torch.cuda.set_device(local)
     D.dist_init(args, distributed=world > 1)
@@ -158,8 +166,8 @@ def run_native(a):
     agent.prepare_dist_model()
     nparams = sum(p.numel() for p in model.parameters())
 
-    B = PER_GPU_BATCH
-    host = make_host_batch(B, seed=rank, pin=True)
+    B = wl["B"]
+    host = make_host_batch(B, seed=rank, pin=True, H=wl["img"])
     np.random.seed(1234 + rank)
     torch.manual_seed(1234 + rank)
 
@@ -307,10 +315,11 @@ def run_native(a):
         torch.cuda.synchronize()
         _streams._ENABLED = side_was
         pair = sorted(c0.elapsed_time(c1) for c0, c1 in cal)[len(cal) // 2]
-        for name, s, e, fl, _meta in ops.PROFILE:
-            f = fams.setdefault(name, {"ms": 0.0, "flops": 0.0, "launches": 0})
+        for name, s, e, fl, _meta, nby in ops.PROFILE:
+            f = fams.setdefault(name, {"ms": 0.0, "flops": 0.0, "launches": 0, "bytes": 0.0})
             f["ms"] += max(s.elapsed_time(e) - pair, 0.0)
             f["flops"] += fl
+            f["bytes"] += nby
             f["launches"] += 1
         step_ms_prof = t0.elapsed_time(t1)
         ops.PROFILE = None
@@ -327,17 +336,17 @@ def run_native(a):
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else \
         "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
     clips = B * world * a.steps
-    fwd = fwd_flops_per_clip("base", 12, B=B)
+    fwd = fwd_flops_per_clip(wl["size"], 12, H=wl["img"], W=wl["img"], B=B, win=wl["win"])
     step_flops = 3.0 * fwd * B
     top = max((k for k in fams if fams[k]["flops"] > 0), key=lambda k: fams[k]["ms"])
     tf = fams[top]["flops"] / (fams[top]["ms"] * 1e-3) / 1e12
     kern_total = sum(f["ms"] for f in fams.values())
     out = {
-        "metric": METRIC, "value": round(clips / (ms * 1e-3), 2), "unit": "clips/s", "n_gpus": world, "steps": a.steps,
+        "metric": wl["metric"], "value": round(clips / (ms * 1e-3), 2), "unit": "clips/s", "n_gpus": world, "steps": a.steps,
         "warmup": max(a.warmup, 3), "ms_per_step": round(ms / a.steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f16 operands, f32 accumulate/statistics/residual/master weights",
         "data": "synthetic (seeded randn frames, random token ids, random-init weights)",
-        "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "params": nparams,
+        "config": {"workload": wl["text"], "per_gpu_batch": B, "global_batch": B * world, "params": nparams,
                    "parallelism": f"dp{world}", "step": "fwd(MLM+VTM) + 2xCE + bwd + grad all-reduce + clip + AdamW"
                    + (" (fused flat-arena kernels)" if agent.fused else " (torch foreach)"),
                    "l2": "working set (activations > 10 GB/step) far exceeds the 126 MB L2; no explicit flush",
@@ -360,6 +369,8 @@ def run_native(a):
         "roofline": {"bound": "tensor", "kernel": top, "achieved": round(tf, 1), "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": round(tf / peak_tf, 4), "traffic": None, "peak_source": peak_src,
                      "launches_per_step": fams[top]["launches"], "ms_per_step": round(fams[top]["ms"], 3),
+                     "algorithmic_flops_per_launch": round(fams[top]["flops"] / fams[top]["launches"]),
+                     "algorithmic_bytes_per_launch": round(fams[top]["bytes"] / fams[top]["launches"]),
                      "share_of_step": round(fams[top]["ms"] / max(kern_total, 1e-9), 3),
                      "how": "CUDA events around every launch of one single-stream eager step issued behind a "
                             "device-side spin (queue kept full, so a pair brackets device time), minus the measured cost "
@@ -381,14 +392,14 @@ def run_native(a):
         out["window_attention"] = wa
     if world > 1:
         out["dp_check"] = dp
-    if not a.no_gpu_baseline and world == 1:
+    if not a.no_gpu_baseline and world == 1 and a.workload == "configs1":
         phase("PyTorch-eager fp16-autocast baseline on the same GPU")
         try:
             out["gpu_torch_baseline"] = gpu_torch_baseline(B, steps=5, warmup=2)
             out["gpu_torch_baseline"]["native_speedup"] = round(out["value"] / out["gpu_torch_baseline"]["value"], 2)
         except Exception as e:   # a baseline must never take the headline down
             out["gpu_torch_baseline"] = {"error": repr(e)[:300]}
-    if not a.no_cpu_baseline and world == 1:
+    if not a.no_cpu_baseline and world == 1 and a.workload == "configs1":
         phase("CPU baseline (oracle port on the host cores)")
         out["cpu_baseline"] = cpu_oracle_baseline(steps=3, warmup=1, B=4, budget_s=60.0)
     _emit(json.dumps(out))
@@ -531,6 +542,73 @@ def run_reference(a):
     _emit(json.dumps(out))
 
 
+MT_SHAPES = (  # (task, task_name, per-GPU batch, text length X, options) from _args/args_multi-task_all.json
+    ("msrvtt-retrieval", 20, dict(X=25)), ("didemo-retrieval", 12, dict(X=100)), ("msvd-qaoe", 60, dict(X=25)),
+    ("tgif-action-qamc", 60, dict(X=100)), ("lsmdc-mc-qamc", 60, dict(X=25, O_=5)), ("msrvtt-captioning", 60, dict(X=50)))
+
+
+def run_multitask(a):
+    """BASELINE configs[4]: multi-task MLM training (swin_base + BERT-base) — one eager training step per task type
+    (forward of LAVENDER_Multi_Task, the task's loss, backward, gradient all-reduce at N > 1, fused clip + AdamW) at the
+    per-GPU batch sizes / text lengths of _args/args_multi-task_all.json; clips/s per task and for a uniform task mix."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import lavender_oracle as O   # synthetic batch generator only (shared with the tests)
+    from lavender_b200 import _lib
+    from lavender_b200 import dist as D
+    from lavender_b200.agent import Agent_Base
+    from lavender_b200.multitask import LAVENDER_Multi_Task, add_task_token, train_step
+    from lavender_b200.pretrain import FakeTokenizer, default_args
+    world, rank, local = D.get_world_size(), D.get_rank(), D.get_local_rank()
+    args = default_args(vis_backbone_size="base", size_batch=60, seed=0, max_iter=100000)
+    torch.cuda.set_device(local)
+    D.dist_init(args, distributed=world > 1)
+    torch.manual_seed(0)
+    model = LAVENDER_Multi_Task(args, FakeTokenizer(), is_decoder=False).cuda()
+    agent = Agent_Base(args, model)
+    agent.prepare_dist_model()
+    steps, warm = max(2, min(a.steps, 5)), 2
+    res, n0 = {}, _lib.launch_count()
+    for ti, (task, B, kw) in enumerate(MT_SHAPES):
+        b = O.make_multitask_batch(task, B=B, seed=rank * 10 + ti, **kw)
+        b = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in b.items()}
+        b["task"] = task
+        add_task_token(b)
+        for _ in range(warm):
+            train_step(agent, dict(b))
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            ls = train_step(agent, dict(b))
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        seqs = B * B if "retrieval" in task else B * kw.get("O_", 1)
+        res[task] = {"per_gpu_batch": B, "text_len": kw["X"], "fusion_sequences_per_step": seqs, "ms_per_step": round(ms.item(), 2),
+                     "clips_per_s": round(B * world / (ms.item() * 1e-3), 1), "loss": round(float(ls), 4)}
+        torch.cuda.empty_cache()
+    if rank != 0:
+        return
+    tot_clips = sum(r["per_gpu_batch"] * world for r in res.values())
+    tot_ms = sum(r["ms_per_step"] for r in res.values())
+    _emit(json.dumps({
+        "metric": "clips/sec multi-task MLM training (uniform task mix)", "value": round(tot_clips / (tot_ms * 1e-3), 1),
+        "unit": "clips/s", "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": round(tot_ms / len(res), 2),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16 operands, f32 accumulate/statistics/residual/master weights", "data": "synthetic",
+        "config": {"workload": "configs[4]: multi-task MLM (args_multi-task_all.json shapes) swin_base + BERT-base, eager steps "
+                               "(retrieval B^2 pairs, QA-OE, QA-MC, QA-MC as retrieval, seq2seq captioning)",
+                   "parallelism": f"dp{world}"},
+        "tasks": res, "gpu_launches": int(_lib.launch_count() - n0)}))
+
+
 def run_check_dp(a):
     """`--check-dp` (torchrun, N >= 2): the data-parallel path against a single process.
       1. N ranks x B clips: eval-mode forward + 2x CE + scaled backward + GradSync (NCCL all-reduce, mean over ranks);
@@ -639,6 +717,9 @@ def main():
                     help="one eager step between cudaProfilerStart/Stop (ncu --profile-from-start off)")
     ap.add_argument("--eval-dropout", action="store_true",
                     help="identity BERT dropout (default: active p=0.1 dropout as in the reference's train() step)")
+    ap.add_argument("--workload", default="configs1", choices=["configs1", "config4", "multitask"],
+                    help="configs1 = the headline (BASELINE configs[1]/[2]); config4 = swin_large_384 (configs[3]); "
+                         "multitask = configs[4] per-task clips/s")
     ap.add_argument("--check-dp", action="store_true",
                     help="N-rank gradients vs one process on the concatenated batch + weight equality after 3 steps")
     a = ap.parse_args()
@@ -653,6 +734,8 @@ def main():
         run_reference(a)
     elif a.check_dp:
         run_check_dp(a)
+    elif a.workload == "multitask":
+        run_multitask(a)
     else:
         run_native(a)
 

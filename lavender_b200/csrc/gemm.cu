@@ -101,6 +101,18 @@ __device__ __forceinline__ void stage_rows(float* stg, int lane, const float (&v
 
 enum { ST_F32 = 0, ST_F32_RMW = 1, ST_F32_RED = 2, ST_F16 = 3 };
 
+// Every lane of the warp has finished reading its rows of the accumulator stage (tcgen05.wait::ld + fence::before_thread_sync
+// executed by the caller): one lane tells the MMA warp — in a CTA pair that is a remote arrive on the leader's barrier, so
+// 8 per CTA and tile instead of 256.
+template <int NCTA>
+__device__ __forceinline__ void release_tmem_stage(uint64_t* bar, int lane) {
+  __syncwarp();
+  if (lane == 0) {
+    if (NCTA == 2) mbar_arrive_cluster(bar, 0);
+    else mbar_arrive(bar);
+  }
+}
+
 // staged chunk -> out (+ prefetched residual, at the pre-resolved output rows).  (rr, cg) = lane's row-in-group /
 // 4-column group; orow[it] < 0 marks rows beyond M.
 template <int MODE>
@@ -275,8 +287,7 @@ __device__ __forceinline__ void epilogue_warps_tma2(const GemmParams& p, const C
     tc_fence_after();
     if ((p.debug & 1) || wg >= nchunks) {  // (a warpgroup without a chunk of a narrow tile just releases the stage)
       tc_fence_before();
-      if (NCTA == 2) mbar_arrive_cluster(tmem_empty + as, 0);
-      else mbar_arrive(tmem_empty + as);
+      release_tmem_stage<NCTA>(tmem_empty + as, lane);
       continue;
     }
     uint32_t accA[32], accB[32];
@@ -291,8 +302,7 @@ __device__ __forceinline__ void epilogue_warps_tma2(const GemmParams& p, const C
         if (ACT == LAV_ACT_GELU_BWD) load_aux(axn, c + 2);
       } else {                // the whole accumulator has been read: hand the TMEM stage back to the MMA warp
         tc_fence_before();
-        if (NCTA == 2) mbar_arrive_cluster(tmem_empty + as, 0);
-        else mbar_arrive(tmem_empty + as);
+        release_tmem_stage<NCTA>(tmem_empty + as, lane);
       }
       float v[32];
       if (e.alpha != 1.0f) {
@@ -409,8 +419,7 @@ __device__ __forceinline__ void epilogue_warps(const GemmParams& p, float* epi_s
     }
     if ((p.debug & 1) || wg >= nchunks) {  // (a warpgroup without a chunk of a narrow tile just releases the stage)
       tc_fence_before();
-      if (NCTA == 2) mbar_arrive_cluster(tmem_empty + as, 0);
-      else mbar_arrive(tmem_empty + as);
+      release_tmem_stage<NCTA>(tmem_empty + as, lane);
       continue;
     }
 #pragma unroll 1
@@ -423,8 +432,7 @@ __device__ __forceinline__ void epilogue_warps(const GemmParams& p, float* epi_s
       tmem_ld_wait();
       if (c + 2 >= nchunks) {  // accumulator fully read: hand the TMEM stage back to the MMA warp early
         tc_fence_before();
-        if (NCTA == 2) mbar_arrive_cluster(tmem_empty + as, 0);  // the leader's MMA warp waits for both CTAs
-        else mbar_arrive(tmem_empty + as);
+        release_tmem_stage<NCTA>(tmem_empty + as, lane);  // (pair: the leader's MMA warp waits for both CTAs)
       }
       float v[32];
 #pragma unroll
@@ -532,7 +540,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tmem_full + s, 1);
-      mbar_init(tmem_empty + s, 256 * NCTA);
+      mbar_init(tmem_empty + s, kEpiWarps * NCTA);  // one elected arrive per epilogue warp
     }
     fence_barrier_init();
   }

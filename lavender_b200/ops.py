@@ -18,10 +18,10 @@ PROFILE_META = False  # also record a shape tag per call (tools/profile_step.py)
 
 
 class _Timed:
-    __slots__ = ("name", "flops", "ev", "meta")
+    __slots__ = ("name", "flops", "ev", "meta", "bytes")
 
-    def __init__(self, name, flops=0.0, meta=None):
-        self.name, self.flops, self.ev, self.meta = name, flops, None, meta
+    def __init__(self, name, flops=0.0, meta=None, nbytes=0.0):
+        self.name, self.flops, self.ev, self.meta, self.bytes = name, flops, None, meta, nbytes
 
     def __enter__(self):
         if PROFILE is not None:
@@ -33,7 +33,7 @@ class _Timed:
         if PROFILE is not None and self.ev is not None:
             end = torch.cuda.Event(enable_timing=True)
             end.record()
-            PROFILE.append((self.name, self.ev, end, self.flops, self.meta if PROFILE_META else None))
+            PROFILE.append((self.name, self.ev, end, self.flops, self.meta if PROFILE_META else None, self.bytes))
         return False
 
 
@@ -92,7 +92,10 @@ def gemm(a, b, out, *, M, N, K, a_major=L.MAJOR_K, b_major=L.MAJOR_K, bias=None,
         e.bias_grad = bias_grad.data_ptr()
     if drop is not None and drop[2] > 0.0:
         e.drop = L.Dropout(drop[0].data_ptr(), int(drop[1]) & 0xFFFFFFFF, float(drop[2]))
-    with _Timed("gemm", 2.0 * M * N * K, ("gemm", M, N, K, a_major, b_major, act, out.dtype == F16, accumulate)):
+    # algorithmic HBM bytes of the launch: both operands once, the output once (+ what the epilogue reads / also writes)
+    nbytes = 2.0 * K * (M + N) + M * N * ((2 if out.dtype == F16 else 4) + (4 if residual is not None else 0)
+                                          + (2 if aux is not None else 0) + (4 if accumulate else 0))
+    with _Timed("gemm", 2.0 * M * N * K, ("gemm", M, N, K, a_major, b_major, act, out.dtype == F16, accumulate), nbytes):
         rc = L.lib().lav_gemm_f16(_ptr(a), a.stride(0), a_major, _ptr(b), b.stride(0), b_major, M, N, K,
                                   ctypes.byref(e), split_k, _stream())
     L.check(rc, "lav_gemm_f16")
