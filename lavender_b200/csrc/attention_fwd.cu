@@ -20,7 +20,10 @@
 
 namespace lav {
 
-constexpr int kAttnThreads = 160;  // warps 0-3: softmax (one TMEM lane quarter each); warp 4: TMA + MMA + TMEM alloc
+// warps 0-7: softmax — warp w owns the TMEM lane quarter (w & 3) and the key-column half (w >> 2) of the score tile, i.e.
+// two threads per query row (the one-thread-per-row chain over 256 columns was the critical path of a CTA);
+// warp 8: TMA + MMA + TMEM alloc
+constexpr int kAttnThreads = 288;
 
 struct AttnFwdParams {
   int L, nheads, nprob, HD;
@@ -54,7 +57,7 @@ struct AttnFwdCfg {
 };
 
 template <int HD, int NKC, bool BMMA>
-__global__ void __launch_bounds__(kAttnThreads)
+__global__ void __launch_bounds__(kAttnThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmBias,
                 const AttnFwdParams p) {
   griddep_launch();  // dependents (GEMMs) may start their prologue under this kernel's tail
@@ -70,13 +73,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const int row0 = prob * p.L;  // first token row of this problem
   const int ncol = min(NP, (p.L + 31) & ~31);  // key columns that can hold a valid key (BERT: 283 -> 288 of 384)
 
-  if (BMMA && warp < 4) {
+  if (BMMA && warp < 8) {
     // identity strip: zero groups with one 16 x 16 identity block at groups 14-15 (K-major, no swizzle:
     // group g = [8 rows x k 0..7 | 8 rows x k 8..15], 16 bytes per row and core matrix)
     uint8_t* id = smem + Cfg::OFF_ID;
-    for (int i = threadIdx.x; i < kIdentBytes / 16; i += 128) reinterpret_cast<uint4*>(id)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < kIdentBytes / 16; i += 256) reinterpret_cast<uint4*>(id)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncwarp();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     if (threadIdx.x < 16) {
       const int r = threadIdx.x;
       const int off = r < 8 ? 14 * 256 + r * 16 + r * 2 : 15 * 256 + 128 + (r - 8) * 16 + (r - 8) * 2;
@@ -84,13 +87,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     }
     fence_proxy_async_smem();
   }
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       tma_prefetch_desc(&tmQKV);
       if (BMMA) tma_prefetch_desc(&tmBias);
       mbar_init(bars + 0, 1);
       mbar_init(bars + 1, 1);
-      mbar_init(bars + 2, 128);
+      mbar_init(bars + 2, 256);
       mbar_init(bars + 3, 1);
       fence_barrier_init();
     }
@@ -103,7 +106,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       // ---- loads
       mbar_arrive_expect_tx(bars + 0, Cfg::Q_BYTES + 2 * Cfg::KV_BYTES + (BMMA ? Cfg::P_BYTES : 0));
@@ -158,10 +161,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       umma_commit(bars + 3);
     }
   } else {
-    // ---- softmax: thread = query row
-    const int i = warp * 32 + lane;  // row within the q tile == TMEM lane
-    const int qi = t * 128 + i;      // token index within the problem
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    // ---- softmax: two threads per query row, each over one half of the key columns
+    const int hsel = warp >> 2;
+    const int i = (warp & 3) * 32 + lane;  // row within the q tile == TMEM lane
+    const int qi = t * 128 + i;            // token index within the problem
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    constexpr int HW = HD / 2;             // O columns written by each thread of the pair
+    constexpr int HC = NP / 2;             // key columns per thread
+    const int jlo = hsel * HC, jhi = min(ncol, jlo + HC);
     const float sc = p.scale;
     const __half* brow = nullptr;
     if (!BMMA && p.bias16) {
@@ -171,6 +178,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const float* kb = p.key_bias ? p.key_bias + (size_t)prob * NP : nullptr;
     DropKey dkey{};
     if (p.drop.on) dkey = drop_key(p.drop);
+    // row-pair exchange (maximum, then partial sum) in the first 2 KB of the Q tile: Q is dead once S has been computed
+    float* xch = reinterpret_cast<float*>(smem);
+    const int pair_bar = 2 + (warp & 3);
 
     auto biased = [&](const uint32_t(&s)[32], int j0, float(&v)[32]) {
 #pragma unroll
@@ -200,7 +210,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     tc_fence_after();
     float m = -INFINITY;
 #pragma unroll 1
-    for (int j0 = 0; j0 < ncol; j0 += 32) {
+    for (int j0 = jlo; j0 < jhi; j0 += 32) {
       uint32_t s[32];
       float v[32];
       tmem_ld_32x32(trow + j0, s);
@@ -209,12 +219,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 #pragma unroll
       for (int j = 0; j < 32; ++j) m = fmaxf(m, v[j]);
     }
+    xch[hsel * 128 + i] = m;
+    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+    m = fmaxf(m, xch[(hsel ^ 1) * 128 + i]);
     if (m == -INFINITY) m = 0.f;
     const float mlog = m * 1.4426950408889634f;
     float l = 0.f;
     uint8_t* prow = smem + Cfg::OFF_P + i * 128;
 #pragma unroll 1
-    for (int j0 = 0; j0 < ncol; j0 += 32) {
+    for (int j0 = jlo; j0 < jhi; j0 += 32) {
       uint32_t s[32];
       float v[32];
       tmem_ld_32x32(trow + j0, s);
@@ -228,9 +241,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       if (p.drop.on) {  // P -> keep * P / (1 - p); the normaliser l stays that of the un-dropped softmax
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const uint32_t m = drop_keep8(dkey, p.drop.thresh, (uint32_t)(row0 + qi), (uint32_t)((j0 >> 3) + j), (uint32_t)h);
+          const uint32_t mk = drop_keep8(dkey, p.drop.thresh, (uint32_t)(row0 + qi), (uint32_t)((j0 >> 3) + j), (uint32_t)h);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) v[8 * j + q] = ((m >> q) & 1u) ? v[8 * j + q] * p.drop.inv_keep : 0.f;
+          for (int q = 0; q < 8; ++q) v[8 * j + q] = ((mk >> q) & 1u) ? v[8 * j + q] * p.drop.inv_keep : 0.f;
         }
       }
       // P (fp16) -> smem, K-major 128B-swizzle atoms of [128 rows x 64 keys]
@@ -244,24 +257,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         *reinterpret_cast<uint4*>(atom + (((chunk0 + j) ^ (i & 7)) << 4)) = u;
       }
     }
+    xch[256 + hsel * 128 + i] = l;      // (second exchange array: the partner may still be reading the maximum)
     fence_proxy_async_smem();
     tc_fence_before();
     mbar_arrive(bars + 2);
+    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+    l += xch[256 + (hsel ^ 1) * 128 + i];
 
     mbar_wait(bars + 3, 0, 13);
     tc_fence_after();
     const float inv = 1.f / l;
     const bool valid = qi < p.L;
-    if (valid && p.lse) p.lse[(size_t)h * p.rows_total + row0 + qi] = m + __logf(l);
-#pragma unroll
-    for (int c0 = 0; c0 < HD; c0 += 32) {
-      uint32_t o[32];
-      tmem_ld_32x32(trow + c0, o);
+    if (valid && hsel == 0 && p.lse) p.lse[(size_t)h * p.rows_total + row0 + qi] = m + __logf(l);
+    {
+      uint32_t o[HW];
+      tmem_ld_cols<HW>(trow + hsel * HW, o);
       tmem_ld_wait();
       if (valid && p.out) {
-        __half* dst = p.out + (size_t)(row0 + qi) * p.ldo + h * HD + c0;
+        __half* dst = p.out + (size_t)(row0 + qi) * p.ldo + h * HD + hsel * HW;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < HW / 8; ++j) {
           uint4 u;
           u.x = pack_half2(__uint_as_float(o[8 * j]) * inv, __uint_as_float(o[8 * j + 1]) * inv);
           u.y = pack_half2(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv);
@@ -271,9 +286,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         }
       }
       if (valid && p.out32) {
-        float* dst = p.out32 + (size_t)(row0 + qi) * p.ldo32 + h * HD + c0;
+        float* dst = p.out32 + (size_t)(row0 + qi) * p.ldo32 + h * HD + hsel * HW;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < HW / 4; ++j)
           reinterpret_cast<float4*>(dst)[j] =
               make_float4(__uint_as_float(o[4 * j]) * inv, __uint_as_float(o[4 * j + 1]) * inv,
                           __uint_as_float(o[4 * j + 2]) * inv, __uint_as_float(o[4 * j + 3]) * inv);
@@ -282,7 +297,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
+  if (warp == 8) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
 }
 
 template <int HD, int NKC, bool BMMA>

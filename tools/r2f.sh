@@ -11,3 +11,8 @@ done
 LAV_GEMM_PAIR=1 timeout 200 python tools/bench_gemm.py --no-cublas > gpurun_out/r2f_pair_shapes.log 2>&1
 timeout 200 python tools/bench_gemm.py --no-cublas > gpurun_out/r2f_single_shapes.log 2>&1
 tail -n 2 gpurun_out/r2f_gemm_tests.log; cat gpurun_out/r2f_pair.log; cut -c1-120 gpurun_out/r2f_pair_shapes.log; echo SINGLE; cut -c1-120 gpurun_out/r2f_single_shapes.log
+# 2-threads-per-row forward attention kernels
+timeout 400 python -m pytest tests/test_attention_gpu.py tests/test_dropout_gpu.py -m gpu -q -x -p no:cacheprovider > gpurun_out/r2f_attn_tests.log 2>&1
+echo "rc=$?" >> gpurun_out/r2f_attn_tests.log
+timeout 300 python tools/bench_attn.py --dropout > gpurun_out/r2f_attn.log 2>&1
+tail -n 3 gpurun_out/r2f_attn_tests.log; cat gpurun_out/r2f_attn.log
