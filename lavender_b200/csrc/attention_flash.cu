@@ -14,10 +14,7 @@
 
 namespace lav {
 
-// warps 0-7: softmax — warp w owns the TMEM lane quarter (w & 3) and the key-column half (w >> 2) of every 128-key block,
-// i.e. TWO threads per query row (round 1 had one: the softmax chain tcgen05.ld -> max -> exp -> pack -> st.shared of
-// 128 columns per thread was the critical path of a CTA, 29 % issue-slot utilisation); warp 8: TMA + MMA + TMEM alloc
-constexpr int kFlashThreads = 288;
+constexpr int kFlashThreads = 160;  // warps 0-3: softmax (one TMEM lane quarter each); warp 4: TMA + MMA + TMEM alloc
 constexpr int kFlashIdentBytes = 30 * 256;
 
 struct FlashParams {
@@ -42,8 +39,7 @@ struct FlashCfg {
   static constexpr int OFF_Q = 0, OFF_KV = TILE;               // stage s: K at OFF_KV + s*2*TILE, V right behind it
   static constexpr int OFF_P = OFF_KV + 4 * TILE;              // P block (fp16 [128][128]); first the bias tile (BMMA)
   static constexpr int OFF_ID = OFF_P + 32768;
-  static constexpr int OFF_X = OFF_ID + (BMMA ? kFlashIdentBytes : 0);   // row-pair exchange: 2 parities x 2 halves x 128 rows x fp32
-  static constexpr int OFF_BAR = OFF_X + 2048;
+  static constexpr int OFF_BAR = OFF_ID + (BMMA ? kFlashIdentBytes : 0);
   static constexpr int SMEM_BYTES = OFF_BAR + 128;
   static constexpr uint32_t SWZ = (HD == 64) ? SWZ_128B : SWZ_64B;
   static constexpr uint32_t SBO = 8 * ROWB;
@@ -51,7 +47,7 @@ struct FlashCfg {
 };
 
 template <int HD, bool BMMA>
-__global__ void __launch_bounds__(kFlashThreads, 2)
+__global__ void __launch_bounds__(kFlashThreads)
 attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmBias,
                       const FlashParams p) {
   griddep_launch();  // dependents (GEMMs) may start their prologue under this kernel's tail
@@ -67,10 +63,10 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
   const int row0 = prob * p.L;
   const int nblk = (p.L + 127) >> 7;
 
-  if (BMMA && warp < 8) {  // identity strip (attention_fwd.cu): zeros with a 16 x 16 identity block at groups 14-15
+  if (BMMA && warp < 4) {  // identity strip (attention_fwd.cu): zeros with a 16 x 16 identity block at groups 14-15
     uint8_t* id = smem + Cfg::OFF_ID;
-    for (int i = threadIdx.x; i < kFlashIdentBytes / 16; i += 256) reinterpret_cast<uint4*>(id)[i] = make_uint4(0u, 0u, 0u, 0u);
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    for (int i = threadIdx.x; i < kFlashIdentBytes / 16; i += 128) reinterpret_cast<uint4*>(id)[i] = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     if (threadIdx.x < 16) {
       const int r = threadIdx.x;
       const int off = r < 8 ? 14 * 256 + r * 16 + r * 2 : 15 * 256 + 128 + (r - 8) * 16 + (r - 8) * 2;
@@ -78,7 +74,7 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
     }
     fence_proxy_async_smem();
   }
-  if (warp == 8) {
+  if (warp == 4) {
     if (lane == 0) {
       tma_prefetch_desc(&tmQKV);
       if (BMMA) tma_prefetch_desc(&tmBias);
@@ -86,7 +82,7 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       mbar_init(bars + 1, 1);
       mbar_init(bars + 2, 1);
       mbar_init(bars + 3, 1);
-      mbar_init(bars + 4, 256);
+      mbar_init(bars + 4, 128);
       mbar_init(bars + 5, 1);
       fence_barrier_init();
     }
@@ -99,7 +95,7 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == 4) {
     if (lane == 0) {
       const int bcls = (BMMA && p.prob_class) ? p.prob_class[prob % p.period] : 0;
       const int brow = (bcls * p.nheads + h) * p.NPb + t * 128;
@@ -167,24 +163,18 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       }
     }
   } else {
-    const int hsel = warp >> 2;                  // key-column half of each block: columns [hsel * 64, hsel * 64 + 64)
-    const int i = (warp & 3) * 32 + lane;        // query row within the tile == TMEM lane
+    const int i = warp * 32 + lane;
     const int qi = t * 128 + i;
-    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    constexpr int HW = HD / 2;                   // O columns rescaled / written by each thread of the row pair
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
     const float sc2 = p.scale * 1.4426950408889634f;  // scores in log2 units
     DropKey dkey{};
     if (p.drop.on) dkey = drop_key(p.drop);
     uint8_t* prow = smem + Cfg::OFF_P + i * 128;
-    float* xch = reinterpret_cast<float*>(smem + Cfg::OFF_X);      // [2][128]: this half's value for the partner thread
-    const int pair_bar = 2 + (warp & 3);                            // named barrier of the two warps that share rows
-    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory"); };
-    float m = -INFINITY, l = 0.f;  // running max (log2 units, common to the pair) and this thread's partial sum
+    float m = -INFINITY, l = 0.f;  // running max (log2 units) and sum
 
     for (int c = 0; c < nblk; ++c) {
       const int nc = min(128, (p.L - c * 128 + 31) & ~31);
       const int nvalid = p.L - c * 128;  // columns >= nvalid are padding
-      const int jlo = hsel * 64, jhi = min(nc, hsel * 64 + 64);
       const float* kb = p.key_bias ? p.key_bias + (size_t)prob * p.NPk + c * 128 : nullptr;
       auto scores = [&](const uint32_t(&sraw)[32], int j0, float(&v)[32]) {
 #pragma unroll
@@ -214,9 +204,9 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       };
       mbar_wait(bars + 3, c & 1, 34);
       tc_fence_after();
-      float mb = -INFINITY;
+      float mb = m;
 #pragma unroll 1
-      for (int j0 = jlo; j0 < jhi; j0 += 32) {   // pass 1: block maximum of this thread's columns
+      for (int j0 = 0; j0 < nc; j0 += 32) {
         uint32_t sraw[32];
         float v[32];
         tmem_ld_32x32(trow + Cfg::COL_S + j0, sraw);
@@ -225,10 +215,6 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
 #pragma unroll
         for (int j = 0; j < 32; ++j) mb = fmaxf(mb, v[j]);
       }
-      // (double-buffered by block parity: the partner may still be reading the previous block's value)
-      xch[((c & 1) * 2 + hsel) * 128 + i] = mb;
-      pair_sync();
-      mb = fmaxf(m, fmaxf(mb, xch[((c & 1) * 2 + (hsel ^ 1)) * 128 + i]));
       const float m_use = mb == -INFINITY ? 0.f : mb;
       const float alpha = exp2f(m - m_use);  // m = -inf on the first block -> 0
       l *= alpha;
@@ -236,18 +222,21 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         mbar_wait(bars + 5, (c - 1) & 1, 35);
         tc_fence_after();
         if (__any_sync(0xffffffffu, alpha != 1.0f)) {
-          uint32_t o[HW];
-          tmem_ld_cols<HW>(trow + Cfg::COL_O + hsel * HW, o);
-          tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < HW; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
-          tmem_st_cols<HW>(trow + Cfg::COL_O + hsel * HW, o);
+          for (int c0 = 0; c0 < HD; c0 += 32) {
+            uint32_t o[32];
+            tmem_ld_32x32(trow + Cfg::COL_O + c0, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+            tmem_st_32x32(trow + Cfg::COL_O + c0, o);
+          }
           tmem_st_wait();
         }
       }
       m = mb;
 #pragma unroll 1
-      for (int j0 = jlo; j0 < jhi; j0 += 32) {   // pass 2: probabilities -> shared memory (fp16, UMMA layout)
+      for (int j0 = 0; j0 < nc; j0 += 32) {
         uint32_t sraw[32];
         float v[32];
         tmem_ld_32x32(trow + Cfg::COL_S + j0, sraw);
@@ -282,24 +271,20 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       mbar_arrive(bars + 4);
     }
 
-    // the row's normaliser = the two partial sums (same running max on both threads)
-    xch[((nblk & 1) * 2 + hsel) * 128 + i] = l;
-    pair_sync();
-    l += xch[((nblk & 1) * 2 + (hsel ^ 1)) * 128 + i];
     mbar_wait(bars + 5, (nblk - 1) & 1, 36);
     tc_fence_after();
     const float inv = 1.f / l;
     const bool valid = qi < p.L;
-    if (valid && hsel == 0 && p.lse)
-      p.lse[(size_t)h * p.rows_total + row0 + qi] = (m == -INFINITY ? 0.f : m) * 0.6931471805599453f + __logf(l);
-    {
-      uint32_t o[HW];
-      tmem_ld_cols<HW>(trow + Cfg::COL_O + hsel * HW, o);
+    if (valid && p.lse) p.lse[(size_t)h * p.rows_total + row0 + qi] = (m == -INFINITY ? 0.f : m) * 0.6931471805599453f + __logf(l);
+#pragma unroll
+    for (int c0 = 0; c0 < HD; c0 += 32) {
+      uint32_t o[32];
+      tmem_ld_32x32(trow + Cfg::COL_O + c0, o);
       tmem_ld_wait();
       if (valid && p.out) {
-        __half* dst = p.out + (size_t)(row0 + qi) * p.ldo + h * HD + hsel * HW;
+        __half* dst = p.out + (size_t)(row0 + qi) * p.ldo + h * HD + c0;
 #pragma unroll
-        for (int j = 0; j < HW / 8; ++j) {
+        for (int j = 0; j < 4; ++j) {
           uint4 u;
           u.x = pack_half2(__uint_as_float(o[8 * j]) * inv, __uint_as_float(o[8 * j + 1]) * inv);
           u.y = pack_half2(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv);
@@ -309,9 +294,9 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         }
       }
       if (valid && p.out32) {
-        float* dst = p.out32 + (size_t)(row0 + qi) * p.ldo32 + h * HD + hsel * HW;
+        float* dst = p.out32 + (size_t)(row0 + qi) * p.ldo32 + h * HD + c0;
 #pragma unroll
-        for (int j = 0; j < HW / 4; ++j)
+        for (int j = 0; j < 8; ++j)
           reinterpret_cast<float4*>(dst)[j] =
               make_float4(__uint_as_float(o[4 * j]) * inv, __uint_as_float(o[4 * j + 1]) * inv,
                           __uint_as_float(o[4 * j + 2]) * inv, __uint_as_float(o[4 * j + 3]) * inv);
@@ -320,7 +305,7 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc<256>(tmem);
+  if (warp == 4) tmem_dealloc<256>(tmem);
 }
 
 template <int HD, bool BMMA>
