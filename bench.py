@@ -412,8 +412,10 @@ def committed_traffic():
     dram__bytes_write.sum -k regex:gemm_f16` over one training step).  ncu cannot run inside a timed bench."""
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "r2_gemm_dram.json")))
-        return d["dram_bytes_per_launch"], (f"profiles/r2_gemm_dram.json: {d['launches']} gemm_f16 launches of one step, "
-                                           f"algorithmic bytes/launch {d.get('algorithmic_bytes_per_launch')}")
+        return d["dram_bytes_per_launch"], (f"profiles/r2_gemm_dram.json: ncu dram__bytes_read.sum + dram__bytes_write.sum averaged "
+                                           f"over the {d['launches']} gemm_f16 launches of one training step (read "
+                                           f"{d['dram_bytes_read_per_launch']}, write {d['dram_bytes_write_per_launch']}: outputs of "
+                                           f"these short kernels are still L2-resident when the kernel ends)")
     except Exception:
         return None, "no committed ncu DRAM capture"
 
