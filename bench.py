@@ -664,6 +664,8 @@ def run_check_dp(a):
     g_dp = ar.grad.clone() / scale
     torch.cuda.synchronize()
     res = {}
+    hooks = (ar.on_swin_backward, ar.on_swin_stage)
+    ar.on_swin_backward = ar.on_swin_stage = None   # the single-process reference run must not issue collectives
     if rank == 0:
         allb = [rank_batch(r) for r in range(world)]
         cat = {k: torch.cat([b[k] for b, _ in allb]).cuda() for k in ("img", "txt", "mask", "ans_mtm")}
@@ -680,6 +682,7 @@ def run_check_dp(a):
         res["grad_norm"] = float(g_1.norm().item())
         del out, tot, g_1, cat
     del g_dp
+    ar.on_swin_backward, ar.on_swin_stage = hooks
     torch.cuda.empty_cache()
     dist.barrier()
     # ---- 3 real training steps, per-rank data: weights must stay bit-identical across ranks

@@ -264,7 +264,10 @@ int lav_xent_bwd(const float* logits, int64_t ld, const int64_t* labels, int row
  * `state` is a caller-owned fp32[16] device array: [0] loss scale, [1] growth tracker, [2] optimizer step count,
  * [3] sum of squares and [4] non-finite count of the (scaled) gradient — both accumulated by lav_grad_stats and
  * cleared by lav_adamw_step —, [5] unscaled gradient norm (out), [6] found_inf (out), [7..9] internal. */
-int lav_grad_stats(const float* grad, int64_t n, float* state, void* stream);
+int lav_grad_stats(const float* grad, int64_t n, float* state, float* ws, int64_t ws_floats, void* stream);
+/* ws (may be NULL): caller-owned fp32 scratch of ws_floats >= 8 * SM count + 1 elements, ZEROED ONCE by the caller: per-block
+ * partial sums + a ticket counter.  With it the sum of squares is reduced in a fixed order (bit-identical on every
+ * data-parallel rank, so replicas stay bit-identical after the clip); without it the blocks use atomicAdd. */
 /* group_of_block[i] = parameter group (0..ngroups-1) of elements [8i, 8i+8), 255 = no gradient (skipped);
  * group_lr / group_wd are fp32 device arrays indexed by group.  The update is skipped when found_inf. */
 int lav_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,

@@ -83,7 +83,7 @@ SIGNATURES = {
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lav_xent_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_void_p]),
-    "lav_grad_stats": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "lav_grad_stats": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p]),
     "lav_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_float,
                                c_float, c_float, c_float, c_void_p, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p,
                                c_int, c_void_p]),

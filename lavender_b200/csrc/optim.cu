@@ -11,7 +11,11 @@ namespace lav {
 constexpr int ST_SCALE = 0, ST_TRACK = 1, ST_STEP = 2, ST_SUMSQ = 3, ST_NONFIN = 4, ST_NORM = 5, ST_FOUND = 6, ST_GMUL = 7,
               ST_BC1 = 8, ST_BC2S = 9;
 
-__global__ void __launch_bounds__(256) grad_stats_kernel(const float* __restrict__ g, int64_t n, float* state) {
+// Sum of squares + non-finite check of the gradient arena.  DETERMINISTIC: every block writes its partial sum to
+// ws[blockIdx.x] and the last block to finish (ticket counter in ws[gridDim.x]) adds the partials in index order, so every
+// data-parallel rank computes bit-identical norms / clip factors from the identical all-reduced gradients and the replicas'
+// weights stay bit-identical (an atomicAdd per block would make the summation order - and the last bits - vary per rank).
+__global__ void __launch_bounds__(256) grad_stats_kernel(const float* __restrict__ g, int64_t n, float* state, float* ws) {
   float ss = 0.f;
   int bad = 0;
   const int64_t n4 = n >> 2;
@@ -28,6 +32,7 @@ __global__ void __launch_bounds__(256) grad_stats_kernel(const float* __restrict
   bad = __any_sync(0xffffffffu, bad);
   __shared__ float s_ss[8];
   __shared__ int s_bad[8];
+  __shared__ bool s_last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane == 0) s_ss[warp] = ss, s_bad[warp] = bad;
   __syncthreads();
@@ -35,8 +40,27 @@ __global__ void __launch_bounds__(256) grad_stats_kernel(const float* __restrict
     float t = 0.f;
     int b = 0;
     for (int w = 0; w < 8; ++w) t += s_ss[w], b |= s_bad[w];
-    atomicAdd(state + ST_SUMSQ, t);
-    if (b || !isfinite(t)) atomicAdd(state + ST_NONFIN, 1.0f);
+    if (b || !isfinite(t)) atomicAdd(state + ST_NONFIN, 1.0f);   // (a flag: order-independent)
+    if (ws == nullptr) {
+      atomicAdd(state + ST_SUMSQ, t);
+      s_last = false;
+    } else {
+      ws[blockIdx.x] = t;
+      __threadfence();
+      const unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(ws + gridDim.x), 1u);
+      s_last = ticket == gridDim.x - 1;
+    }
+  }
+  __syncthreads();
+  if (s_last && warp == 0) {   // fixed-order tree over the partials: lane l adds ws[l], ws[l + 32], ...; then a shuffle tree
+    __threadfence();
+    float t = 0.f;
+    for (unsigned i = lane; i < gridDim.x; i += 32) t += __ldcg(ws + i);
+    t = warp_sum(t);
+    if (lane == 0) {
+      state[ST_SUMSQ] += t;
+      *reinterpret_cast<unsigned*>(ws + gridDim.x) = 0u;   // ready for the next step
+    }
   }
 }
 
@@ -130,11 +154,15 @@ adamw_update_kernel(float* __restrict__ p, const float* __restrict__ g, float* _
 
 using namespace lav;
 
-extern "C" int lav_grad_stats(const float* grad, int64_t n, float* state, void* stream) {
+extern "C" int lav_grad_stats(const float* grad, int64_t n, float* state, float* ws, int64_t ws_floats, void* stream) {
   LAV_REQUIRE(grad && state && ((uintptr_t)grad % 16) == 0, "lav_grad_stats: bad arguments");
   if (n <= 0) return LAV_OK;
-  const int grid = (int)std::min<int64_t>((n / 4 + 255) / 256 + 1, (int64_t)sm_count() * 8);
-  grad_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(grad, n, state);
+  int grid = (int)std::min<int64_t>((n / 4 + 255) / 256 + 1, (int64_t)sm_count() * 8);
+  if (ws) {
+    LAV_REQUIRE(ws_floats >= 2, "lav_grad_stats: workspace too small");
+    grid = (int)std::min<int64_t>(grid, ws_floats - 1);
+  }
+  grad_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(grad, n, state, ws);
   LAV_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return LAV_OK;

@@ -319,10 +319,12 @@ def xent_bwd(logits, labels, ignore_index, row_lse, gout, count, d32=None, d16=N
     L.check(rc, "lav_xent_bwd")
 
 
-def grad_stats(grad, state):
+def grad_stats(grad, state, ws=None):
+    """ws: zero-initialised fp32 scratch (>= 8 * SMs + 1) for the deterministic fixed-order reduction (see the header)."""
     assert grad.dtype == torch.float32 and grad.is_contiguous() and state.dtype == torch.float32
     with _Timed("optimizer"):
-        rc = L.lib().lav_grad_stats(_p(grad), grad.numel(), _p(state), _stream())
+        rc = L.lib().lav_grad_stats(_p(grad), grad.numel(), _p(state), _p(ws), ws.numel() if ws is not None else 0,
+                                    _stream())
     L.check(rc, "lav_grad_stats")
 
 

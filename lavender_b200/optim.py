@@ -101,6 +101,8 @@ class FlatAdamW(torch.optim.Optimizer):
         # per kernel group: non-skipped steps taken before its first update (-1 = not started; set by the kernel)
         self.group_step0 = torch.full((n,), -1.0, dtype=torch.float32, device=dev)
         self.group_bc = torch.zeros(2 * n, dtype=torch.float32, device=dev)
+        # scratch of the deterministic gradient-norm reduction (per-block partials + ticket counter; zeroed once)
+        self.stats_ws = torch.zeros(8 * 160 + 1, dtype=torch.float32, device=dev) if cuda else None
 
     def _refresh_active(self):
         """Blocks of parameters whose .grad is None are skipped (torch semantics), e.g. emb_odr / unused heads."""
@@ -141,7 +143,7 @@ class FlatAdamW(torch.optim.Optimizer):
         sc = self.scaler
         fresh16 = ar._ver16 is not None and ar._ver16 == ar._version()
         ng = max(1, len(self._kgroups))
-        ops.grad_stats(ar.grad, sc.state)
+        ops.grad_stats(ar.grad, sc.state, self.stats_ws)
         ops.adamw_step(ar.flat, ar.grad, self.exp_avg, self.exp_avg_sq, self.group_of_block, self.hyper[0, :ng],
                        self.hyper[1, :ng], sc.state, beta1=b1, beta2=b2, eps=self.param_groups[0]["eps"],
                        max_grad_norm=self.max_grad_norm, growth_factor=sc.growth_factor,
