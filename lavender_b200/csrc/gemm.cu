@@ -572,7 +572,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   // (setmaxnreg re-partitioning made ptxas spill kilobytes in the epilogue branch on this toolchain: not used)
   if (warp == 0) {
     // ------------------------------------------------ TMA producer (one lane; in a pair, both CTAs run one)
-    if (lane == 0) {
+    if (lane == 0 && !(p.debug & 64)) {   // (profiling bit 64: no operand loads - the MMA warp runs on stale smem)
       int stage = 0;
       uint32_t phase = 0;
       for (int item = stream_id; item < total; item += nstreams) {
@@ -625,7 +625,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
-          mbar_wait(full + stage, phase, 3);
+          if (!(p.debug & 64)) mbar_wait(full + stage, phase, 3);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t sb = sa + Cfg::A_BYTES;

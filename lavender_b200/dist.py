@@ -202,19 +202,25 @@ class GradSync:
                 t.div_(self.world)
 
     def _side(self, spans):
-        """Reduce `spans` on the communication stream, ordered after everything enqueued on the current stream so far
-        (incl. the weight-gradient side stream, joined by finalize_grads)."""
-        self.arena.finalize_grads()
+        """Reduce `spans` on the communication stream, ordered after everything enqueued so far on the current stream AND
+        on the weight-gradient side stream.  The critical path itself does not wait for the weight gradients here (joining
+        them into it at both overlap points cost ~0.5 ms per step); the span's gradients are all written by native
+        kernels straight into the arena, so no autograd-side copy (finalize_grads) is needed before the reduction."""
         if self.arena.grad.is_cuda:
+            from . import streams
             if self._stream is None:
                 self._stream = torch.cuda.Stream()
                 self._event = torch.cuda.Event()
             cur = torch.cuda.current_stream()
             self._stream.wait_stream(cur)
+            wg = streams.pending_stream(self.arena.grad.device)
+            if wg is not None:
+                self._stream.wait_stream(wg)
             with torch.cuda.stream(self._stream):
                 self._reduce(spans)
                 self._event.record(self._stream)
         else:
+            self.arena.finalize_grads()
             self._reduce(spans)
 
     def start_early(self):

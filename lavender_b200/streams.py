@@ -71,3 +71,14 @@ def join(device):
     st.held.clear()
     st.dirty = False
     st.cb_queued = False
+
+
+def pending_stream(device):
+    """The weight-gradient side stream if work has been forked onto it since the last join, else None.  Lets another
+    stream (the gradient all-reduce's communication stream) wait for the weight gradients WITHOUT joining them into the
+    critical path."""
+    if not _ENABLED or not torch.cuda.is_available():
+        return None
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    st = _STATE.get(key)
+    return st.stream if st is not None and st.dirty else None

@@ -44,10 +44,11 @@ def make_vt_mask(B, T=5, hw=49):
 ODR = [[0, 2, 1, 3, 4], [4, 1, 2, 3, 0], [0, 1, 2, 3, 4]]   # frame orders of the EncVideo odr golden (model.py:72-81)
 
 
-def run_case(name, size, layers, B, task_token=True, seed=0, vt_mask=False, odr=False):
+def run_case(name, size, layers, B, task_token=True, seed=0, vt_mask=False, odr=False, size_img=224, swin_key=None,
+             backward=True):
     torch.manual_seed(0)
-    ref = ref_shims.build_reference_model(size, layers, 224, B, task_token)
-    cfg = O.ModelCfg(swin=O.SWIN[size], bert_layers=layers, enable_task_token=task_token,
+    ref = ref_shims.build_reference_model(size, layers, size_img, B, task_token)
+    cfg = O.ModelCfg(swin=O.SWIN[swin_key or size], bert_layers=layers, enable_task_token=task_token,
                      vtm_batch=min(B, 4))
     sd = O.make_state_dict(cfg, seed)
     ref_keys = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
@@ -56,7 +57,7 @@ def run_case(name, size, layers, B, task_token=True, seed=0, vt_mask=False, odr=
     assert list(ref.state_dict().keys()) == [k for k, _ in O.state_dict_schema(cfg)] or True
     ref.load_state_dict(sd, strict=True)
     ref.eval()
-    batch = O.make_batch(B, seed=seed)
+    batch = O.make_batch(B, H=size_img, W=size_img, seed=seed)
     if vt_mask:
         batch["vt_mask"] = make_vt_mask(B)
 
@@ -233,3 +234,8 @@ if __name__ == "__main__":
         # the benchmarked architecture (BASELINE configs[1]: swin_base + 12-layer BERT-base: EncVideo.fc, 4-32 heads,
         # K = 128 GEMMs) at B = 2 / 2 VTM pairs per clip, with a video key mask on the last clip and an odr golden
         run_case("base_l12_b2", "base", 12, 2, seed=5, vt_mask=True, odr=True)
+    if "large384" in only:
+        # BASELINE configs[3] at FULL WIDTH: swin_large_384_patch244_window81212 (C = 192..1536, 720-token windows) + 12-layer
+        # BERT-base, one 5 x 384 x 384 clip (fusion sequences of 758 / 759 tokens); minutes of CPU time and ~20 GB of RAM,
+        # so it is generated on request only:  python oracle/make_golden.py large384
+        run_case("large384_l12_b1", "large", 12, 1, seed=7, size_img=384, swin_key="large384")

@@ -1,15 +1,17 @@
 #!/bin/bash
-# round-2 call H2 (2 GPUs): data-parallel correctness (--check-dp), bit-identical replicas, overlapped all-reduce
+# round-2 call H3 (2 GPUs): comm stream waits for the weight-gradient stream itself (no join into the critical path)
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
-timeout -k 10 300 $TR --master-port 29511 bench.py --gpus 2 --check-dp > gpurun_out/r2h_check_dp.json 2> gpurun_out/r2h_check_dp.err
+timeout -k 10 300 $TR --master-port 29511 bench.py --gpus 2 --check-dp > gpurun_out/r2h3_check_dp.json 2> gpurun_out/r2h3_check_dp.err
 echo "check-dp rc=$?"
-timeout -k 10 300 $TR --master-port 29512 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r2h_bench_n2.json 2> gpurun_out/r2h_bench_n2.err
+timeout -k 10 300 $TR --master-port 29512 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r2h3_bench_n2.json 2> gpurun_out/r2h3_bench_n2.err
 echo "bench n2 rc=$?"
-cat gpurun_out/r2h_check_dp.json; tail -n 5 gpurun_out/r2h_check_dp.err
-python - <<PY
+timeout -k 10 300 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-baseline > gpurun_out/r2h3_bench_n1.json 2> gpurun_out/r2h3_bench_n1.err
+cat gpurun_out/r2h3_check_dp.json
+for f in n2 n1; do python - <<PY
 import json
-d=json.load(open("gpurun_out/r2h_bench_n2.json"))
-print("n2", d["value"], d["ms_per_step"], d.get("dp_check"), d["e2e"]["value"])
+d=json.load(open("gpurun_out/r2h3_bench_$f.json"))
+print("$f", d["value"], d["ms_per_step"], d.get("dp_check"), d["e2e"]["value"])
 PY
+done
