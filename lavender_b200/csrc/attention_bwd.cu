@@ -42,8 +42,9 @@ template <int HD, bool BMMA>
 struct AttnBwdCfg {
   static constexpr int ROWB = HD * 2;
   static constexpr int TILE = 128 * ROWB;
-  static constexpr int OFF_K = 0, OFF_V = TILE, OFF_Q = 2 * TILE, OFF_DO = 4 * TILE;  // Q, dO double-buffered
-  static constexpr int OFF_P = 6 * TILE, OFF_DS = OFF_P + 32768;
+  // K / V double-buffered by work item (persistent CTAs prefetch the next item's chunk), Q / dO by (item, query tile) step
+  static constexpr int OFF_K = 0, OFF_V = 2 * TILE, OFF_Q = 4 * TILE, OFF_DO = 6 * TILE;
+  static constexpr int OFF_P = 8 * TILE, OFF_DS = OFF_P + 32768;
   static constexpr int OFF_BIAS = OFF_DS + 32768;                                     // 2 x [128][128] fp16
   static constexpr int OFF_ID = OFF_BIAS + (BMMA ? 65536 : 0);
   static constexpr int OFF_BAR = OFF_ID + (BMMA ? kIdentBytesB : 0);
@@ -61,14 +62,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   using Cfg = AttnBwdCfg<HD, BMMA>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);  // 0 kv | 1,2 q/dO buf | 3 S,dP | 4 P,dS | 5 mma2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  // barriers: 0,1 K/V buffer | 2,3 Q/dO(/bias) buffer | 4 S,dP ready | 5 P,dS ready | 6 dV,dK,dQ MMAs done | 7 dK,dV read out
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c = blockIdx.x, h = blockIdx.y, prob = blockIdx.z;
-  const int row0 = prob * p.L;
+  // PERSISTENT: one CTA per SM walks work items (key chunk c, head h, problem) = blockIdx.x, + gridDim.x, ...; an item is
+  // nqt steps (query tiles).  Round 1 launched one CTA per item: with nqt = 2-3 the per-CTA prologue (512-column TMEM
+  // allocation, identity strip, barriers), the first K/V/Q/dO/bias loads and the dK/dV read-out were ~half of a CTA's life
+  // and nothing overlapped them at 1 CTA/SM.  Now the next item's operands are prefetched and its S / dP products issued
+  // while the softmax warps finish the current item.
+  const int nkc = (p.L + 127) / 128;
   const int nqt = (p.L + 127) / 128;
-  const int jmax = min(128, (p.L - c * 128 + 31) & ~31);  // key columns of this chunk that can hold a valid key
+  const int nitems = nkc * p.nheads * p.nprob;
+  auto item_c = [&](int it) { return it % nkc; };
+  auto item_h = [&](int it) { return (it / nkc) % p.nheads; };
+  auto item_prob = [&](int it) { return it / (nkc * p.nheads); };
 
   if (BMMA && warp < 8) {  // identity strip (zeros with a 16 x 16 identity block at groups 14-15), as in attention_fwd.cu
     uint8_t* id = smem + Cfg::OFF_ID;
@@ -91,8 +100,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       mbar_init(bars + 1, 1);
       mbar_init(bars + 2, 1);
       mbar_init(bars + 3, 1);
-      mbar_init(bars + 4, 256);
-      mbar_init(bars + 5, 1);
+      mbar_init(bars + 4, 1);
+      mbar_init(bars + 5, 256);
+      mbar_init(bars + 6, 1);
+      mbar_init(bars + 7, 256);
       fence_barrier_init();
     }
     __syncwarp();
@@ -106,41 +117,47 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
   if (warp == 8) {
     if (lane == 0) {
-      const int bcls = (BMMA && p.prob_class) ? p.prob_class[prob % p.period] : 0;
-      auto load_q = [&](int t) {
-        const int b = t & 1;
-        mbar_arrive_expect_tx(bars + 1 + b, 2 * Cfg::TILE + (BMMA ? 32768 : 0));
-        tma_load_2d(smem + Cfg::OFF_Q + b * Cfg::TILE, &tmQKV, bars + 1 + b, p.q_off + h * HD, row0 + t * 128);
-        tma_load_2d(smem + Cfg::OFF_DO + b * Cfg::TILE, &tmDO, bars + 1 + b, h * HD, row0 + t * 128);
-        if (BMMA) {  // bias rows t*128.., key columns c*128..: two boxes of [128 rows x 64 columns]
-          const int brow = (bcls * p.nheads + h) * p.NPb + t * 128;
-          tma_load_2d(smem + Cfg::OFF_BIAS + b * 32768, &tmBias, bars + 1 + b, c * 128, brow);
-          tma_load_2d(smem + Cfg::OFF_BIAS + b * 32768 + 16384, &tmBias, bars + 1 + b, c * 128 + 64, brow);
-        }
-      };
-      mbar_arrive_expect_tx(bars + 0, 2 * Cfg::TILE);
-      tma_load_2d(smem + Cfg::OFF_K, &tmQKV, bars + 0, p.k_off + h * HD, row0 + c * 128);
-      tma_load_2d(smem + Cfg::OFF_V, &tmQKV, bars + 0, p.v_off + h * HD, row0 + c * 128);
-      load_q(0);
-      if (nqt > 1) load_q(1);
-      mbar_wait(bars + 0, 0, 20);
-      const uint32_t id_s = make_idesc_f16(128, jmax, 0, 0);      // S / dP : K-major x K-major, narrow last chunk
       constexpr uint32_t id_t = make_idesc_f16(128, HD, 1, 1);    // dV / dK: MN-major A (P/dS transposed), MN-major B
       constexpr uint32_t id_q = make_idesc_f16(128, HD, 0, 1);    // dQ     : K-major A (dS), MN-major B (K)
-      const uint32_t sk = smem_u32(smem + Cfg::OFF_K), sv = smem_u32(smem + Cfg::OFF_V);
       const uint32_t sp = smem_u32(smem + Cfg::OFF_P), sds = smem_u32(smem + Cfg::OFF_DS);
-      // S_t = Q_t K^T (+ I * Bias_t), dP_t = dO_t V^T.  Issued one query tile AHEAD: the softmax warps have consumed
-      // S / dP of tile t when they publish P / dS, so the tile-(t+1) products run under their dQ read-out.
-      auto issue_s_dp = [&](int t) {
-        const int b = t & 1;
+      const int nmine = blockIdx.x < nitems ? (nitems - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;   // items of this CTA
+      const int nsteps = nmine * nqt;
+      auto item_of = [&](int k) { return (int)blockIdx.x + k * (int)gridDim.x; };
+      auto jmax_of = [&](int it) { return min(128, (p.L - item_c(it) * 128 + 31) & ~31); };
+      auto load_kv = [&](int k) {   // item ordinal k -> K/V buffer k & 1
+        const int it = item_of(k), kb = k & 1;
+        const int row0 = item_prob(it) * p.L;
+        mbar_arrive_expect_tx(bars + kb, 2 * Cfg::TILE);
+        tma_load_2d(smem + Cfg::OFF_K + kb * Cfg::TILE, &tmQKV, bars + kb, p.k_off + item_h(it) * HD, row0 + item_c(it) * 128);
+        tma_load_2d(smem + Cfg::OFF_V + kb * Cfg::TILE, &tmQKV, bars + kb, p.v_off + item_h(it) * HD, row0 + item_c(it) * 128);
+      };
+      auto load_q = [&](int s) {    // step s = (item ordinal s / nqt, query tile s % nqt) -> Q/dO/bias buffer s & 1
+        const int it = item_of(s / nqt), t = s % nqt, b = s & 1;
+        const int h = item_h(it), row0 = item_prob(it) * p.L;
+        mbar_arrive_expect_tx(bars + 2 + b, 2 * Cfg::TILE + (BMMA ? 32768 : 0));
+        tma_load_2d(smem + Cfg::OFF_Q + b * Cfg::TILE, &tmQKV, bars + 2 + b, p.q_off + h * HD, row0 + t * 128);
+        tma_load_2d(smem + Cfg::OFF_DO + b * Cfg::TILE, &tmDO, bars + 2 + b, h * HD, row0 + t * 128);
+        if (BMMA) {  // bias rows t*128.., key columns c*128..: two boxes of [128 rows x 64 columns]
+          const int bcls = p.prob_class ? p.prob_class[item_prob(it) % p.period] : 0;
+          const int brow = (bcls * p.nheads + h) * p.NPb + t * 128;
+          tma_load_2d(smem + Cfg::OFF_BIAS + b * 32768, &tmBias, bars + 2 + b, item_c(it) * 128, brow);
+          tma_load_2d(smem + Cfg::OFF_BIAS + b * 32768 + 16384, &tmBias, bars + 2 + b, item_c(it) * 128 + 64, brow);
+        }
+      };
+      // S = Q K^T (+ I * Bias), dP = dO V^T of step s.  Issued one step AHEAD of the softmax warps (also across items).
+      auto issue_s_dp = [&](int s) {
+        const int k = s / nqt, b = s & 1, kb = k & 1;
         const uint32_t sq = smem_u32(smem + Cfg::OFF_Q + b * Cfg::TILE);
         const uint32_t sdo = smem_u32(smem + Cfg::OFF_DO + b * Cfg::TILE);
-        mbar_wait(bars + 1 + b, (t >> 1) & 1, 21);
+        const uint32_t sk = smem_u32(smem + Cfg::OFF_K + kb * Cfg::TILE), sv = smem_u32(smem + Cfg::OFF_V + kb * Cfg::TILE);
+        if (s % nqt == 0) mbar_wait(bars + kb, (k >> 1) & 1, 20);   // first step of an item: its K / V chunk has landed
+        mbar_wait(bars + 2 + b, (s >> 1) & 1, 21);
         tc_fence_after();
+        const uint32_t id_s = make_idesc_f16(128, jmax_of(item_of(k)), 0, 0);  // K-major x K-major, narrow last chunk
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          umma_f16_ss(tmem + Cfg::COL_S, make_smem_desc(sq + k * 32, 0, Cfg::SBO, Cfg::SWZ),
-                      make_smem_desc(sk + k * 32, 0, Cfg::SBO, Cfg::SWZ), id_s, k > 0);
+        for (int kk = 0; kk < HD / 16; ++kk)
+          umma_f16_ss(tmem + Cfg::COL_S, make_smem_desc(sq + kk * 32, 0, Cfg::SBO, Cfg::SWZ),
+                      make_smem_desc(sk + kk * 32, 0, Cfg::SBO, Cfg::SWZ), id_s, kk > 0);
         if (BMMA) {  // S += I * Bias
           constexpr uint32_t id_b = make_idesc_f16(128, 128, 0, 1);
           const uint32_t sid = smem_u32(smem + Cfg::OFF_ID), sbias = smem_u32(smem + Cfg::OFF_BIAS + b * 32768);
@@ -150,36 +167,46 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                         make_smem_desc(sbias + kk * 2048, 16384, 1024, SWZ_128B), id_b, 1u);
         }
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          umma_f16_ss(tmem + Cfg::COL_DP, make_smem_desc(sdo + k * 32, 0, Cfg::SBO, Cfg::SWZ),
-                      make_smem_desc(sv + k * 32, 0, Cfg::SBO, Cfg::SWZ), id_s, k > 0);
-        umma_commit(bars + 3);
+        for (int kk = 0; kk < HD / 16; ++kk)
+          umma_f16_ss(tmem + Cfg::COL_DP, make_smem_desc(sdo + kk * 32, 0, Cfg::SBO, Cfg::SWZ),
+                      make_smem_desc(sv + kk * 32, 0, Cfg::SBO, Cfg::SWZ), id_s, kk > 0);
+        umma_commit(bars + 4);
       };
-      issue_s_dp(0);
-      for (int t = 0; t < nqt; ++t) {
-        const int b = t & 1;
+      if (nsteps > 0) {
+        load_kv(0);
+        load_q(0);
+        if (nsteps > 1) load_q(1);
+        if (nmine > 1) load_kv(1);
+        issue_s_dp(0);
+      }
+      for (int s = 0; s < nsteps; ++s) {
+        const int k = s / nqt, t = s % nqt, b = s & 1, kb = k & 1;
+        const int jmax = jmax_of(item_of(k));
         const uint32_t sq = smem_u32(smem + Cfg::OFF_Q + b * Cfg::TILE);
         const uint32_t sdo = smem_u32(smem + Cfg::OFF_DO + b * Cfg::TILE);
-        mbar_wait(bars + 4, t & 1, 22);
+        const uint32_t sk = smem_u32(smem + Cfg::OFF_K + kb * Cfg::TILE);
+        mbar_wait(bars + 5, s & 1, 22);       // P, dS of this step are in shared memory
+        if (t == 0 && k > 0) mbar_wait(bars + 7, (k - 1) & 1, 26);   // the previous item's dK / dV have been read out of TMEM
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {  // contraction over the 128 query rows, 16 per MMA
-          const uint64_t b_do = make_smem_desc(sdo + k * 16 * Cfg::ROWB, 0, Cfg::SBO, Cfg::SWZ);
-          const uint64_t b_q = make_smem_desc(sq + k * 16 * Cfg::ROWB, 0, Cfg::SBO, Cfg::SWZ);
-          umma_f16_ss(tmem + Cfg::COL_DV, make_smem_desc(sp + k * 2048, 16384, 1024, SWZ_128B), b_do, id_t,
-                      (t > 0 || k > 0));
-          umma_f16_ss(tmem + Cfg::COL_DK, make_smem_desc(sds + k * 2048, 16384, 1024, SWZ_128B), b_q, id_t,
-                      (t > 0 || k > 0));
+        for (int kk = 0; kk < 8; ++kk) {  // contraction over the 128 query rows, 16 per MMA
+          const uint64_t b_do = make_smem_desc(sdo + kk * 16 * Cfg::ROWB, 0, Cfg::SBO, Cfg::SWZ);
+          const uint64_t b_q = make_smem_desc(sq + kk * 16 * Cfg::ROWB, 0, Cfg::SBO, Cfg::SWZ);
+          umma_f16_ss(tmem + Cfg::COL_DV, make_smem_desc(sp + kk * 2048, 16384, 1024, SWZ_128B), b_do, id_t,
+                      (t > 0 || kk > 0));
+          umma_f16_ss(tmem + Cfg::COL_DK, make_smem_desc(sds + kk * 2048, 16384, 1024, SWZ_128B), b_q, id_t,
+                      (t > 0 || kk > 0));
         }
 #pragma unroll 4
-        for (int k = 0; k < jmax / 16; ++k)  // contraction over the (valid) keys of this chunk
-          umma_f16_ss(tmem + Cfg::COL_DQ, make_smem_desc(sds + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024, SWZ_128B),
-                      make_smem_desc(sk + k * 16 * Cfg::ROWB, 0, Cfg::SBO, Cfg::SWZ), id_q, k > 0);
-        umma_commit(bars + 5);
-        if (t + 1 < nqt) issue_s_dp(t + 1);
-        if (t + 2 < nqt) {  // refill this Q/dO buffer once the MMAs above have consumed it
-          mbar_wait(bars + 5, t & 1, 23);
-          load_q(t + 2);
+        for (int kk = 0; kk < jmax / 16; ++kk)  // contraction over the (valid) keys of this chunk
+          umma_f16_ss(tmem + Cfg::COL_DQ, make_smem_desc(sds + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024, SWZ_128B),
+                      make_smem_desc(sk + kk * 16 * Cfg::ROWB, 0, Cfg::SBO, Cfg::SWZ), id_q, kk > 0);
+        umma_commit(bars + 6);
+        if (s + 1 < nsteps) issue_s_dp(s + 1);
+        if (s + 2 < nsteps || (t == nqt - 1 && k + 2 < nmine)) {
+          mbar_wait(bars + 6, s & 1, 23);     // the MMAs above have consumed this step's Q / dO buffer (and, on an item's
+          if (s + 2 < nsteps) load_q(s + 2);  // last step, its K / V buffer): refill them for step s + 2 / item k + 2
+          if (t == nqt - 1 && k + 2 < nmine) load_kv(k + 2);
         }
       }
     }
@@ -192,148 +219,156 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     constexpr int HW = HD / 2;  // output columns of dQ / dK / dV handled by each half
     const float sc_log2 = p.scale * 1.4426950408889634f;
-    const int cls = (p.bias16 && p.prob_class) ? p.prob_class[prob % p.period] : 0;
-    const float* kb = p.key_bias ? p.key_bias + (size_t)prob * p.NPk + c * 128 : nullptr;
     uint8_t* prow = smem + Cfg::OFF_P + i * 128;
     uint8_t* dsrow = smem + Cfg::OFF_DS + i * 128;
     DropKey dkey{};
     if (p.drop.on) dkey = drop_key(p.drop);
 
-    for (int t = 0; t < nqt; ++t) {
-      const int qi = t * 128 + i;
-      const bool valid = qi < p.L;
-      float lse_l2 = 0.f, delta = 0.f;
-      if (valid) {  // two scalars per row, requested before the wait on the tensor core
-        lse_l2 = p.lse[(size_t)h * p.rows_total + row0 + qi] * 1.4426950408889634f;
-        delta = p.delta[(size_t)h * p.rows_total + row0 + qi];
-      }
-      const __half* brow = (!BMMA && p.bias16) ? p.bias16 + (((size_t)cls * p.nheads + h) * p.NPb + min(qi, p.NPb - 1)) * p.NPb + c * 128
-                                    : nullptr;
-      __half* dsg = (p.ds_out && valid) ? p.ds_out + (((size_t)prob * p.nheads + h) * p.NPs + qi) * p.NPs + c * 128
-                                        : nullptr;
-      mbar_wait(bars + 3, t & 1, 24);
-      tc_fence_after();
+    int s = 0;   // step counter of this CTA (same sequence as the MMA warp's)
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      const int c = item_c(item), h = item_h(item), prob = item_prob(item);
+      const int row0 = prob * p.L;
+      const int jmax = min(128, (p.L - c * 128 + 31) & ~31);  // key columns of this chunk that can hold a valid key
+      const int cls = (p.bias16 && p.prob_class) ? p.prob_class[prob % p.period] : 0;
+      const float* kb = p.key_bias ? p.key_bias + (size_t)prob * p.NPk + c * 128 : nullptr;
+      for (int t = 0; t < nqt; ++t, ++s) {
+        const int qi = t * 128 + i;
+        const bool valid = qi < p.L;
+        float lse_l2 = 0.f, delta = 0.f;
+        if (valid) {  // two scalars per row, requested before the wait on the tensor core
+          lse_l2 = p.lse[(size_t)h * p.rows_total + row0 + qi] * 1.4426950408889634f;
+          delta = p.delta[(size_t)h * p.rows_total + row0 + qi];
+        }
+        const __half* brow = (!BMMA && p.bias16) ? p.bias16 + (((size_t)cls * p.nheads + h) * p.NPb + min(qi, p.NPb - 1)) * p.NPb + c * 128
+                                      : nullptr;
+        __half* dsg = (p.ds_out && valid) ? p.ds_out + (((size_t)prob * p.nheads + h) * p.NPs + qi) * p.NPs + c * 128
+                                          : nullptr;
+        mbar_wait(bars + 4, s & 1, 24);
+        tc_fence_after();
 #pragma unroll 1
-      for (int j0 = hsel * 64; j0 < min(jmax, hsel * 64 + 64); j0 += 32) {
-        uint32_t s[32], dp[32];
-        tmem_ld_32x32(trow + Cfg::COL_S + j0, s);
-        tmem_ld_32x32(trow + Cfg::COL_DP + j0, dp);
-        tmem_ld_wait();
-        float pv[32], dsv[32];
+        for (int j0 = hsel * 64; j0 < min(jmax, hsel * 64 + 64); j0 += 32) {
+          uint32_t sr[32], dp[32];
+          tmem_ld_32x32(trow + Cfg::COL_S + j0, sr);
+          tmem_ld_32x32(trow + Cfg::COL_DP + j0, dp);
+          tmem_ld_wait();
+          float pv[32], dsv[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) pv[j] = __uint_as_float(s[j]) * sc_log2 - lse_l2;
-        if (brow) {
+          for (int j = 0; j < 32; ++j) pv[j] = __uint_as_float(sr[j]) * sc_log2 - lse_l2;
+          if (brow) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 u = *reinterpret_cast<const uint4*>(brow + j0 + 8 * j);
+              const __half2* hh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float2 f = __half22float2(hh[q]);
+                // the dense bias holds bias / scale (lav_relpos_bias_expand): back to log2 units with scale * log2(e)
+                pv[8 * j + 2 * q] += f.x * sc_log2, pv[8 * j + 2 * q + 1] += f.y * sc_log2;
+              }
+            }
+          }
+          if (kb) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 f = __ldg(reinterpret_cast<const float4*>(kb + j0) + j);
+              pv[4 * j] += f.x * 1.4426950408889634f, pv[4 * j + 1] += f.y * 1.4426950408889634f;
+              pv[4 * j + 2] += f.z * 1.4426950408889634f, pv[4 * j + 3] += f.w * 1.4426950408889634f;
+            }
+          }
+          if (p.causal_from >= 0 && c * 128 + j0 + 31 >= p.causal_from) {  // seq2seq mask, as in attention_flash.cu
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = c * 128 + j0 + j;
+              if (col >= p.causal_from && col > qi) pv[j] = -INFINITY;
+            }
+          }
+          if (!p.drop.on) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float pe = valid ? exp2f(pv[j]) : 0.f;
+              pv[j] = pe;
+              dsv[j] = pe * (__uint_as_float(dp[j]) - delta);
+            }
+          } else {  // O = (keep * P / (1-p)) V: dV uses the dropped P, dP = keep * dP_drop / (1-p), dS = P (dP - delta)
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              const uint32_t m = drop_keep8(dkey, p.drop.thresh, (uint32_t)(row0 + qi), (uint32_t)(((c * 128 + j0) >> 3) + j8),
+                                            (uint32_t)h);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const int j = 8 * j8 + q;
+                const float pe = valid ? exp2f(pv[j]) : 0.f;
+                const float kc = ((m >> q) & 1u) ? p.drop.inv_keep : 0.f;
+                pv[j] = pe * kc;
+                dsv[j] = pe * (kc * __uint_as_float(dp[j]) - delta);
+              }
+            }
+          }
+          uint8_t* pa = prow + (j0 >> 6) * 16384;
+          uint8_t* da = dsrow + (j0 >> 6) * 16384;
+          const int chunk0 = (j0 & 63) >> 3;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            uint4 u = *reinterpret_cast<const uint4*>(brow + j0 + 8 * j);
-            const __half2* hh = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float2 f = __half22float2(hh[q]);
-              // the dense bias holds bias / scale (lav_relpos_bias_expand): back to log2 units with scale * log2(e)
-              pv[8 * j + 2 * q] += f.x * sc_log2, pv[8 * j + 2 * q + 1] += f.y * sc_log2;
-            }
+            uint4 u, w;
+            u.x = pack_half2(pv[8 * j], pv[8 * j + 1]), u.y = pack_half2(pv[8 * j + 2], pv[8 * j + 3]);
+            u.z = pack_half2(pv[8 * j + 4], pv[8 * j + 5]), u.w = pack_half2(pv[8 * j + 6], pv[8 * j + 7]);
+            w.x = pack_half2(dsv[8 * j], dsv[8 * j + 1]), w.y = pack_half2(dsv[8 * j + 2], dsv[8 * j + 3]);
+            w.z = pack_half2(dsv[8 * j + 4], dsv[8 * j + 5]), w.w = pack_half2(dsv[8 * j + 6], dsv[8 * j + 7]);
+            const int off = ((chunk0 + j) ^ (i & 7)) << 4;
+            *reinterpret_cast<uint4*>(pa + off) = u;
+            *reinterpret_cast<uint4*>(da + off) = w;
+            if (dsg) reinterpret_cast<uint4*>(dsg + j0)[j] = w;
           }
         }
-        if (kb) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 f = __ldg(reinterpret_cast<const float4*>(kb + j0) + j);
-            pv[4 * j] += f.x * 1.4426950408889634f, pv[4 * j + 1] += f.y * 1.4426950408889634f;
-            pv[4 * j + 2] += f.z * 1.4426950408889634f, pv[4 * j + 3] += f.w * 1.4426950408889634f;
-          }
-        }
-        if (p.causal_from >= 0 && c * 128 + j0 + 31 >= p.causal_from) {  // seq2seq mask, as in attention_flash.cu
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = c * 128 + j0 + j;
-            if (col >= p.causal_from && col > qi) pv[j] = -INFINITY;
-          }
-        }
-        if (!p.drop.on) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float pe = valid ? exp2f(pv[j]) : 0.f;
-            pv[j] = pe;
-            dsv[j] = pe * (__uint_as_float(dp[j]) - delta);
-          }
-        } else {  // O = (keep * P / (1-p)) V: dV uses the dropped P, dP = keep * dP_drop / (1-p), dS = P (dP - delta)
-#pragma unroll
-          for (int j8 = 0; j8 < 4; ++j8) {
-            const uint32_t m = drop_keep8(dkey, p.drop.thresh, (uint32_t)(row0 + qi), (uint32_t)(((c * 128 + j0) >> 3) + j8),
-                                          (uint32_t)h);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int j = 8 * j8 + q;
-              const float pe = valid ? exp2f(pv[j]) : 0.f;
-              const float kc = ((m >> q) & 1u) ? p.drop.inv_keep : 0.f;
-              pv[j] = pe * kc;
-              dsv[j] = pe * (kc * __uint_as_float(dp[j]) - delta);
-            }
-          }
-        }
-        uint8_t* pa = prow + (j0 >> 6) * 16384;
-        uint8_t* da = dsrow + (j0 >> 6) * 16384;
-        const int chunk0 = (j0 & 63) >> 3;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 u, w;
-          u.x = pack_half2(pv[8 * j], pv[8 * j + 1]), u.y = pack_half2(pv[8 * j + 2], pv[8 * j + 3]);
-          u.z = pack_half2(pv[8 * j + 4], pv[8 * j + 5]), u.w = pack_half2(pv[8 * j + 6], pv[8 * j + 7]);
-          w.x = pack_half2(dsv[8 * j], dsv[8 * j + 1]), w.y = pack_half2(dsv[8 * j + 2], dsv[8 * j + 3]);
-          w.z = pack_half2(dsv[8 * j + 4], dsv[8 * j + 5]), w.w = pack_half2(dsv[8 * j + 6], dsv[8 * j + 7]);
-          const int off = ((chunk0 + j) ^ (i & 7)) << 4;
-          *reinterpret_cast<uint4*>(pa + off) = u;
-          *reinterpret_cast<uint4*>(da + off) = w;
-          if (dsg) reinterpret_cast<uint4*>(dsg + j0)[j] = w;
-        }
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(bars + 4);
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(bars + 5);
 
-      mbar_wait(bars + 5, t & 1, 25);
-      tc_fence_after();
-      {
-        uint32_t o[HW];
-        tmem_ld_cols<HW>(trow + Cfg::COL_DQ + hsel * HW, o);
-        tmem_ld_wait();
-        if (valid) {
-          float* dst = p.dq_acc + (size_t)(row0 + qi) * p.lddq + h * HD + hsel * HW;
+        mbar_wait(bars + 6, s & 1, 25);
+        tc_fence_after();
+        {
+          uint32_t o[HW];
+          tmem_ld_cols<HW>(trow + Cfg::COL_DQ + hsel * HW, o);
+          tmem_ld_wait();
+          if (valid) {
+            float* dst = p.dq_acc + (size_t)(row0 + qi) * p.lddq + h * HD + hsel * HW;
 #pragma unroll
-          for (int j = 0; j < HW / 4; ++j)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j),
-                         "f"(__uint_as_float(o[4 * j]) * p.scale), "f"(__uint_as_float(o[4 * j + 1]) * p.scale),
-                         "f"(__uint_as_float(o[4 * j + 2]) * p.scale), "f"(__uint_as_float(o[4 * j + 3]) * p.scale)
-                         : "memory");
+            for (int j = 0; j < HW / 4; ++j)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j),
+                           "f"(__uint_as_float(o[4 * j]) * p.scale), "f"(__uint_as_float(o[4 * j + 1]) * p.scale),
+                           "f"(__uint_as_float(o[4 * j + 2]) * p.scale), "f"(__uint_as_float(o[4 * j + 3]) * p.scale)
+                           : "memory");
+          }
         }
+        tc_fence_before();
       }
-      tc_fence_before();
-    }
-    // ---- dK_c, dV_c : thread = key row of this chunk
-    const int kj = c * 128 + i;
-    const bool kvalid = kj < p.L;
-    {
-      uint32_t dk[HW], dv[HW];
-      tmem_ld_cols<HW>(trow + Cfg::COL_DK + hsel * HW, dk);
-      tmem_ld_cols<HW>(trow + Cfg::COL_DV + hsel * HW, dv);
-      tmem_ld_wait();
-      if (kvalid) {
-        __half* gk = p.dqkv + (size_t)(row0 + kj) * p.lddqkv + p.k_off + h * HD + hsel * HW;
-        __half* gv = p.dqkv + (size_t)(row0 + kj) * p.lddqkv + p.v_off + h * HD + hsel * HW;
+      // ---- dK_c, dV_c of this item: thread = key row of the chunk (the last step's MMAs have completed: bars + 6 above)
+      const int kj = c * 128 + i;
+      const bool kvalid = kj < p.L;
+      {
+        uint32_t dk[HW], dv[HW];
+        tmem_ld_cols<HW>(trow + Cfg::COL_DK + hsel * HW, dk);
+        tmem_ld_cols<HW>(trow + Cfg::COL_DV + hsel * HW, dv);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(bars + 7);   // the accumulators may be overwritten by the next item's first dV / dK MMAs
+        if (kvalid) {
+          __half* gk = p.dqkv + (size_t)(row0 + kj) * p.lddqkv + p.k_off + h * HD + hsel * HW;
+          __half* gv = p.dqkv + (size_t)(row0 + kj) * p.lddqkv + p.v_off + h * HD + hsel * HW;
 #pragma unroll
-        for (int j = 0; j < HW / 8; ++j) {
-          uint4 u, w;
-          u.x = pack_half2(__uint_as_float(dk[8 * j]) * p.scale, __uint_as_float(dk[8 * j + 1]) * p.scale);
-          u.y = pack_half2(__uint_as_float(dk[8 * j + 2]) * p.scale, __uint_as_float(dk[8 * j + 3]) * p.scale);
-          u.z = pack_half2(__uint_as_float(dk[8 * j + 4]) * p.scale, __uint_as_float(dk[8 * j + 5]) * p.scale);
-          u.w = pack_half2(__uint_as_float(dk[8 * j + 6]) * p.scale, __uint_as_float(dk[8 * j + 7]) * p.scale);
-          w.x = pack_half2(__uint_as_float(dv[8 * j]), __uint_as_float(dv[8 * j + 1]));
-          w.y = pack_half2(__uint_as_float(dv[8 * j + 2]), __uint_as_float(dv[8 * j + 3]));
-          w.z = pack_half2(__uint_as_float(dv[8 * j + 4]), __uint_as_float(dv[8 * j + 5]));
-          w.w = pack_half2(__uint_as_float(dv[8 * j + 6]), __uint_as_float(dv[8 * j + 7]));
-          reinterpret_cast<uint4*>(gk)[j] = u;
-          reinterpret_cast<uint4*>(gv)[j] = w;
+          for (int j = 0; j < HW / 8; ++j) {
+            uint4 u, w;
+            u.x = pack_half2(__uint_as_float(dk[8 * j]) * p.scale, __uint_as_float(dk[8 * j + 1]) * p.scale);
+            u.y = pack_half2(__uint_as_float(dk[8 * j + 2]) * p.scale, __uint_as_float(dk[8 * j + 3]) * p.scale);
+            u.z = pack_half2(__uint_as_float(dk[8 * j + 4]) * p.scale, __uint_as_float(dk[8 * j + 5]) * p.scale);
+            u.w = pack_half2(__uint_as_float(dk[8 * j + 6]) * p.scale, __uint_as_float(dk[8 * j + 7]) * p.scale);
+            w.x = pack_half2(__uint_as_float(dv[8 * j]), __uint_as_float(dv[8 * j + 1]));
+            w.y = pack_half2(__uint_as_float(dv[8 * j + 2]), __uint_as_float(dv[8 * j + 3]));
+            w.z = pack_half2(__uint_as_float(dv[8 * j + 4]), __uint_as_float(dv[8 * j + 5]));
+            w.w = pack_half2(__uint_as_float(dv[8 * j + 6]), __uint_as_float(dv[8 * j + 7]));
+            reinterpret_cast<uint4*>(gk)[j] = u;
+            reinterpret_cast<uint4*>(gv)[j] = w;
+          }
         }
       }
     }
@@ -427,7 +462,8 @@ static int launch_attn_bwd(const void* qkv, int64_t ld, const AttnBwdParams& p, 
     LAV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  dim3 grid(nkc, p.nheads, p.nprob);
+  const int nitems = nkc * p.nheads * p.nprob;
+  dim3 grid(std::min(nitems, sm_count()));   // persistent: one CTA per SM walks the (key chunk, head, problem) items
   LAV_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kAttnBwdThreads), Cfg::SMEM_BYTES, s, tq, tdo, tb, p));
   LAV_CHECK_CUDA(cudaGetLastError());
   count_launch();

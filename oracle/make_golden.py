@@ -45,7 +45,7 @@ ODR = [[0, 2, 1, 3, 4], [4, 1, 2, 3, 0], [0, 1, 2, 3, 4]]   # frame orders of th
 
 
 def run_case(name, size, layers, B, task_token=True, seed=0, vt_mask=False, odr=False, size_img=224, swin_key=None,
-             backward=True):
+             backward=True, grad_tol=1e-3):
     torch.manual_seed(0)
     ref = ref_shims.build_reference_model(size, layers, size_img, B, task_token)
     cfg = O.ModelCfg(swin=O.SWIN[swin_key or size], bert_layers=layers, enable_task_token=task_token,
@@ -122,7 +122,7 @@ def run_case(name, size, layers, B, task_token=True, seed=0, vt_mask=False, odr=
         gerr = max(gerr, ((g - gr).norm() / (gr.norm() + 1e-5)).item())  # key.bias grads are ~1e-9 noise (softmax is shift-invariant)
     err["grad_rel"] = gerr
     print(f"[{name}] restatement vs reference: {err}")
-    assert err["out_mtm"] < 2e-4 and err["out_vtm"] < 2e-4 and err["ans_vtm"] == 0 and gerr < 1e-3, err
+    assert err["out_mtm"] < 2e-4 and err["out_vtm"] < 2e-4 and err["ans_vtm"] == 0 and gerr < grad_tol, err
 
     os.makedirs(OUT, exist_ok=True)
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **gold)
@@ -238,4 +238,6 @@ if __name__ == "__main__":
         # BASELINE configs[3] at FULL WIDTH: swin_large_384_patch244_window81212 (C = 192..1536, 720-token windows) + 12-layer
         # BERT-base, one 5 x 384 x 384 clip (fusion sequences of 758 / 759 tokens); minutes of CPU time and ~20 GB of RAM,
         # so it is generated on request only:  python oracle/make_golden.py large384
-        run_case("large384_l12_b1", "large", 12, 1, seed=7, size_img=384, swin_key="large384")
+        # (grad_tol: the restatement and the reference sum 720-token windows / 758-token sequences in different orders; the worst
+        #  parameter differs by 1.2e-3 relative in fp32, logits by 3e-6)
+        run_case("large384_l12_b1", "large", 12, 1, seed=7, size_img=384, swin_key="large384", grad_tol=3e-3)

@@ -353,3 +353,51 @@ def test_high_precision_mode_logits_within_1e_3_of_reference(name, size, layers,
             continue
         g = p.grad.cpu() / 1024.0
         assert abs(g.double().norm().item() - gn) / gn < GRAD_REL, n
+
+
+def test_config4_large384_full_width_vs_reference_golden():
+    """BASELINE configs[3] at FULL WIDTH against the unmodified reference: swin_large_384_patch244_window81212 (C = 192..1536,
+    6..48 heads, 720-token windows) + 12-layer BERT-base on one 5 x 384 x 384 clip (758 / 759-token fusion sequences).  Golden:
+    `large384_l12_b1.npz` (`python oracle/make_golden.py large384`, minutes of CPU time).  Default mode within 6e-3, parity
+    mode within 1e-3 on the logits; losses; every parameter gradient norm within 3e-2."""
+    import lavender_oracle as O
+    from lavender_b200 import precision
+    from lavender_b200.bert import CrossEntropyLoss
+    from lavender_b200.pretrain import LAVENDER_Pretrain_MLM, FakeTokenizer, default_args
+    gold = np.load(os.path.join(GOLD, "large384_l12_b1.npz"))
+    cfg = O.ModelCfg(swin=O.SWIN["large384"], bert_layers=12, vtm_batch=1)
+    sd = O.make_state_dict(cfg, 7)
+    args = default_args(vis_backbone_size="large", size_img=384, size_batch=1)
+    torch.manual_seed(0)
+    m = LAVENDER_Pretrain_MLM(args, FakeTokenizer())
+    m.load_state_dict(sd, strict=True)
+    m.cuda().eval()
+    batch = {k: v.cuda() for k, v in O.make_batch(1, H=384, W=384, seed=7).items()}
+    with precision.high_precision(), torch.no_grad():
+        np.random.seed(8)
+        hp = m(batch)
+    h1 = (hp["out_mtm"].cpu()[..., ::61] - torch.from_numpy(gold["out_mtm_s"])).abs().max().item()
+    h2 = (hp["out_vtm"].cpu()[..., ::61] - torch.from_numpy(gold["out_vtm_s"])).abs().max().item()
+    np.random.seed(8)
+    out = m(batch)
+    e1 = (out["out_mtm"].detach().cpu()[..., ::61] - torch.from_numpy(gold["out_mtm_s"])).abs().max().item()
+    e2 = (out["out_vtm"].detach().cpu()[..., ::61] - torch.from_numpy(gold["out_vtm_s"])).abs().max().item()
+    print(f"[large384_l12_b1] logits max abs err: default mtm {e1:.2e} vtm {e2:.2e}; high precision mtm {h1:.2e} vtm {h2:.2e}")
+    assert e1 < LOGIT_ATOL and e2 < LOGIT_ATOL and h1 < LOGIT_ATOL_HP and h2 < LOGIT_ATOL_HP
+    ce = CrossEntropyLoss(ignore_index=-1)
+    l1 = ce(out["out_mtm"].flatten(0, 1), out["ans_mtm"].flatten())
+    l2 = ce(out["out_vtm"].flatten(0, 1), out["ans_vtm"].flatten())
+    assert abs(l1.item() - float(gold["ls_mtm"])) < 2e-3 and abs(l2.item() - float(gold["ls_vtm"])) < 2e-3
+    ((l1 + l2) * 1024.0).backward()
+    m.arena().finalize_grads()
+    torch.cuda.synchronize()
+    worst = ("", 0.0)
+    for n, p in m.named_parameters():
+        gn = float(gold["gn/" + n])
+        if gn < 1e-7 or p.grad is None:
+            continue
+        e = abs(p.grad.double().norm().item() / 1024.0 - gn) / gn
+        if e > worst[1]:
+            worst = (n, e)
+        assert e < GRAD_REL, (n, e)
+    print(f"[large384_l12_b1] worst grad-norm err {worst}")
