@@ -46,8 +46,7 @@ struct AttnBwdCfg {
   static constexpr int OFF_K = 0, OFF_V = 2 * TILE, OFF_Q = 4 * TILE, OFF_DO = 6 * TILE;
   static constexpr int OFF_P = 8 * TILE, OFF_DS = OFF_P + 32768;
   static constexpr int OFF_BIAS = OFF_DS + 32768;                                     // 2 x [128][128] fp16
-  static constexpr int OFF_ID = OFF_BIAS + (BMMA ? 65536 : 0);
-  static constexpr int OFF_BAR = OFF_ID + (BMMA ? kIdentBytesB : 0);
+  static constexpr int OFF_BAR = OFF_BIAS + (BMMA ? 65536 : 0);
   static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
   static constexpr uint32_t SWZ = (HD == 64) ? SWZ_128B : SWZ_64B;
   static constexpr uint32_t SBO = 8 * ROWB;
@@ -79,18 +78,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   auto item_h = [&](int it) { return (it / nkc) % p.nheads; };
   auto item_prob = [&](int it) { return it / (nkc * p.nheads); };
 
-  if (BMMA && warp < 8) {  // identity strip (zeros with a 16 x 16 identity block at groups 14-15), as in attention_fwd.cu
-    uint8_t* id = smem + Cfg::OFF_ID;
-    for (int i = threadIdx.x; i < kIdentBytesB / 16; i += 256) reinterpret_cast<uint4*>(id)[i] = make_uint4(0u, 0u, 0u, 0u);
-    __syncwarp();
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (threadIdx.x < 16) {
-      const int r = threadIdx.x;
-      const int off = r < 8 ? 14 * 256 + r * 16 + r * 2 : 15 * 256 + 128 + (r - 8) * 16 + (r - 8) * 2;
-      *reinterpret_cast<__half*>(id + off) = __float2half_rn(1.0f);
-    }
-    fence_proxy_async_smem();
-  }
   if (warp == 8) {
     if (lane == 0) {
       tma_prefetch_desc(&tmQKV);
@@ -158,14 +145,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         for (int kk = 0; kk < HD / 16; ++kk)
           umma_f16_ss(tmem + Cfg::COL_S, make_smem_desc(sq + kk * 32, 0, Cfg::SBO, Cfg::SWZ),
                       make_smem_desc(sk + kk * 32, 0, Cfg::SBO, Cfg::SWZ), id_s, kk > 0);
-        if (BMMA) {  // S += I * Bias
-          constexpr uint32_t id_b = make_idesc_f16(128, 128, 0, 1);
-          const uint32_t sid = smem_u32(smem + Cfg::OFF_ID), sbias = smem_u32(smem + Cfg::OFF_BIAS + b * 32768);
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk)
-            umma_f16_ss(tmem + Cfg::COL_S, make_smem_desc(sid + (14 - 2 * kk) * 256, 128, 256, SWZ_NONE),
-                        make_smem_desc(sbias + kk * 2048, 16384, 1024, SWZ_128B), id_b, 1u);
-        }
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk)
           umma_f16_ss(tmem + Cfg::COL_DP, make_smem_desc(sdo + kk * 32, 0, Cfg::SBO, Cfg::SWZ),
@@ -243,6 +222,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                                       : nullptr;
         __half* dsg = (p.ds_out && valid) ? p.ds_out + (((size_t)prob * p.nheads + h) * p.NPs + qi) * p.NPs + c * 128
                                           : nullptr;
+        if (BMMA) mbar_wait(bars + 2 + (s & 1), (s >> 1) & 1, 27);   // this step's bias tile (TMA) is in shared memory
         mbar_wait(bars + 4, s & 1, 24);
         tc_fence_after();
 #pragma unroll 1
@@ -254,7 +234,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           float pv[32], dsv[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) pv[j] = __uint_as_float(sr[j]) * sc_log2 - lse_l2;
-          if (brow) {
+          if (BMMA) {
+            // relative-position bias + shift mask from the TMA-staged [128 x 128] tile of this step (same 128B-swizzled
+            // [128 rows x 64 keys] atoms as P / dS); it holds bias / scale, so one FMA brings it to log2 units
+            const uint8_t* bt = smem + Cfg::OFF_BIAS + (s & 1) * 32768 + (j0 >> 6) * 16384 + i * 128;
+            const int chunk0 = (j0 & 63) >> 3;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 u = *reinterpret_cast<const uint4*>(bt + (((chunk0 + j) ^ (i & 7)) << 4));
+              const __half2* hh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float2 f = __half22float2(hh[q]);
+                pv[8 * j + 2 * q] = fmaf(f.x, sc_log2, pv[8 * j + 2 * q]);
+                pv[8 * j + 2 * q + 1] = fmaf(f.y, sc_log2, pv[8 * j + 2 * q + 1]);
+              }
+            }
+          } else if (brow) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 u = *reinterpret_cast<const uint4*>(brow + j0 + 8 * j);

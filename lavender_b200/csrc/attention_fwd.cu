@@ -48,8 +48,7 @@ struct AttnFwdCfg {
   static constexpr int KV_BYTES = NKC * 128 * ROWB;      // per K or V
   static constexpr int P_BYTES = 128 * NKC * 128 * 2;    // bias tile (fp16 [128][NKC*128]) first, P afterwards
   static constexpr int OFF_K = Q_BYTES, OFF_V = OFF_K + KV_BYTES, OFF_P = OFF_V + KV_BYTES;
-  static constexpr int OFF_ID = OFF_P + P_BYTES;
-  static constexpr int OFF_BAR = OFF_ID + (BMMA ? kIdentBytes : 0);
+  static constexpr int OFF_BAR = OFF_P + P_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 64;        // the dynamic window itself is 1024-byte aligned (checked)
   static constexpr int TMEM_COLS = (NKC * 128 <= 256) ? 256 : 512;
   static constexpr uint32_t SWZ = (HD == 64) ? SWZ_128B : SWZ_64B;
@@ -73,20 +72,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const int row0 = prob * p.L;  // first token row of this problem
   const int ncol = min(NP, (p.L + 31) & ~31);  // key columns that can hold a valid key (BERT: 283 -> 288 of 384)
 
-  if (BMMA && warp < 8) {
-    // identity strip: zero groups with one 16 x 16 identity block at groups 14-15 (K-major, no swizzle:
-    // group g = [8 rows x k 0..7 | 8 rows x k 8..15], 16 bytes per row and core matrix)
-    uint8_t* id = smem + Cfg::OFF_ID;
-    for (int i = threadIdx.x; i < kIdentBytes / 16; i += 256) reinterpret_cast<uint4*>(id)[i] = make_uint4(0u, 0u, 0u, 0u);
-    __syncwarp();
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (threadIdx.x < 16) {
-      const int r = threadIdx.x;
-      const int off = r < 8 ? 14 * 256 + r * 16 + r * 2 : 15 * 256 + 128 + (r - 8) * 16 + (r - 8) * 2;
-      *reinterpret_cast<__half*>(id + off) = __float2half_rn(1.0f);
-    }
-    fence_proxy_async_smem();
-  }
   if (warp == 8) {
     if (lane == 0) {
       tma_prefetch_desc(&tmQKV);
@@ -137,17 +122,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           umma_f16_ss(tmem + c * 128, make_smem_desc(sq + k * 32, 0, Cfg::SBO, Cfg::SWZ),
                       make_smem_desc(sk + c * 128 * Cfg::ROWB + k * 32, 0, Cfg::SBO, Cfg::SWZ), idesc_s, k > 0);
       }
-      if (BMMA) {  // S += I * Bias: A = identity slice (K-major, no swizzle), B = bias tile (MN-major, 128B swizzle)
-        constexpr uint32_t idesc_b = make_idesc_f16(128, 128, 0, 1);
-        const uint32_t sid = smem_u32(smem + Cfg::OFF_ID), sbias = smem_u32(smem + Cfg::OFF_P);
-#pragma unroll
-        for (int c = 0; c < NKC; ++c)
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk)
-            if (c * 128 < ncol)
-              umma_f16_ss(tmem + c * 128, make_smem_desc(sid + (14 - 2 * kk) * 256, 128, 256, SWZ_NONE),
-                        make_smem_desc(sbias + c * 32768 + kk * 2048, 16384, 1024, SWZ_128B), idesc_b, 1u);
-      }
       umma_commit(bars + 1);
       // ---- O = P V  (M=128, N=HD, K=NP; A = P K-major 128B swizzle, B = V MN-major)
       mbar_wait(bars + 2, 0, 11);
@@ -185,7 +159,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     auto biased = [&](const uint32_t(&s)[32], int j0, float(&v)[32]) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(s[j]) * sc;
-      if (brow) {
+      if (BMMA) {
+        // relative-position bias + shift mask: this row's 32 entries of the TMA-staged tile (same [128 rows x 64 keys]
+        // 128B-swizzled atoms as P, which later overwrites them in place); the tile holds bias / scale
+        const uint8_t* brow_s = smem + Cfg::OFF_P + (j0 >> 6) * 16384 + i * 128;
+        const int chunk0 = (j0 & 63) >> 3;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 u = *reinterpret_cast<const uint4*>(brow_s + (((chunk0 + j) ^ (i & 7)) << 4));
+          const __half2* hh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 f = __half22float2(hh[q]);
+            v[8 * j + 2 * q] = fmaf(f.x, sc, v[8 * j + 2 * q]), v[8 * j + 2 * q + 1] = fmaf(f.y, sc, v[8 * j + 2 * q + 1]);
+          }
+        }
+      } else if (brow) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           uint4 u = *reinterpret_cast<const uint4*>(brow + j0 + 8 * j);
@@ -206,6 +195,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       }
     };
 
+    if (BMMA) mbar_wait(bars + 0, 0, 14);   // the TMA-staged bias tile (the MMA thread waited for it too)
     mbar_wait(bars + 1, 0, 12);
     tc_fence_after();
     float m = -INFINITY;
