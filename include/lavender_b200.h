@@ -42,6 +42,10 @@ int64_t lav_launch_count(void);
 /* queries device 0..n: fills sm_count; returns LAV_E_NO_DEVICE when no sm_100 device is present */
 int lav_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
 
+/* Profiling aid: a caller-owned device buffer of n_u64 uint64 that the instrumented attention kernels fill with clock64()
+ * stamps (8 per CTA: tools/trace_attn.py); NULL switches it off (the default).  Not used on the hot path. */
+int lav_debug_set_trace(void* buf, int64_t n_u64);
+
 /* ---- dropout ---------------------------------------------------------------------------------------
  * HF BERT's nn.Dropout sites (hidden_dropout_prob / attention_probs_dropout_prob = 0.1, active in train() mode as
  * Agent_Pretrain_MLM.step runs it, main_pretrain_mlm.py:147) are folded into the kernels that produce the dropped
@@ -256,6 +260,16 @@ int lav_xent_fwd(const float* logits, int64_t ld, const int64_t* labels, int row
 int lav_xent_bwd(const float* logits, int64_t ld, const int64_t* labels, int rows, int V, int64_t ignore_index,
                  const float* row_lse, const float* gout, const float* count, float* d32, int64_t ldd32, void* d16,
                  int64_t ldd16, void* stream);
+
+/* ---- GPU input pipeline ------------------------------------------------------------
+ * Per-frame transform of the reference's loader (dataset.py:118-175: Resize(size_img) -> RandomCrop / CenterCrop ->
+ * ToTensor -> Normalize on PIL images) on decoded uint8 RGB frames already in device memory:
+ *   src  [T][Hs][Ws][3] uint8 (frames `frame_stride` bytes apart), resized to Hr x Wr with Pillow's two-pass antialiased
+ *   bilinear resample (bit-exact: 22-bit fixed-point weights, uint8 rounding after each pass), cropped to the S x S window
+ *   at (top, left), scaled by 1/255 and normalised:  out[t][c][y][x] = (pixel / 255 - mean[c]) / std[c]   (fp32 [T][3][S][S]).
+ * mean / std are HOST pointers to 3 floats.  JPEG entropy decoding stays on the host (cv2 / PIL as in dataset.py:177-186). */
+int lav_frames_resize_crop_norm_u8(const uint8_t* src, int T, int Hs, int Ws, int64_t frame_stride, int Hr, int Wr, int S,
+                                   int top, int left, const float* mean, const float* stdv, float* out, void* stream);
 
 /* ---- fused optimizer step on the flat arena ----------------------------------------
  * Device-side restatement of Agent_Base.backward_step (agent.py:240-250): GradScaler.unscale_ with the inf check,

@@ -43,6 +43,9 @@ SIGNATURES = {
     "lav_last_error": (ctypes.c_char_p, []),
     "lav_launch_count": (c_int64, []),
     "lav_device_info": (c_int, [c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
+    "lav_debug_set_trace": (c_int, [c_void_p, c_int64]),
+    "lav_frames_resize_crop_norm_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, c_int, c_int, c_int, c_int, c_int,
+                                               ctypes.POINTER(c_float), ctypes.POINTER(c_float), c_void_p, c_void_p]),
     "lav_gemm_f16": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_int, c_int, c_int,
                              ctypes.POINTER(GemmEpilogue), c_int, c_void_p]),
     "lav_layernorm_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p,

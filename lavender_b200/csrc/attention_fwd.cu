@@ -36,6 +36,7 @@ struct AttnFwdParams {
   float* out32; int64_t ldo32;             // optional fp32 copy of O (high-precision mode)
   float* lse; int64_t rows_total;
   DropParams drop;                         // attention-probability dropout (BERT, train mode)
+  unsigned long long* trace;               // profiling: 8 clock64() stamps per CTA, or null
 };
 
 constexpr int kIdentGroups = 30;                         // 16-group window sliding by 2 groups per k-step, 8 k-steps
@@ -61,6 +62,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 const AttnFwdParams p) {
   griddep_launch();  // dependents (GEMMs) may start their prologue under this kernel's tail
   using Cfg = AttnFwdCfg<HD, NKC, BMMA>;
+  const int cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  auto stamp = [&](int k) {
+    if (p.trace) p.trace[(size_t)cta_lin * 8 + k] = clock64();
+  };
+  if (threadIdx.x == 0) stamp(0);
   constexpr int NP = NKC * 128;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // swizzled TMA / UMMA tiles need the 1024-byte alignment
@@ -90,6 +96,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (threadIdx.x == 0) stamp(1);
 
   if (warp == 8) {
     if (lane == 0) {
@@ -109,6 +116,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         tma_load_2d(smem + Cfg::OFF_V + c * 128 * Cfg::ROWB, &tmQKV, bars + 0, p.v_off + h * HD, row0 + c * 128);
       }
       mbar_wait(bars + 0, 0, 10);
+      stamp(2);
       tc_fence_after();
       // ---- S_c = Q K_cᵀ  (M=128, N=128, K=HD; both operands K-major)
       const uint32_t sq = smem_u32(smem), sk = smem_u32(smem + Cfg::OFF_K);
@@ -197,6 +205,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
     if (BMMA) mbar_wait(bars + 0, 0, 14);   // the TMA-staged bias tile (the MMA thread waited for it too)
     mbar_wait(bars + 1, 0, 12);
+    if (threadIdx.x == 0) stamp(3);
     tc_fence_after();
     float m = -INFINITY;
 #pragma unroll 1
@@ -209,6 +218,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 #pragma unroll
       for (int j = 0; j < 32; ++j) m = fmaxf(m, v[j]);
     }
+    if (threadIdx.x == 0) stamp(4);
     xch[hsel * 128 + i] = m;
     asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
     m = fmaxf(m, xch[(hsel ^ 1) * 128 + i]);
@@ -251,10 +261,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     fence_proxy_async_smem();
     tc_fence_before();
     mbar_arrive(bars + 2);
+    if (threadIdx.x == 0) stamp(5);
     asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
     l += xch[256 + (hsel ^ 1) * 128 + i];
 
     mbar_wait(bars + 3, 0, 13);
+    if (threadIdx.x == 0) stamp(6);
     tc_fence_after();
     const float inv = 1.f / l;
     const bool valid = qi < p.L;
@@ -287,6 +299,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) stamp(7);
   if (warp == 8) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
 }
 
@@ -368,6 +381,10 @@ extern "C" int lav_attn_fwd_ex(const void* qkv, int64_t ld, int64_t rows_total, 
   p.key_bias = key_bias, p.out = (__half*)out16, p.ldo = ldo, p.lse = lse, p.rows_total = rows_total;
   p.out32 = out32, p.ldo32 = ldo32;
   p.drop = make_drop(drop);
+  {
+    const int64_t ctas = (int64_t)((L + 127) / 128) * nheads * nprob;
+    p.trace = (trace_buffer() && trace_capacity() >= ctas * 8) ? trace_buffer() : nullptr;
+  }
   cudaStream_t s = (cudaStream_t)stream;
   const int ncls = 8;  // row extent of the bias tensor map: an upper bound on the classes a dense tensor holds (2^3
                        // shifted axes); only the classes named by prob_class are ever addressed

@@ -21,6 +21,12 @@ int set_error(int code, const char* fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+static unsigned long long* g_trace = nullptr;
+static int64_t g_trace_cap = 0;
+unsigned long long* trace_buffer() { return g_trace; }
+int64_t trace_capacity() { return g_trace_cap; }
+void set_trace(unsigned long long* p, int64_t n) { g_trace = p, g_trace_cap = n; }
+
 bool pdl_enabled() {  // LAV_PDL=0 disables programmatic dependent launch
   static int v = -1;
   if (v < 0) {
@@ -38,6 +44,8 @@ bool pdl_all_enabled() {
   }
   return v == 1;
 }
+
+void set_trace(unsigned long long* p, int64_t n);
 
 int sm_count() {
   static int cached[64];
@@ -100,6 +108,10 @@ int encode_tmap_2d(CUtensorMap* map, const void* ptr, int elt_bytes, uint64_t ro
 extern "C" {
 
 int lav_abi_version(void) { return 3; }
+int lav_debug_set_trace(void* buf, int64_t n_u64) {
+  lav::set_trace(reinterpret_cast<unsigned long long*>(buf), buf ? n_u64 : 0);
+  return LAV_OK;
+}
 const char* lav_last_error(void) { return lav::g_err; }
 int64_t lav_launch_count(void) { return lav::g_launches.load(); }
 

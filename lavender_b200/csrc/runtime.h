@@ -11,6 +11,9 @@ namespace lav {
 int set_error(int code, const char* fmt, ...);
 void count_launch(int n = 1);
 int sm_count();  // of the current device (cached per device)
+// profiling aid (lav_debug_set_trace): device buffer that instrumented kernels fill with clock64() stamps, or null
+unsigned long long* trace_buffer();
+int64_t trace_capacity();
 
 // 2-D fp16 tensor map: `rows` x `cols` elements, row stride `ld` elements, box `box_rows` x `box_cols`,
 // swizzle = CU_TENSOR_MAP_SWIZZLE_{32B,64B,128B}. Out-of-bounds elements read as zero.
