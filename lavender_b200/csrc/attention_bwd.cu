@@ -1,6 +1,6 @@
 // Fused attention backward for sm_100a (recompute from the saved log-sum-exp; nothing [N,N]-shaped is kept from
-// the forward).  One CTA per (128-key chunk c, head, problem); it keeps K_c / V_c resident and loops over the
-// 128-row query tiles t:
+// the forward).  Persistent CTAs (one per SM) walk work items (128-key chunk c, head, problem); an item keeps K_c / V_c
+// resident (double-buffered against the next item's) and loops over the 128-row query tiles t:
 //     S  = Q_t K_cᵀ , dP = dO_t V_cᵀ                 (tcgen05 -> TMEM)
 //     P  = exp(scale*S + bias - lse) , dS = P ∘ (dP - delta)          (registers, thread = query row)
 //     dV_c += Pᵀ dO_t , dK_c += dSᵀ Q_t , dQ_t = dS K_c               (tcgen05; P/dS staged in smem as fp16)
@@ -33,11 +33,8 @@ struct AttnBwdParams {
   DropParams drop;                          // attention-probability dropout of the forward (regenerated here)
 };
 
-constexpr int kIdentGroupsB = 30;                // see attention_fwd.cu: sliding 128 x 16 identity slices
-constexpr int kIdentBytesB = kIdentGroupsB * 256;
-
-// BMMA (window attention with the dense relative-position bias): S = Q K^T + I * Bias on the tensor core, the
-// 128 x 128 bias tile of each query tile TMA-staged (double-buffered like Q / dO) instead of being read by threads.
+// BMMA (window attention with the dense relative-position bias): the 128 x 128 bias tile of each query tile is TMA-staged
+// (double-buffered like Q / dO) and each softmax thread adds its own row of it to the S values it reads from TMEM.
 template <int HD, bool BMMA>
 struct AttnBwdCfg {
   static constexpr int ROWB = HD * 2;
@@ -68,7 +65,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // PERSISTENT: one CTA per SM walks work items (key chunk c, head h, problem) = blockIdx.x, + gridDim.x, ...; an item is
   // nqt steps (query tiles).  Round 1 launched one CTA per item: with nqt = 2-3 the per-CTA prologue (512-column TMEM
-  // allocation, identity strip, barriers), the first K/V/Q/dO/bias loads and the dK/dV read-out were ~half of a CTA's life
+  // allocation, barriers), the first K/V/Q/dO/bias loads and the dK/dV read-out were ~half of a CTA's life
   // and nothing overlapped them at 1 CTA/SM.  Now the next item's operands are prefetched and its S / dP products issued
   // while the softmax warps finish the current item.
   const int nkc = (p.L + 127) / 128;

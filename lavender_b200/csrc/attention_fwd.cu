@@ -7,10 +7,10 @@
 //     layout, O = P V is a second tcgen05 MMA whose accumulator aliases the dead S columns.
 //   * relative-position bias + shift mask (+ a large negative on the padded key columns) come pre-expanded as a dense
 //     fp16 [class][head][NP][NP] tensor (lav_relpos_bias_expand, values already divided by `scale`).  The window
-//     kernel never touches it with a thread: the 128 x 256 bias tile is TMA-staged and ADDED BY THE TENSOR CORE,
-//     S = Q K^T + I * Bias, with the 128 x 128 identity supplied as eight 128 x 16 slices of one 7.5 KB
-//     shared-memory strip (a 16 x 16 identity block between zero rows, addressed through a sliding UMMA descriptor);
-//     the bias tile's shared memory is then reused for P.  BERT passes an additive per-key fp32 row instead.
+//     kernel TMA-stages the 128 x 256 bias tile into the shared memory that later holds P; each softmax thread adds
+//     its own row of it to the S values it reads from TMEM (round 1 added it on the tensor core through an identity
+//     MMA: 8 more tcgen05.mma per tile on an issue-bound warp, removed in round 2).  BERT passes an additive per-key
+//     fp32 row instead.
 // Nothing of size [B_, nh, N, N] ever reaches HBM.
 #include <cstdlib>
 
@@ -38,9 +38,6 @@ struct AttnFwdParams {
   DropParams drop;                         // attention-probability dropout (BERT, train mode)
   unsigned long long* trace;               // profiling: 8 clock64() stamps per CTA, or null
 };
-
-constexpr int kIdentGroups = 30;                         // 16-group window sliding by 2 groups per k-step, 8 k-steps
-constexpr int kIdentBytes = kIdentGroups * 256;          // group = 8 rows x 16 k: two 128-byte core matrices
 
 template <int HD, int NKC, bool BMMA>
 struct AttnFwdCfg {
@@ -333,8 +330,9 @@ static int launch_attn_fwd(const void* qkv, int64_t ld, int64_t rows_total, cons
 // dense[cls][h][i][j] = (table[rel_index(i,j)][h] + (label[cls][i] != label[cls][j] ? -100 : 0)) * inv_scale, and
 // kMaskedKey for the padded key columns j >= L (video_swin.py:153-160, compute_mask :290-305).  rel_index is passed in
 // (int32 [L][L], the [:N,:N] slice).  inv_scale = 1 / softmax scale: the attention kernels add the tile to the RAW
-// Q K^T accumulator (by an identity MMA) and apply `scale` to the sum.  kMaskedKey is finite on purpose: the identity
-// MMA multiplies every bias element by 0 or 1 and 0 * -inf would be NaN; exp() of it is exactly 0 all the same.
+// Q K^T accumulator and apply `scale` to the sum.  kMaskedKey is finite on purpose: the flash kernel (attention_flash.cu)
+// still adds the tile through an identity MMA, which multiplies every bias element by 0 or 1, and 0 * -inf would be NaN;
+// exp() of it is exactly 0 all the same.
 constexpr float kMaskedKey = -30000.0f;
 __global__ void relpos_bias_expand_kernel(const float* table, int nheads, const int32_t* rel_index, int L,
                                           const uint8_t* labels, int ncls, __half* dense, int NP, float inv_scale) {

@@ -864,8 +864,14 @@ extern "C" int lav_gemm_f16(const void* A, int64_t lda, int a_major, const void*
   int bn = 128, splits = 1;
   double best = 1e30;
   const int cands[4] = {256, 192, 128, 64};
+  static int forced_bn = -1;  // LAV_GEMM_BN=64|128|192|256: tile-width override for tools/bench_gemm.py (tuning the model)
+  if (forced_bn < 0) {
+    const char* e = getenv("LAV_GEMM_BN");
+    forced_bn = e ? atoi(e) : 0;
+  }
   for (int ci = 0; ci < 4; ++ci) {
     const int c = cands[ci];
+    if (forced_bn > 0 && c != forced_bn && !(epi->bias_grad && forced_bn > 192 && c == 192)) continue;
     if (ncta == 2 && c != 256 && c != 128) continue;        // pair tiles: B halves must be whole 64-row atoms
     if (epi->bias_grad && c > 192) continue;                // the side accumulator needs 32 spare TMEM columns
     if (c > 64 && c >= 2 * ((N + 63) / 64 * 64) && !(ncta == 2 && c == 128)) continue;  // far wider than the problem

@@ -47,6 +47,20 @@ def main():
         shapes += [(f"m{M}", M, 2048, 512, "fwd") for M in (128, 1024, 18944, 37888)]
         shapes += [("swin_s2_fc1_gelu", 7840, 2048, 512, "gelu"), ("swin_s2_fc2_res", 7840, 512, 2048, "res"),
                    ("swin_s0_fc1_gelu", 125440, 512, 128, "gelu"), ("swin_s2_fc1_wgrad", 2048, 512, 7840, "wgrad")]
+    if "--hot" in sys.argv:   # every GEMM shape of a Swin stage-2 block and of a BERT layer at B = 8 (configs[1])
+        shapes = [("s2_qkv", 7840, 1536, 512, "fwd"), ("s2_proj_res", 7840, 512, 512, "res"),
+                  ("s2_fc1_gelu", 7840, 2048, 512, "gelu"), ("s2_fc2_res", 7840, 512, 2048, "res"),
+                  ("s2_fc2_dgrad_gelu", 7840, 2048, 512, "dgrad_gelu"), ("s2_fc1_dgrad", 7840, 512, 2048, "dgrad"),
+                  ("s2_proj_dgrad", 7840, 512, 512, "dgrad"), ("s2_qkv_dgrad", 7840, 512, 1536, "dgrad"),
+                  ("s2_fc1_wgrad", 2048, 512, 7840, "wgrad"), ("s2_fc2_wgrad", 512, 2048, 7840, "wgrad"),
+                  ("s2_proj_wgrad", 512, 512, 7840, "wgrad"), ("s2_qkv_wgrad", 1536, 512, 7840, "wgrad"),
+                  ("s1_qkv", 31360, 768, 256, "fwd"), ("s1_fc1_gelu", 31360, 1024, 256, "gelu"),
+                  ("s1_fc2_res", 31360, 256, 1024, "res"), ("s1_fc2_dgrad_gelu", 31360, 1024, 256, "dgrad_gelu"),
+                  ("bert_qkv", 11360, 2304, 768, "fwd"), ("bert_out", 11360, 768, 768, "fwd32"),
+                  ("bert_ffn1", 11360, 3072, 768, "gelu"), ("bert_ffn2", 11360, 768, 3072, "fwd32"),
+                  ("bert_ffn2_dgrad_gelu", 11360, 3072, 768, "dgrad_gelu"), ("bert_ffn1_dgrad", 11360, 768, 3072, "dgrad"),
+                  ("bert_qkv_dgrad", 11360, 768, 2304, "dgrad"), ("bert_ffn1_wgrad", 3072, 768, 11360, "wgrad"),
+                  ("bert_qkv_wgrad", 2304, 768, 11360, "wgrad")]
     only = [a for a in sys.argv[1:] if not a.startswith("-")]
     if only:
         shapes = [s_ for s_ in shapes if s_[0] in only]
@@ -55,7 +69,8 @@ def main():
             a = torch.randn(K, M, device="cuda").half()
             b = torch.randn(K, N, device="cuda").half()
             out = torch.zeros(M, N, device="cuda")
-            fn = lambda: ops.gemm(a, b, out, M=M, N=N, K=K, a_major=1, b_major=1, accumulate=True)
+            bg = torch.zeros(M, device="cuda") if "--hot" in sys.argv else None   # the path's wgrads carry the bias gradient
+            fn = lambda: ops.gemm(a, b, out, M=M, N=N, K=K, a_major=1, b_major=1, accumulate=True, bias_grad=bg)
         elif mode in ("dgrad", "dgrad_gelu"):
             a = torch.randn(M, K, device="cuda").half()
             b = torch.randn(K, N, device="cuda").half()
@@ -98,7 +113,8 @@ def main():
                          cublas_ms=round(ms_t, 4), cublas_tflops=round(2.0 * M * N * K / ms_t / 1e9, 1)))
         print(rows[-1], flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "bench_gemm.json"), "w"), indent=1)
+    name = os.environ.get("LAV_BENCH_GEMM_OUT", "bench_gemm.json")
+    json.dump(rows, open(os.path.join(ROOT, "gpurun_out", name), "w"), indent=1)
 
 
 if __name__ == "__main__":

@@ -1,37 +1,59 @@
-"""Micro-benchmark of the LayerNorm kernels on the hot path's shapes (CUDA events, L2 flushed between runs)."""
+"""Row-kernel micro-benchmark: LayerNorm forward / backward and the gradient casts at the step's shapes (B = 8, base),
+one launch per measurement between L2 flushes, CUDA events; reports us and algorithmic GB/s."""
+import json
 import os
 import sys
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from lavender_b200 import ops  # noqa: E402
-from bench_gemm import timeit  # noqa: E402
+
+dev = torch.device("cuda:0")
+SHAPES = [("swin_s0", 125440, 128, True), ("swin_s1", 31360, 256, True), ("swin_s2", 7840, 512, True),
+          ("swin_s3", 1960, 1024, True), ("bert", 40 * 284, 768, False)]
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 
-def main():
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    for rows, C in [(7840, 512), (125440, 128), (31360, 256), (9088, 768), (1960, 1024)]:
-        x = torch.randn(rows, C, device="cuda")
-        g, b = torch.rand(C, device="cuda") + 0.5, torch.randn(C, device="cuda")
-        y16 = torch.empty(rows, C, device="cuda", dtype=torch.float16)
-        mean, rstd = torch.empty(rows, device="cuda"), torch.empty(rows, device="cuda")
-        perm = torch.randperm(rows, device="cuda").to(torch.int32)
-        fwd = lambda: ops.layernorm_fwd(x, g, b, 1e-5, rows=rows, C=C, row_map=perm, out16=y16, mean=mean, rstd=rstd)
-        tf = timeit(fwd, flush=flush)
-        dy = torch.randn(rows, C, device="cuda").half()
-        add = torch.randn(rows, C, device="cuda")
-        dx = torch.empty(rows, C, device="cuda")
-        dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
-        bwd = lambda: ops.layernorm_bwd(dy, x, g, mean, rstd, rows=rows, C=C, row_map=perm, add32=add, dx32=dx, dgamma=dg,
-                                        dbeta=db)
-        tb = timeit(bwd, flush=flush)
-        bf, bb = rows * C * 6, rows * C * 14
-        print(f"rows={rows:6d} C={C:4d}  fwd {tf * 1e3:6.1f} us ({bf / tf / 1e6:6.0f} GB/s)  bwd {tb * 1e3:6.1f} us "
-              f"({bb / tb / 1e6:6.0f} GB/s)", flush=True)
+def timeit(fn, n=12):
+    ts = []
+    for _ in range(n):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2]
 
 
-if __name__ == "__main__":
-    main()
+out = []
+for tag, rows, C, mapped in SHAPES:
+    g = torch.Generator(device="cpu").manual_seed(0)
+    x = torch.randn(rows, C, generator=g).to(dev)
+    gamma, beta = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+    rmap = torch.randperm(rows, generator=g).to(dev, torch.int32) if mapped else None
+    if mapped:   # window partition keeps runs of 7 tokens contiguous; a random permutation is the worst case, so use runs
+        base = torch.arange(rows, dtype=torch.int32).view(-1, 7) if rows % 7 == 0 else torch.arange(rows, dtype=torch.int32).view(-1, 1)
+        rmap = base[torch.randperm(base.shape[0], generator=g)].reshape(-1).to(dev)
+    y16 = torch.empty(rows, C, dtype=torch.float16, device=dev)
+    mean, rstd = torch.empty(rows, device=dev), torch.empty(rows, device=dev)
+    t_f = timeit(lambda: ops.layernorm_fwd(x, gamma, beta, 1e-5, rows=rows, C=C, row_map=rmap, out16=y16, mean=mean, rstd=rstd))
+    dy = torch.randn(rows, C, generator=g).to(dev, torch.float16)
+    add = torch.randn(rows, C, generator=g).to(dev)
+    dx = torch.empty(rows, C, device=dev)
+    dg, db = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+    t_b = timeit(lambda: ops.layernorm_bwd(dy, x, gamma, mean, rstd, rows=rows, C=C, row_map=rmap, add32=add, dx32=dx,
+                                           dgamma=dg, dbeta=db))
+    o16 = torch.empty(rows, C, dtype=torch.float16, device=dev)
+    t_c = timeit(lambda: ops.scale_cast(x, o16, rows=rows, C=C))
+    rec = {"tag": tag, "rows": rows, "C": C,
+           "ln_fwd_us": round(t_f, 1), "ln_fwd_GBps": round(rows * C * 6 / t_f / 1e3, 0),
+           "ln_bwd_us": round(t_b, 1), "ln_bwd_GBps": round(rows * C * 14 / t_b / 1e3, 0),
+           "cast_us": round(t_c, 1), "cast_GBps": round(rows * C * 6 / t_c / 1e3, 0)}
+    print(json.dumps(rec))
+    out.append(rec)
+if len(sys.argv) > 1:
+    json.dump(out, open(sys.argv[1], "w"), indent=1)
