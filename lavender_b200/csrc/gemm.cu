@@ -318,14 +318,24 @@ __device__ __forceinline__ void epilogue_warps_tma2(const GemmParams& p, const C
       }
       if (ACT == LAV_ACT_GELU) {
         if (aux_out) stage_and_store<false>(tmAux, buf, nb, lane, v, col0, row_base, rows_valid, p.debug);
+        if (!(p.debug & 128)) {  // (profiling bit 128: no activation math)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        }
       } else if (ACT == LAV_ACT_GELU_BWD) {
         const __half2* h2 = reinterpret_cast<const __half2*>(axc);
+        if (p.debug & 128) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float2 x = __half22float2(h2[j]);
-          v[2 * j] *= gelu_erf_grad(x.x), v[2 * j + 1] *= gelu_erf_grad(x.y);
+          for (int j = 0; j < 16; ++j) {
+            const float2 x = __half22float2(h2[j]);
+            v[2 * j] *= x.x, v[2 * j + 1] *= x.y;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float2 x = __half22float2(h2[j]);
+            v[2 * j] *= gelu_erf_grad(x.x), v[2 * j + 1] *= gelu_erf_grad(x.y);
+          }
         }
       }
       stage_and_store<F32>(tmOut, buf, nb, lane, v, col0, row_base, rows_valid, p.debug);

@@ -318,6 +318,141 @@ __global__ void __launch_bounds__(kRowThreads) ln_bwd_kernel(const LnBwdParams p
   }
 }
 
+// Wide rows (C = 512 ... 1024: Swin stages 2-3, BERT): the register-resident kernel above runs ONE block of 8 warps per
+// SM there (the row + the per-lane dgamma / dbeta sums take 130-200 registers), and a warp alternates between "loads in
+// flight" and "math + stores", so only ~30 KB per SM are in flight on average: 1.7 TB/s.  Here the in-flight bytes live
+// in shared memory instead: every warp owns a ring of `depth` row slots (x row | dy row | add row) filled by 1-D bulk
+// copies (cp.async.bulk -> mbarrier), issued `depth` rows ahead by lane 0, so 120-190 KB per SM stay in flight while the
+// warps do math on rows that have already landed.  Same arithmetic, same outputs, same parameter-gradient path.
+template <int NV>
+__global__ void __launch_bounds__(kRowThreads, 1) ln_bwd_staged_kernel(const LnBwdParams p, int depth) {
+  extern __shared__ __align__(128) uint8_t sm_raw[];
+  griddep_launch();
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  constexpr int wpb = kRowThreads / 32;
+  const int c4 = p.C >> 2;
+  const uint32_t xb = p.C * 4u, dyb = p.dy_f32 ? p.C * 4u : p.C * 2u, adb = p.add32 ? p.C * 4u : 0u;
+  const uint32_t stage_bytes = xb + dyb + adb;
+  float* red = reinterpret_cast<float*>(sm_raw);                                   // [8 warps][C]
+  uint64_t* mybar = reinterpret_cast<uint64_t*>(sm_raw + (size_t)wpb * p.C * 4) + wy * 4;  // 4 barriers per warp
+  uint8_t* my = sm_raw + (size_t)wpb * p.C * 4 + 256 + (size_t)wy * depth * stage_bytes;
+  if (lane == 0) {
+    for (int s = 0; s < depth; ++s) mbar_init(mybar + s, 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  griddep_wait();
+  DropKey dkey{};
+  if (p.drop.on) dkey = drop_key(p.drop);
+  const int r0 = blockIdx.x * wpb + wy, stride = gridDim.x * wpb;
+  auto issue = [&](int r, int s) {  // lane 0: the three rows of output row r into slot s
+    const int64_t srow = p.map ? p.map[r] : (int64_t)r;
+    uint8_t* dst = my + (size_t)s * stage_bytes;
+    mbar_arrive_expect_tx(mybar + s, stage_bytes);
+    bulk_load_1d(dst, p.x + srow * p.ldx, xb, mybar + s);
+    bulk_load_1d(dst + xb, reinterpret_cast<const uint8_t*>(p.dy) + (int64_t)r * p.lddy * (p.dy_f32 ? 4 : 2), dyb, mybar + s);
+    if (adb) bulk_load_1d(dst + xb + dyb, p.add32 + srow * p.ldadd, adb, mybar + s);
+  };
+  if (lane == 0)
+    for (int s = 0; s < depth; ++s)
+      if (r0 + s * stride < p.rows) issue(r0 + s * stride, s);
+  float4 ag[NV], ab[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) ag[k] = make_float4(0.f, 0.f, 0.f, 0.f), ab[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float mean_n = 0.f, rstd_n = 0.f;
+  int64_t srow_n = 0;
+  if (r0 < p.rows) mean_n = p.mean[r0], rstd_n = p.rstd[r0], srow_n = p.map ? p.map[r0] : (int64_t)r0;
+  int s = 0;
+  uint32_t par = 0;
+  for (int r = r0; r < p.rows; r += stride) {
+    const float mean = mean_n, rstd = rstd_n;
+    const int64_t srow = srow_n;
+    if (r + stride < p.rows) {  // the next row's scalars travel under this row's math
+      const int rn = r + stride;
+      mean_n = p.mean[rn], rstd_n = p.rstd[rn], srow_n = p.map ? p.map[rn] : (int64_t)rn;
+    }
+    mbar_wait(mybar + s, par, 40);
+    const uint8_t* st = my + (size_t)s * stage_bytes;
+    float4 v[NV], d[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int i = lane + 32 * k;
+      if (i < c4) {
+        v[k] = *reinterpret_cast<const float4*>(st + i * 16);
+        if (p.dy_f32) d[k] = *reinterpret_cast<const float4*>(st + xb + i * 16);
+        else {
+          const uint2 u = *reinterpret_cast<const uint2*>(st + xb + i * 8);
+          const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+          const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+          d[k] = make_float4(a.x, a.y, b.x, b.y);
+        }
+        const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gamma) + i);
+        const float x0 = (v[k].x - mean) * rstd, x1 = (v[k].y - mean) * rstd, x2 = (v[k].z - mean) * rstd,
+                    x3 = (v[k].w - mean) * rstd;
+        ag[k].x += d[k].x * x0, ag[k].y += d[k].y * x1, ag[k].z += d[k].z * x2, ag[k].w += d[k].w * x3;
+        ab[k].x += d[k].x, ab[k].y += d[k].y, ab[k].z += d[k].z, ab[k].w += d[k].w;
+        d[k].x *= ga.x, d[k].y *= ga.y, d[k].z *= ga.z, d[k].w *= ga.w;  // a = dy * gamma
+        v[k] = make_float4(x0, x1, x2, x3);                              // xhat
+        s1 += (d[k].x + d[k].y) + (d[k].z + d[k].w);
+        s2 += (d[k].x * x0 + d[k].y * x1) + (d[k].z * x2 + d[k].w * x3);
+      }
+    }
+    s1 = warp_sum(s1) / p.C;
+    s2 = warp_sum(s2) / p.C;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int i = lane + 32 * k;
+      if (i < c4) {
+        const int col = i * 4;
+        float4 o;
+        o.x = rstd * (d[k].x - s1 - v[k].x * s2), o.y = rstd * (d[k].y - s1 - v[k].y * s2);
+        o.z = rstd * (d[k].z - s1 - v[k].z * s2), o.w = rstd * (d[k].w - s1 - v[k].w * s2);
+        if (adb) {
+          const float4 a = *reinterpret_cast<const float4*>(st + xb + dyb + i * 16);
+          o.x += a.x, o.y += a.y, o.z += a.z, o.w += a.w;
+        }
+        if (p.dx32) *reinterpret_cast<float4*>(p.dx32 + srow * p.lddx32 + col) = o;
+        if (p.dx16) {
+          if (p.drop.on) {
+            const uint32_t m = drop_keep8(dkey, p.drop.thresh, (uint32_t)r, (uint32_t)(col >> 3), 0u) >> (col & 7);
+            o.x = (m & 1u) ? o.x * p.drop.inv_keep : 0.f, o.y = (m & 2u) ? o.y * p.drop.inv_keep : 0.f;
+            o.z = (m & 4u) ? o.z * p.drop.inv_keep : 0.f, o.w = (m & 8u) ? o.w * p.drop.inv_keep : 0.f;
+          }
+          *reinterpret_cast<uint2*>(p.dx16 + (int64_t)r * p.lddx16 + col) =
+              make_uint2(pack_half2(o.x, o.y), pack_half2(o.z, o.w));
+        }
+      }
+    }
+    // every lane has consumed its part of the slot (the values above were used): refill it `depth` rows ahead
+    __syncwarp();
+    if (lane == 0 && r + depth * stride < p.rows) {
+      fence_proxy_async_smem();
+      issue(r + depth * stride, s);
+    }
+    if (++s == depth) s = 0, par ^= 1;
+  }
+  // block reduction of the per-lane column sums, as in ln_bwd_kernel<true>
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int i = lane + 32 * k;
+      if (i < c4) *reinterpret_cast<float4*>(red + wy * p.C + i * 4) = pass == 0 ? ag[k] : ab[k];
+    }
+    __syncthreads();
+    float* dst = p.param_ws ? p.param_ws + ((size_t)blockIdx.x * 2 + pass) * p.C : (pass == 0 ? p.dgamma : p.dbeta);
+    for (int c = threadIdx.x; c < p.C; c += kRowThreads) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += red[w * p.C + c];
+      if (p.param_ws) dst[c] = t;
+      else atomicAdd(dst + c, t);
+    }
+  }
+}
+
 // dgamma[c] += sum_b ws[b][0][c] ; dbeta[c] += sum_b ws[b][1][c]   (second stage of the fused parameter gradients)
 __global__ void __launch_bounds__(1024) ln_param_reduce_kernel(const float* ws, int nblocks, int C, float* dgamma, float* dbeta) {
   griddep_launch();
@@ -555,6 +690,15 @@ extern "C" int lav_layernorm_fwd(const float* x, int64_t ldx, const int32_t* row
   return LAV_OK;
 }
 
+static bool ln_staged_enabled() {  // LAV_LN_STAGED=0: the register-resident kernel for every width (A/B testing)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LAV_LN_STAGED");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 extern "C" int lav_layernorm_bwd(const void* dy, int64_t lddy, int dy_is_f32, const float* x, int64_t ldx,
                                  const int32_t* row_map, int G, int C, const float* gamma, const float* mean,
                                  const float* rstd, const float* add32, int64_t ldadd, float* dx32, int64_t lddx32,
@@ -569,6 +713,37 @@ extern "C" int lav_layernorm_bwd(const void* dy, int64_t lddy, int dy_is_f32, co
                 dx32, lddx32, (__half*)dx16, lddx16, dgamma, dbeta, rows, make_drop(drop16), nullptr};
   LAV_REQUIRE(!p.drop.on || (dx16 && G == 1), "lav_layernorm_bwd: drop16 needs dx16 and G == 1");
   cudaStream_t s = (cudaStream_t)stream;
+  if (dgamma && G == 1 && C >= 512 && C <= 1024 && (C % 8) == 0 && ln_staged_enabled() &&
+      ((uintptr_t)x % 16) == 0 && ((uintptr_t)dy % 16) == 0 && (dy_is_f32 || (lddy % 8) == 0) &&
+      (!add32 || (((uintptr_t)add32 % 16) == 0 && (ldadd % 4) == 0))) {
+    // wide rows: shared-memory staged kernel, one persistent block per SM (see ln_bwd_staged_kernel)
+    const size_t stage = (size_t)C * 4 + (dy_is_f32 ? (size_t)C * 4 : (size_t)C * 2) + (add32 ? (size_t)C * 4 : 0);
+    const size_t fixed = (size_t)8 * C * 4 + 256;
+    const int depth = (int)std::min<size_t>(4, (227 * 1024 - fixed) / (8 * stage));
+    if (depth >= 2) {
+      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((rows + 7) / 8, (int64_t)sm_count()));
+      if (param_ws && ws_floats >= (int64_t)grid * 2 * C) p.param_ws = param_ws;
+      const size_t smem = fixed + (size_t)8 * depth * stage;
+      static bool attr_set = false;
+      if (!attr_set) {
+        LAV_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_staged_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        LAV_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_staged_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        LAV_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_staged_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+      }
+      if (C <= 512) LAV_CHECK_CUDA(launch_pdl(ln_bwd_staged_kernel<4>, dim3(grid), dim3(kRowThreads), smem, s, p, depth));
+      else if (C <= 768) LAV_CHECK_CUDA(launch_pdl(ln_bwd_staged_kernel<6>, dim3(grid), dim3(kRowThreads), smem, s, p, depth));
+      else LAV_CHECK_CUDA(launch_pdl(ln_bwd_staged_kernel<8>, dim3(grid), dim3(kRowThreads), smem, s, p, depth));
+      LAV_CHECK_CUDA(cudaGetLastError());
+      count_launch();
+      if (p.param_ws) {
+        LAV_CHECK_CUDA(launch_pdl(ln_param_reduce_kernel, dim3((2 * C + 31) / 32), dim3(1024), 0, s, p.param_ws, grid, C, dgamma, dbeta));
+        LAV_CHECK_CUDA(cudaGetLastError());
+        count_launch();
+      }
+      return LAV_OK;
+    }
+  }
   if (dgamma && G == 1 && C <= 1024) {
     // fused: the per-block column reduction (2 * C atomics per block) must amortise over the rows a block walks, and
     // narrow rows need many resident warps to cover the load latency: blocks per SM grow as the rows get narrower

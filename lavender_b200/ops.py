@@ -109,7 +109,7 @@ def _p(t):
 def layernorm_fwd(x, gamma, beta, eps, *, rows, C, G=1, row_map=None, out16=None, out32=None, mean=None, rstd=None):
     """out[r] = LN(concat_g x[row_map[r*G+g]]) (width G*C); x fp32 2-D."""
     assert x.dtype == torch.float32 and x.stride(-1) == 1
-    with _Timed("layernorm_fwd"):
+    with _Timed("layernorm_fwd", 0.0, ("ln_fwd", rows, C, G, row_map is not None)):
         rc = L.lib().lav_layernorm_fwd(_p(x), x.stride(0), _p(row_map), G, C, _p(gamma), _p(beta), eps,
                                        _p(out16), out16.stride(0) if out16 is not None else 0,
                                        _p(out32), out32.stride(0) if out32 is not None else 0,
@@ -123,7 +123,8 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, *, rows, C, G=1, row_map=None, add32
     ws = None
     if dgamma is not None and G == 1 and C <= 1024:   # scratch for the per-block partial sums of dgamma / dbeta
         ws = torch.empty(8 * 148 * 2 * C, dtype=torch.float32, device=x.device)
-    with _Timed("layernorm_bwd"):
+    with _Timed("layernorm_bwd", 0.0, ("ln_bwd", rows, C, G, row_map is not None, dy.dtype == F16, add32 is not None,
+                                       dx32 is not None, dx16 is not None)):
         rc = L.lib().lav_layernorm_bwd(_p(dy), dy.stride(0), int(dy.dtype == torch.float32), _p(x), x.stride(0),
                                        _p(row_map), G, C, _p(gamma), _p(mean), _p(rstd),
                                        _p(add32), add32.stride(0) if add32 is not None else 0,
@@ -136,7 +137,7 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, *, rows, C, G=1, row_map=None, add32
 
 def scale_cast(x, out16, *, rows, C, row_map=None, row_scale=None, rows_per_scale=1, alpha=1.0):
     assert x.dtype == torch.float32 and out16.dtype == F16
-    with _Timed("cast"):
+    with _Timed("cast", 0.0, ("cast", rows, C, row_map is not None)):
         rc = L.lib().lav_scale_cast_f16(_p(x), x.stride(0), _p(row_map), _p(row_scale), rows_per_scale, alpha,
                                         _p(out16), out16.stride(0), rows, C, _stream())
     L.check(rc, "lav_scale_cast_f16")
@@ -175,7 +176,7 @@ def attn_fwd(qkv, out, lse, *, q_off, k_off, v_off, head_dim, nheads, nprob, L_t
         _chk16(out, "out")
     assert out32 is None or (out32.dtype == torch.float32 and out32.stride(-1) == 1)
     fam = "win_attn_fwd" if head_dim == 32 else "bert_attn_fwd"
-    with _Timed(fam, 4.0 * L_tok * L_tok * head_dim * nheads * nprob):
+    with _Timed(fam, 4.0 * L_tok * L_tok * head_dim * nheads * nprob, (fam, L_tok, head_dim, nheads, nprob)):
       rc = L.lib().lav_attn_fwd_ex(_p(qkv), qkv.stride(0), qkv.shape[0], q_off, k_off, v_off, head_dim, nheads, nprob,
                                  L_tok, scale, _p(bias16), bias16.shape[-1] if bias16 is not None else 0,
                                  _p(prob_class), prob_class.numel() if prob_class is not None else 1, _p(key_bias),
@@ -189,7 +190,7 @@ def attn_bwd(qkv, out, dout, lse, dq_acc, dqkv, *, q_off, k_off, v_off, head_dim
              bias16=None, prob_class=None, key_bias=None, ds16=None, drop=None, causal_from=-1):
     fam = "win_attn_bwd" if head_dim == 32 else "bert_attn_bwd"
     delta = torch.empty(nheads, qkv.shape[0], dtype=torch.float32, device=qkv.device)   # workspace: rowsum(dO * O)
-    with _Timed(fam, 8.0 * L_tok * L_tok * head_dim * nheads * nprob):
+    with _Timed(fam, 8.0 * L_tok * L_tok * head_dim * nheads * nprob, (fam, L_tok, head_dim, nheads, nprob)):
       rc = L.lib().lav_attn_bwd_f16(_p(qkv), qkv.stride(0), qkv.shape[0], q_off, k_off, v_off, head_dim, nheads, nprob,
                                   L_tok, scale, _p(bias16), bias16.shape[-1] if bias16 is not None else 0,
                                   _p(prob_class), prob_class.numel() if prob_class is not None else 1,

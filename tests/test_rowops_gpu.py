@@ -7,7 +7,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("rows,C,G", [(1000, 96, 1), (4096, 128, 1), (777, 768, 1), (980, 128, 4), (245, 512, 4),
-                                      (300, 1024, 1)])
+                                      (300, 1024, 1), (7840, 512, 1), (11360, 768, 1), (5000, 1024, 1)])
 def test_layernorm_fwd_bwd(rows, C, G):
     from lavender_b200 import ops
     torch.manual_seed(0)
@@ -45,6 +45,40 @@ def test_layernorm_fwd_bwd(rows, C, G):
         assert (dbeta - bref.grad).abs().max().item() < tol * rows ** 0.5 * 4
         if dx16 is not None:
             assert (dx16.float() - (xg.grad + add)[row_map.long()]).abs().max().item() < 2e-2
+
+
+def test_layernorm_bwd_wide_rows_in_place_and_without_add():
+    """The shared-memory staged kernel (C >= 512) in the two other forms the path uses: in place (add32 is dx32, Swin
+    norm1) and without a residual gradient (BERT), over enough rows for every warp's ring to wrap several times."""
+    from lavender_b200 import ops
+    torch.manual_seed(1)
+    rows, C = 9000, 768
+    x = torch.randn(rows, C, device="cuda") * 1.5 - 0.3
+    gamma = 1 + 0.1 * torch.randn(C, device="cuda")
+    beta = torch.zeros(C, device="cuda")
+    y32 = torch.zeros(rows, C, device="cuda")
+    mean, rstd = torch.zeros(rows, device="cuda"), torch.zeros(rows, device="cuda")
+    ops.layernorm_fwd(x, gamma, beta, 1e-12, rows=rows, C=C, out32=y32, mean=mean, rstd=rstd)
+    xg, gref = x.clone().requires_grad_(True), gamma.clone().requires_grad_(True)
+    dy = torch.randn(rows, C, device="cuda")
+    F.layer_norm(xg, (C,), gref, beta, 1e-12).backward(dy)
+    # BERT form: fp32 dy, no add, dx32 + dx16
+    dx32, dx16 = torch.zeros(rows, C, device="cuda"), torch.zeros(rows, C, device="cuda", dtype=torch.float16)
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    ops.layernorm_bwd(dy, x, gamma, mean, rstd, rows=rows, C=C, dx32=dx32, dx16=dx16, dgamma=dg, dbeta=db)
+    assert (dx32 - xg.grad).abs().max().item() < 2e-4
+    assert (dx16.float() - xg.grad).abs().max().item() < 2e-2
+    assert (dg - gref.grad).abs().max().item() < 0.1 and (db - dy.sum(0)).abs().max().item() < 0.1
+    # Swin norm1 form: fp16 dy, row map, add32 and dx32 the same buffer
+    rmap = torch.randperm(rows, device="cuda").to(torch.int32)
+    g1 = torch.randn(rows, C, device="cuda")
+    want = g1.clone()
+    xs = torch.empty_like(x)
+    xs[rmap.long()] = x   # x stored in source order: output row r reads xs[rmap[r]] = x[r]
+    want[rmap.long()] += xg.grad
+    dg.zero_(), db.zero_()
+    ops.layernorm_bwd(dy.half(), xs, gamma, mean, rstd, rows=rows, C=C, row_map=rmap, add32=g1, dx32=g1, dgamma=dg, dbeta=db)
+    assert (g1 - want).abs().max().item() < 2e-2
 
 
 def test_layernorm_identity_no_map_eps12():

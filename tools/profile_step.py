@@ -73,10 +73,12 @@ def main():
                         for k, v in sorted(fam.items(), key=lambda kv: -kv[1][0])},
            "shapes": {k: {"ms": round(v[0], 3), "n": v[1], "us_each": round(1e3 * v[0] / v[1], 1),
                           "tflops": round(v[2] / v[0] / 1e9, 1) if v[2] else None}
-                      for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][0])[:60]}}
+                      for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][0])[:120]}}
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     json.dump(res, open(a.out, "w"), indent=1)
-    print(json.dumps(res, indent=1)[:6000])
+    print(json.dumps({k: res[k] for k in ("plain_step_ms", "host_issue_ms_per_step", "families")}, indent=1))
+    for k, v in res["shapes"].items():
+        print(f'{v["ms"]:7.3f} ms  n={v["n"]:3d}  {v["us_each"]:7.1f} us  {str(v["tflops"]):>7s} TF  {k}')
 
 
 if __name__ == "__main__":
