@@ -392,6 +392,11 @@ def run_native(a):
         out["window_attention"] = wa
     if world > 1:
         out["dp_check"] = dp
+    if world == 1 and a.workload == "configs1":
+        try:
+            out["input_pipeline"] = input_pipeline_probe(B)
+        except Exception as e:
+            out["input_pipeline"] = {"error": repr(e)[:300]}
     if not a.no_gpu_baseline and world == 1 and a.workload == "configs1":
         phase("PyTorch-eager fp16-autocast baseline on the same GPU")
         try:
@@ -427,6 +432,40 @@ def committed_window_attention_profile():
         return json.load(open(os.path.join(ROOT, "profiles", "r2_window_attention_ncu.json")))
     except Exception:
         return None
+
+
+def input_pipeline_probe(B, T=5, H=360, W=640, S=224):
+    """the frame transform that replaces the loader's PIL / torchvision work (csrc/frames.cu) on the frames of
+    one batch (B clips x T decoded 360x640 uint8 frames -> [B, T, 3, 224, 224] fp32), inputs resident, CUDA events; HBM-bound:
+    algorithmic bytes = uint8 source rows the crop touches + fp32 output."""
+    import torch
+    from lavender_b200.input_pipeline import GpuClipTransform, crop_offsets, resized_size
+    tf = GpuClipTransform(S)
+    src = torch.randint(0, 256, (B * T, H, W, 3), dtype=torch.uint8, device="cuda")
+    dst = torch.empty(B * T, 3, S, S, device="cuda")
+    tf.run(src, (B * T, H, W), out=dst)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 20
+    e0.record()
+    for _ in range(n):
+        tf.run(src, (B * T, H, W), out=dst)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    hr, wr = resized_size(H, W, S)
+    _top, left = crop_offsets(hr, wr, S)
+    src_bytes = B * T * H * int(round(S * W / wr)) * 3        # the source columns under the crop, every row
+    nbytes = src_bytes + dst.numel() * 4
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
+    except Exception:
+        peak = None
+    return {"kernel": "frames_resize_crop_norm_kernel", "frames_per_s": round(B * T / (ms * 1e-3), 0),
+            "clips_per_s": round(B / (ms * 1e-3), 0), "us_per_batch": round(ms * 1e3, 1),
+            "algorithmic_GBps": round(nbytes / (ms * 1e-3) / 1e9, 1), "hbm_peak_GBps": peak,
+            "frac": round(nbytes / (ms * 1e-3) / 1e9 / peak, 4) if peak else None,
+            "parity": "bit-identical uint8 pixels vs PIL/torchvision (tests/test_input_pipeline.py)"}
 
 
 def gpu_torch_baseline(B, steps, warmup):

@@ -139,6 +139,16 @@ int lav_layernorm_bwd(const void* dy, int64_t lddy, int dy_is_f32, const float* 
                       const float* rstd, const float* add32, int64_t ldadd, float* dx32, int64_t lddx32,
                       void* dx16, int64_t lddx16, float* dgamma, float* dbeta, float* param_ws, int64_t ws_floats,
                       int rows, const LavDropout* drop16, void* stream);
+/* Same, with the gradient cast that follows the LayerNorm backward in the Swin block folded in (the scale_cast of
+ * video_swin.py's backward: DropPath scale, :46-54, and the roll + window_partition gather, :218-227, of the gradient):
+ *   dx16[dst row] = fp16( dx16_row_scale[src row / dx16_rows_per_scale] * value ),
+ *   dst row = dx16_row_map[src row] if given, else the src row if dx16_at_src, else r.  G must be 1. */
+int lav_layernorm_bwd_ex(const void* dy, int64_t lddy, int dy_is_f32, const float* x, int64_t ldx,
+                         const int32_t* row_map, int G, int C, const float* gamma, const float* mean,
+                         const float* rstd, const float* add32, int64_t ldadd, float* dx32, int64_t lddx32,
+                         void* dx16, int64_t lddx16, const int32_t* dx16_row_map, int dx16_at_src,
+                         const float* dx16_row_scale, int dx16_rows_per_scale, float* dgamma, float* dbeta,
+                         float* param_ws, int64_t ws_floats, int rows, const LavDropout* drop16, void* stream);
 /* param_ws (may be NULL): caller-owned scratch of ws_floats fp32 (>= 8 * SM count * 2 * C is always enough) for the
  * per-block partial sums of dgamma / dbeta; without it the blocks add to dgamma / dbeta with atomics. */
 /* drop16 (may be NULL): dx16 is additionally multiplied by the dropout mask of site drop16 at (r, column) — the

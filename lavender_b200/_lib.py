@@ -53,6 +53,10 @@ SIGNATURES = {
     "lav_layernorm_bwd": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
                                   c_void_p, c_void_p, c_void_p, c_int64, c_int, ctypes.POINTER(Dropout), c_void_p]),
+    "lav_layernorm_bwd_ex": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
+                                     c_void_p, c_int, c_void_p, c_int,
+                                     c_void_p, c_void_p, c_void_p, c_int64, c_int, ctypes.POINTER(Dropout), c_void_p]),
     "lav_dropout_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, ctypes.POINTER(Dropout), c_void_p]),
     "lav_dropout_mask": (c_int, [c_void_p, c_int, c_int, c_int, ctypes.POINTER(Dropout), c_void_p]),
     "lav_scale_cast_f16": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_float, c_void_p, c_int64, c_int,

@@ -161,7 +161,17 @@ struct LnBwdParams {
   int rows;
   DropParams drop;  // mask applied to dx16 only
   float* param_ws;  // fused parameter gradients: per-block partial sums [grid][2][C] (null: atomics straight to dgamma/dbeta)
+  // where dx16 goes (fused gradient casts, lav_layernorm_bwd_ex): row dx16_map[src row], else the src row, else row r;
+  // multiplied by dx16_scale[src row / dx16_rps] (DropPath keep factor of the consumer)
+  const int32_t* dx16_map; int dx16_at_src; const float* dx16_scale; int dx16_rps;
 };
+
+__device__ __forceinline__ int64_t dx16_row(const LnBwdParams& p, int r, int64_t srow) {
+  return p.dx16_map ? (int64_t)p.dx16_map[srow] : (p.dx16_at_src ? srow : (int64_t)r);
+}
+__device__ __forceinline__ float dx16_factor(const LnBwdParams& p, int64_t srow) {
+  return p.dx16_scale ? p.dx16_scale[srow / p.dx16_rps] : 1.0f;
+}
 
 __device__ __forceinline__ float4 load_dy4(const LnBwdParams& p, int r, int col) {
   if (p.dy_f32) return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.dy) + (int64_t)r * p.lddy + col);
@@ -195,6 +205,8 @@ __global__ void __launch_bounds__(kRowThreads) ln_bwd_kernel(const LnBwdParams p
     for (int g = 0; g < 4; ++g)
       if (g < p.G) srow[g] = p.map ? p.map[(int64_t)r * p.G + g] : (int64_t)r * p.G + g;
     const float mean = p.mean[r], rstd = p.rstd[r];
+    const int64_t drow16 = p.dx16 ? dx16_row(p, r, srow[0]) : 0;
+    const float sc16 = p.dx16 ? dx16_factor(p, srow[0]) : 1.0f;
     float s1 = 0.f, s2 = 0.f;
     if (PARAMS) {  // G == 1: the row lives in registers; every global load is issued before the first use
       float4 v[NV], d[NV], ad[NV];
@@ -241,8 +253,8 @@ __global__ void __launch_bounds__(kRowThreads) ln_bwd_kernel(const LnBwdParams p
               o.x = (m & 1u) ? o.x * p.drop.inv_keep : 0.f, o.y = (m & 2u) ? o.y * p.drop.inv_keep : 0.f;
               o.z = (m & 4u) ? o.z * p.drop.inv_keep : 0.f, o.w = (m & 8u) ? o.w * p.drop.inv_keep : 0.f;
             }
-            *reinterpret_cast<uint2*>(p.dx16 + (int64_t)r * p.lddx16 + col) =
-                make_uint2(pack_half2(o.x, o.y), pack_half2(o.z, o.w));
+            *reinterpret_cast<uint2*>(p.dx16 + drow16 * p.lddx16 + col) =
+                make_uint2(pack_half2(o.x * sc16, o.y * sc16), pack_half2(o.z * sc16, o.w * sc16));
           }
         }
       }
@@ -286,8 +298,8 @@ __global__ void __launch_bounds__(kRowThreads) ln_bwd_kernel(const LnBwdParams p
               o.x = (m & 1u) ? o.x * p.drop.inv_keep : 0.f, o.y = (m & 2u) ? o.y * p.drop.inv_keep : 0.f;
               o.z = (m & 4u) ? o.z * p.drop.inv_keep : 0.f, o.w = (m & 8u) ? o.w * p.drop.inv_keep : 0.f;
             }
-            *reinterpret_cast<uint2*>(p.dx16 + (int64_t)r * p.lddx16 + col) =
-                make_uint2(pack_half2(o.x, o.y), pack_half2(o.z, o.w));
+            *reinterpret_cast<uint2*>(p.dx16 + drow16 * p.lddx16 + col) =
+                make_uint2(pack_half2(o.x * sc16, o.y * sc16), pack_half2(o.z * sc16, o.w * sc16));
           }
         }
   }
@@ -371,6 +383,8 @@ __global__ void __launch_bounds__(kRowThreads, 1) ln_bwd_staged_kernel(const LnB
       const int rn = r + stride;
       mean_n = p.mean[rn], rstd_n = p.rstd[rn], srow_n = p.map ? p.map[rn] : (int64_t)rn;
     }
+    const int64_t drow16 = p.dx16 ? dx16_row(p, r, srow) : 0;
+    const float sc16 = p.dx16 ? dx16_factor(p, srow) : 1.0f;
     mbar_wait(mybar + s, par, 40);
     const uint8_t* st = my + (size_t)s * stage_bytes;
     float4 v[NV], d[NV];
@@ -419,8 +433,8 @@ __global__ void __launch_bounds__(kRowThreads, 1) ln_bwd_staged_kernel(const LnB
             o.x = (m & 1u) ? o.x * p.drop.inv_keep : 0.f, o.y = (m & 2u) ? o.y * p.drop.inv_keep : 0.f;
             o.z = (m & 4u) ? o.z * p.drop.inv_keep : 0.f, o.w = (m & 8u) ? o.w * p.drop.inv_keep : 0.f;
           }
-          *reinterpret_cast<uint2*>(p.dx16 + (int64_t)r * p.lddx16 + col) =
-              make_uint2(pack_half2(o.x, o.y), pack_half2(o.z, o.w));
+          *reinterpret_cast<uint2*>(p.dx16 + drow16 * p.lddx16 + col) =
+              make_uint2(pack_half2(o.x * sc16, o.y * sc16), pack_half2(o.z * sc16, o.w * sc16));
         }
       }
     }
@@ -703,14 +717,27 @@ extern "C" int lav_layernorm_bwd(const void* dy, int64_t lddy, int dy_is_f32, co
                                  const int32_t* row_map, int G, int C, const float* gamma, const float* mean,
                                  const float* rstd, const float* add32, int64_t ldadd, float* dx32, int64_t lddx32,
                                  void* dx16, int64_t lddx16, float* dgamma, float* dbeta, float* param_ws, int64_t ws_floats,
-                      int rows, const LavDropout* drop16, void* stream) {
+                                 int rows, const LavDropout* drop16, void* stream) {
+  return lav_layernorm_bwd_ex(dy, lddy, dy_is_f32, x, ldx, row_map, G, C, gamma, mean, rstd, add32, ldadd, dx32, lddx32, dx16,
+                              lddx16, nullptr, 0, nullptr, 1, dgamma, dbeta, param_ws, ws_floats, rows, drop16, stream);
+}
+
+extern "C" int lav_layernorm_bwd_ex(const void* dy, int64_t lddy, int dy_is_f32, const float* x, int64_t ldx,
+                                    const int32_t* row_map, int G, int C, const float* gamma, const float* mean,
+                                    const float* rstd, const float* add32, int64_t ldadd, float* dx32, int64_t lddx32,
+                                    void* dx16, int64_t lddx16, const int32_t* dx16_row_map, int dx16_at_src,
+                                    const float* dx16_row_scale, int dx16_rows_per_scale, float* dgamma, float* dbeta,
+                                    float* param_ws, int64_t ws_floats, int rows, const LavDropout* drop16, void* stream) {
+  LAV_REQUIRE(!(dx16_row_map || dx16_at_src || dx16_row_scale) || (dx16 && G == 1 && dx16_rows_per_scale >= 1),
+              "lav_layernorm_bwd_ex: the dx16 placement / scale options need dx16, G == 1 and rows_per_scale >= 1");
   LAV_REQUIRE(dy && x && gamma && mean && rstd && (dx32 || dx16), "lav_layernorm_bwd: null pointer");
   LAV_REQUIRE(G >= 1 && G <= 4 && C > 0 && (C % 4) == 0 && (ldx % 4) == 0 && (lddy % 4) == 0,
               "lav_layernorm_bwd: need C%%4==0, 1<=G<=4, ld%%4==0");
   LAV_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "lav_layernorm_bwd: dgamma/dbeta must come together");
   if (rows <= 0) return LAV_OK;
   LnBwdParams p{dy, lddy, dy_is_f32, x, ldx, row_map, G, C, gamma, mean, rstd, add32, ldadd,
-                dx32, lddx32, (__half*)dx16, lddx16, dgamma, dbeta, rows, make_drop(drop16), nullptr};
+                dx32, lddx32, (__half*)dx16, lddx16, dgamma, dbeta, rows, make_drop(drop16), nullptr,
+                dx16_row_map, dx16_at_src, dx16_row_scale, dx16_rows_per_scale > 0 ? dx16_rows_per_scale : 1};
   LAV_REQUIRE(!p.drop.on || (dx16 && G == 1), "lav_layernorm_bwd: drop16 needs dx16 and G == 1");
   cudaStream_t s = (cudaStream_t)stream;
   if (dgamma && G == 1 && C >= 512 && C <= 1024 && (C % 8) == 0 && ln_staged_enabled() &&

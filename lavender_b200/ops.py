@@ -118,21 +118,24 @@ def layernorm_fwd(x, gamma, beta, eps, *, rows, C, G=1, row_map=None, out16=None
 
 
 def layernorm_bwd(dy, x, gamma, mean, rstd, *, rows, C, G=1, row_map=None, add32=None, dx32=None, dx16=None,
-                  dgamma=None, dbeta=None, drop16=None):
+                  dgamma=None, dbeta=None, drop16=None, dx16_map=None, dx16_at_src=False, dx16_scale=None, dx16_rps=1):
+    """dx16 lands at row dx16_map[src row] / the src row (dx16_at_src) / r, times dx16_scale[src row // dx16_rps]:
+    the gradient cast (+ window gather, + DropPath scale) that would otherwise follow as a separate kernel."""
     assert dy.dtype in (F16, torch.float32) and x.dtype == torch.float32
     ws = None
     if dgamma is not None and G == 1 and C <= 1024:   # scratch for the per-block partial sums of dgamma / dbeta
         ws = torch.empty(8 * 148 * 2 * C, dtype=torch.float32, device=x.device)
     with _Timed("layernorm_bwd", 0.0, ("ln_bwd", rows, C, G, row_map is not None, dy.dtype == F16, add32 is not None,
                                        dx32 is not None, dx16 is not None)):
-        rc = L.lib().lav_layernorm_bwd(_p(dy), dy.stride(0), int(dy.dtype == torch.float32), _p(x), x.stride(0),
-                                       _p(row_map), G, C, _p(gamma), _p(mean), _p(rstd),
-                                       _p(add32), add32.stride(0) if add32 is not None else 0,
-                                       _p(dx32), dx32.stride(0) if dx32 is not None else 0,
-                                       _p(dx16), dx16.stride(0) if dx16 is not None else 0,
-                                       _p(dgamma), _p(dbeta), _p(ws), ws.numel() if ws is not None else 0, rows,
-                                       _drop(drop16), _stream())
-    L.check(rc, "lav_layernorm_bwd")
+        rc = L.lib().lav_layernorm_bwd_ex(_p(dy), dy.stride(0), int(dy.dtype == torch.float32), _p(x), x.stride(0),
+                                          _p(row_map), G, C, _p(gamma), _p(mean), _p(rstd),
+                                          _p(add32), add32.stride(0) if add32 is not None else 0,
+                                          _p(dx32), dx32.stride(0) if dx32 is not None else 0,
+                                          _p(dx16), dx16.stride(0) if dx16 is not None else 0,
+                                          _p(dx16_map), int(bool(dx16_at_src)), _p(dx16_scale), int(dx16_rps),
+                                          _p(dgamma), _p(dbeta), _p(ws), ws.numel() if ws is not None else 0, rows,
+                                          _drop(drop16), _stream())
+    L.check(rc, "lav_layernorm_bwd_ex")
 
 
 def scale_cast(x, out16, *, rows, C, row_map=None, row_scale=None, rows_per_scale=1, alpha=1.0):

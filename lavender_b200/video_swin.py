@@ -95,6 +95,18 @@ def window_row_map(B, D, H, W, ws, ss, device):
 
 
 @lru_cache(maxsize=64)
+def window_row_map_inv(B, D, H, W, ws, ss, device):
+    """inv[token-major row] = window-major row (the map above is a permutation: the feature map divides the window)."""
+    m = window_row_map(B, D, H, W, ws, ss, device).long()
+    inv = torch.empty_like(m, dtype=torch.int32)
+    inv[m] = torch.arange(m.numel(), dtype=torch.int32, device=m.device)
+    return inv
+
+
+FUSE_CASTS = os.environ.get("LAV_FUSE_CASTS", "1") != "0"   # gradient casts emitted by the LayerNorm backward kernels
+
+
+@lru_cache(maxsize=64)
 def merge_row_map(B, D, H, W, device):
     """map[r*4+g] for PatchMerging (video_swin.py:278-282): x0=(even h, even w), x1=(odd h, even w),
     x2=(even h, odd w), x3=(odd h, odd w)."""
@@ -353,10 +365,12 @@ class _SwinFn(torch.autograd.Function):
             for b, blk in enumerate(layer.blocks):
                 ss = ss_full if any(v > 0 for v in blk.shift_size) else (0, 0, 0)
                 rmap = window_row_map(B, D, Hc, Wc, ws, ss, dev)
+                rinv = window_row_map_inv(B, D, Hc, Wc, ws, ss, dev) if FUSE_CASTS else None
                 labels, cls_of = shift_mask_classes(D, Hc, Wc, ws, ss, dev)
                 k1 = keep[bi, 0].contiguous() if keep is not None and blk.drop_path_rate > 0 else None
                 k2 = keep[bi, 1].contiguous() if keep is not None and blk.drop_path_rate > 0 else None
                 xcur, sv = _block_fwd(ar, blk, xcur, M, C, N, NP, B * nW, rmap, labels, cls_of, k1, k2, rps, dev)
+                sv["rinv"] = rinv
                 saved["blocks"].append(sv)
                 bi += 1
             if layer.downsample is not None:
@@ -398,10 +412,19 @@ class _SwinFn(torch.autograd.Function):
         gout2 = gout.reshape(M, C)
         if not gout2.is_contiguous():
             gout2 = gout2.contiguous()
-        ops.layernorm_bwd(gout2, xin, mod.norm.weight, fm, fr, rows=M, C=C, dx32=g, dgamma=ar.g(mod.norm.weight),
-                          dbeta=ar.g(mod.norm.bias))
         blocks = saved["blocks"]
         bi = len(blocks)
+        # fused gradient casts: every LayerNorm backward that produces a block-input gradient also emits the fp16 operand
+        # its consumer starts with (the next block's MLP branch: DropPath-scaled; a PatchMerging reduction: plain)
+        g16 = None
+        if FUSE_CASTS and bi > 0:
+            g16 = empty16(M, C, device=dev)
+            ops.layernorm_bwd(gout2, xin, mod.norm.weight, fm, fr, rows=M, C=C, dx32=g, dx16=g16, dx16_at_src=True,
+                              dx16_scale=blocks[-1]["k2"], dx16_rps=blocks[-1]["rps"], dgamma=ar.g(mod.norm.weight),
+                              dbeta=ar.g(mod.norm.bias))
+        else:
+            ops.layernorm_bwd(gout2, xin, mod.norm.weight, fm, fr, rows=M, C=C, dx32=g, dgamma=ar.g(mod.norm.weight),
+                              dbeta=ar.g(mod.norm.bias))
         ds_ws = {}
         for s in range(mod.num_layers - 1, -1, -1):
             layer = mod.layers[s]
@@ -411,16 +434,25 @@ class _SwinFn(torch.autograd.Function):
                 ds = layer.downsample
                 xprev, y16, mm, mr, mmap, Mp, Cp = saved["merges"][s]
                 M4 = Mp // 4
-                g16 = ops.scale_cast(g, empty16(M4, 2 * Cp, device=dev), rows=M4, C=2 * Cp)
+                if g16 is None:
+                    g16 = ops.scale_cast(g, empty16(M4, 2 * Cp, device=dev), rows=M4, C=2 * Cp)
                 linear_wgrad(g16, y16, ar.g(ds.reduction.weight))
                 dy16 = empty16(M4, 4 * Cp, device=dev)
                 linear_dgrad(g16, ar.w16(ds.reduction.weight), dy16)
                 g = empty32(Mp, Cp, device=dev)
                 ops.layernorm_bwd(dy16, xprev, ds.norm.weight, mm, mr, rows=M4, C=Cp, G=4, row_map=mmap, dx32=g,
                                   dgamma=ar.g(ds.norm.weight), dbeta=ar.g(ds.norm.bias))
+                g16 = None   # (the G = 4 scatter kernel has no fused fp16 output)
             for b in range(layer.depth - 1, -1, -1):
                 bi -= 1
-                g = _block_bwd(ar, layer.blocks[b], g, blocks[bi], ds_ws, dev)
+                # consumer of this block's input gradient: the previous block (its k2), a PatchMerging (plain), or the
+                # patch embedding's LayerNorm (fp32: nothing to emit)
+                emit = None
+                if FUSE_CASTS and b > 0:
+                    emit = (blocks[bi - 1]["k2"], blocks[bi - 1]["rps"])
+                elif FUSE_CASTS and s > 0:
+                    emit = (None, 1)
+                g, g16 = _block_bwd(ar, layer.blocks[b], g, blocks[bi], ds_ws, dev, g16, emit)
         for old in ds_ws.values():   # the side stream may still read the last dS workspaces
             streams.hold(dev, *old["bufs"])
         cols16, y, pm, pr = saved["pe"]
@@ -488,14 +520,17 @@ def _block_fwd(ar, blk, x, M, C, N, NP, nprob, rmap, labels, cls_of, k1, k2, rps
     return x2, sv
 
 
-def _block_bwd(ar, blk, g, sv, ds_ws, dev):
+def _block_bwd(ar, blk, g, sv, ds_ws, dev, g16=None, emit=None):
+    """g16: fp16(k2 * g) if the producer of g already emitted it; emit = (row scale or None, rows per scale) asks norm1's
+    backward for the fp16 operand of this block's consumer.  Returns (input gradient fp32, that operand or None)."""
     at = blk.attn
     M, C, N, NP, nprob, rps = sv["M"], sv["C"], sv["N"], sv["NP"], sv["nprob"], sv["rps"]
     nh = blk.num_heads
     hd = C // nh
     fc1, fc2 = blk.mlp.fc1, blk.mlp.fc2
     # ---- MLP branch: x2 = x1 + k2 * (fc2(gelu(fc1(LN2(x1)))))
-    g16 = ops.scale_cast(g, empty16(M, C, device=dev), rows=M, C=C, row_scale=sv["k2"], rows_per_scale=rps)
+    if g16 is None:
+        g16 = ops.scale_cast(g, empty16(M, C, device=dev), rows=M, C=C, row_scale=sv["k2"], rows_per_scale=rps)
     linear_wgrad(g16, sv["h16"], ar.g(fc2.weight), ar.g(fc2.bias))
     da16 = empty16(M, 4 * C, device=dev)
     linear_dgrad(g16, ar.w16(fc2.weight), da16, act=L.ACT_GELU_BWD, aux=sv["a16"])
@@ -503,11 +538,17 @@ def _block_bwd(ar, blk, g, sv, ds_ws, dev):
     dy2 = empty16(M, C, device=dev)
     linear_dgrad(da16, ar.w16(fc1.weight), dy2)
     g1 = empty32(M, C, device=dev)
-    ops.layernorm_bwd(dy2, sv["x1"], blk.norm2.weight, sv["m2"], sv["r2"], rows=M, C=C, add32=g, dx32=g1,
-                      dgamma=ar.g(blk.norm2.weight), dbeta=ar.g(blk.norm2.bias))
     # ---- attention branch: x1[map] = x[map] + k1 * proj(attn(qkv(LN1(x)[map])))
-    go16 = ops.scale_cast(g1, empty16(M, C, device=dev), rows=M, C=C, row_map=sv["rmap"], row_scale=sv["k1"],
-                          rows_per_scale=rps)
+    if sv.get("rinv") is not None:   # norm2's backward also writes go16 = fp16(k1 * g1) in window order
+        go16 = empty16(M, C, device=dev)
+        ops.layernorm_bwd(dy2, sv["x1"], blk.norm2.weight, sv["m2"], sv["r2"], rows=M, C=C, add32=g, dx32=g1, dx16=go16,
+                          dx16_map=sv["rinv"], dx16_scale=sv["k1"], dx16_rps=rps,
+                          dgamma=ar.g(blk.norm2.weight), dbeta=ar.g(blk.norm2.bias))
+    else:
+        ops.layernorm_bwd(dy2, sv["x1"], blk.norm2.weight, sv["m2"], sv["r2"], rows=M, C=C, add32=g, dx32=g1,
+                          dgamma=ar.g(blk.norm2.weight), dbeta=ar.g(blk.norm2.bias))
+        go16 = ops.scale_cast(g1, empty16(M, C, device=dev), rows=M, C=C, row_map=sv["rmap"], row_scale=sv["k1"],
+                              rows_per_scale=rps)
     linear_wgrad(go16, sv["o16"], ar.g(at.proj.weight), ar.g(at.proj.bias))
     do16 = empty16(M, C, device=dev)
     linear_dgrad(go16, ar.w16(at.proj.weight), do16)
@@ -544,9 +585,16 @@ def _block_bwd(ar, blk, g, sv, ds_ws, dev):
     linear_wgrad(dqkv16, sv["y16"], ar.g(at.qkv.weight), ar.g(at.qkv.bias))
     dy1 = empty16(M, C, device=dev)
     linear_dgrad(dqkv16, ar.w16(at.qkv.weight), dy1)
-    ops.layernorm_bwd(dy1, sv["x"], blk.norm1.weight, sv["m1"], sv["r1"], rows=M, C=C, row_map=sv["rmap"], add32=g1,
-                      dx32=g1, dgamma=ar.g(blk.norm1.weight), dbeta=ar.g(blk.norm1.bias))
-    return g1
+    gn16 = None
+    if emit is not None:
+        gn16 = empty16(M, C, device=dev)
+        ops.layernorm_bwd(dy1, sv["x"], blk.norm1.weight, sv["m1"], sv["r1"], rows=M, C=C, row_map=sv["rmap"], add32=g1,
+                          dx32=g1, dx16=gn16, dx16_at_src=True, dx16_scale=emit[0], dx16_rps=emit[1],
+                          dgamma=ar.g(blk.norm1.weight), dbeta=ar.g(blk.norm1.bias))
+    else:
+        ops.layernorm_bwd(dy1, sv["x"], blk.norm1.weight, sv["m1"], sv["r1"], rows=M, C=C, row_map=sv["rmap"], add32=g1,
+                          dx32=g1, dgamma=ar.g(blk.norm1.weight), dbeta=ar.g(blk.norm1.bias))
+    return g1, gn16
 
 
 def _rel_index(attn, N, dev):

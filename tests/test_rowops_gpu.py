@@ -81,6 +81,46 @@ def test_layernorm_bwd_wide_rows_in_place_and_without_add():
     assert (g1 - want).abs().max().item() < 2e-2
 
 
+@pytest.mark.parametrize("rows,C,rps", [(245 * 8, 128, 245), (7840, 512, 980), (1960, 1024, 245)])
+def test_layernorm_bwd_fused_gradient_casts(rows, C, rps):
+    """lav_layernorm_bwd_ex: the fp16 operand of the consumer (window-gathered / DropPath-scaled) written by the LayerNorm
+    backward itself equals the separate scale_cast kernel applied to its fp32 output."""
+    from lavender_b200 import ops
+    torch.manual_seed(2)
+    x = torch.randn(rows, C, device="cuda")
+    gamma = 1 + 0.1 * torch.randn(C, device="cuda")
+    mean, rstd = x.mean(1).contiguous(), (x.var(1, unbiased=False) + 1e-5).rsqrt().contiguous()
+    dy = torch.randn(rows, C, device="cuda").half()
+    add = torch.randn(rows, C, device="cuda")
+    # window partition permutes rows inside a sample only (the scale is per sample on both sides of the map)
+    rmap = torch.cat([torch.randperm(rps, device="cuda") + i * rps for i in range(rows // rps)]).to(torch.int32)
+    rinv = torch.empty_like(rmap)
+    rinv[rmap.long()] = torch.arange(rows, device="cuda", dtype=torch.int32)
+    keep = (torch.rand(rows // rps, device="cuda") > 0.3).float() / 0.7
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    # (1) norm2 form: token-order rows, fp16 output scattered to window order, scaled per sample
+    dx32 = torch.zeros(rows, C, device="cuda")
+    fused = torch.zeros(rows, C, device="cuda", dtype=torch.float16)
+    ops.layernorm_bwd(dy, x, gamma, mean, rstd, rows=rows, C=C, add32=add, dx32=dx32, dx16=fused, dx16_map=rinv,
+                      dx16_scale=keep, dx16_rps=rps, dgamma=dg, dbeta=db)
+    want = ops.scale_cast(dx32, torch.zeros_like(fused), rows=rows, C=C, row_map=rmap, row_scale=keep, rows_per_scale=rps)
+    assert (fused.float() - want.float()).abs().max().item() <= 1e-3 * want.float().abs().max().item()
+    assert (fused != want).float().mean().item() < 1e-3
+    # (2) norm1 form: window-order rows scattered to token order (in place on add32), fp16 output at the token rows
+    g1 = add.clone()
+    fused2 = torch.zeros(rows, C, device="cuda", dtype=torch.float16)
+    ops.layernorm_bwd(dy, x, gamma, mean, rstd, rows=rows, C=C, row_map=rmap, add32=g1, dx32=g1, dx16=fused2,
+                      dx16_at_src=True, dx16_scale=keep, dx16_rps=rps, dgamma=dg, dbeta=db)
+    want2 = ops.scale_cast(g1, torch.zeros_like(fused2), rows=rows, C=C, row_scale=keep, rows_per_scale=rps)
+    assert (fused2 != want2).float().mean().item() < 1e-3
+    # (3) plain (PatchMerging consumer): no scale
+    fused3 = torch.zeros(rows, C, device="cuda", dtype=torch.float16)
+    g2 = add.clone()
+    ops.layernorm_bwd(dy, x, gamma, mean, rstd, rows=rows, C=C, row_map=rmap, add32=g2, dx32=g2, dx16=fused3,
+                      dx16_at_src=True, dgamma=dg, dbeta=db)
+    assert (fused3 != g2.half()).float().mean().item() < 1e-3
+
+
 def test_layernorm_identity_no_map_eps12():
     from lavender_b200 import ops
     x = torch.randn(333, 768, device="cuda")
