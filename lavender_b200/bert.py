@@ -385,10 +385,20 @@ class BertOnlyMLMHead(nn.Module):
         return _MLMHeadFn.apply(sequence_output, self, p.transform.dense.weight, p.transform.dense.bias,
                                 p.transform.LayerNorm.weight, p.transform.LayerNorm.bias, p.decoder.weight, p.bias)
 
+    def forward_split(self, rows, split):
+        """One head pass over `rows` [M, H] returned as two logits tensors (rows [:split] and [split:]): the MLM and VTM rows
+        of a pre-training step share the transform / decoder GEMMs, the decoder weight gradient and the logit-gradient
+        cast instead of running the 30522-wide head twice on 128 + 32 rows (main_pretrain_mlm.py:69,115 call it twice)."""
+        require_cuda(rows, "BertOnlyMLMHead")
+        assert rows.dim() == 2 and 0 < split < rows.shape[0]
+        p = self.predictions
+        return _MLMHeadFn.apply(rows, self, p.transform.dense.weight, p.transform.dense.bias, p.transform.LayerNorm.weight,
+                                p.transform.LayerNorm.bias, p.decoder.weight, p.bias, split)
+
 
 class _MLMHeadFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, mod, wd, bd, gamma, beta, wdec, bdec):
+    def forward(ctx, x, mod, wd, bd, gamma, beta, wdec, bdec, split=0):
         dev = x.device
         ar = arena_of(mod)
         ar.refresh16()
@@ -417,28 +427,41 @@ class _MLMHeadFn(torch.autograd.Function):
         else:
             linear_fwd(t16, ar.w16(wdec), bdec, logits[:, :V])
         ctx.mod, ctx.params = mod, (wd, bd, gamma, beta, wdec, bdec)
-        ctx.saved, ctx.shp = (x16, pre16, t32, mean, rstd, t16), shp
+        ctx.saved, ctx.shp, ctx.split = (x16, pre16, t32, mean, rstd, t16), shp, split
+        if split:
+            return logits[:split, :V], logits[split:, :V]
         return logits[:, :V].view(*shp[:-1], V)
 
     @staticmethod
-    def backward(ctx, gl):
+    def backward(ctx, *gls):
         mod = ctx.mod
         wd, bd, gamma, beta, wdec, bdec = ctx.params
         x16, pre16, t32, mean, rstd, t16 = ctx.saved
         ar = arena_of(mod)
         ar.prepare_grads([wd, bd, gamma, beta, wdec, bdec])
-        dev = gl.device
+        dev = x16.device
         M, H = x16.shape
         V = wdec.shape[0]
         Vp = (V + 7) // 8 * 8
-        g2 = gl.reshape(M, V)
         gl16 = torch.zeros(M, Vp, dtype=F16, device=dev) if Vp != V else empty16(M, Vp, device=dev)
-        ops.scale_cast(g2, gl16, rows=M, C=V)
+        r0 = 0
+        for gl, n in zip(gls, (ctx.split, M - ctx.split) if ctx.split else (M,)):
+            if gl is not None:
+                ops.scale_cast(gl.reshape(n, V), gl16[r0:r0 + n], rows=n, C=V)
+            elif Vp == V:
+                gl16[r0:r0 + n].zero_()
+            r0 += n
         linear_wgrad(gl16, t16, ar.g(wdec), ar.g(bdec), n_valid=V)
-        dt16 = empty16(M, H, device=dev)
-        ops.gemm(gl16, ar.w16(wdec), dt16, M=M, N=H, K=V, b_major=L.MAJOR_MN)
+        if M <= 1024:
+            # skinny rows x K = vocab: 3-12 output tiles for 148 SMs -> split-K into a zeroed fp32 buffer (r1: one CTA per
+            # tile walked all 477 k-blocks: 180-280 us per call for 6 GFLOP)
+            dt = torch.zeros(M, H, dtype=F32, device=dev)
+            ops.gemm(gl16, ar.w16(wdec), dt, M=M, N=H, K=V, b_major=L.MAJOR_MN, accumulate=True)
+        else:
+            dt = empty16(M, H, device=dev)
+            ops.gemm(gl16, ar.w16(wdec), dt, M=M, N=H, K=V, b_major=L.MAJOR_MN)
         dpre_g = empty16(M, H, device=dev)  # grad wrt gelu output (fp16), then through gelu'
-        ops.layernorm_bwd(dt16, t32, gamma, mean, rstd, rows=M, C=H, dx16=dpre_g, dgamma=ar.g(gamma), dbeta=ar.g(beta))
+        ops.layernorm_bwd(dt, t32, gamma, mean, rstd, rows=M, C=H, dx16=dpre_g, dgamma=ar.g(gamma), dbeta=ar.g(beta))
         dpre16 = ops.gelu_bwd(dpre_g, pre16, empty16(M, H, device=dev))
         linear_wgrad(dpre16, x16, ar.g(wd), ar.g(bd))
         gx = None
@@ -446,7 +469,7 @@ class _MLMHeadFn(torch.autograd.Function):
             gx = empty32(M, H, device=dev)
             linear_dgrad(dpre16, ar.w16(wd), gx)
             gx = gx.view(ctx.shp)
-        return (gx,) + (None,) * 7
+        return (gx,) + (None,) * 8
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -420,12 +420,31 @@ relpos_bias_grad_kernel(const __half* ds, int nprob, int nheads, int NP, int L, 
   const int p0 = blockIdx.y * probs_per_block, p1 = min(nprob, p0 + probs_per_block);
   for (int jb = lane * 8; jb < NP; jb += 256) {
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int pr = p0; pr < p1; ++pr) {
-      uint4 u = *reinterpret_cast<const uint4*>(ds + (((size_t)pr * nheads + h) * NP + i) * NP + jb);
+    const size_t pstride = (size_t)nheads * NP * NP;
+    const __half* src = ds + (((size_t)p0 * nheads + h) * NP + i) * NP + jb;
+    int pr = p0;
+    // 8 problems per trip, all eight 16-byte loads issued before the first add: the rows of one (h, i) are a whole
+    // [nheads, NP, NP] slab apart, so the memory-level parallelism has to come from here (r1: one load in flight per lane)
+    for (; pr + 8 <= p1; pr += 8, src += 8 * pstride) {
+      uint4 u[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) u[k] = __ldcs(reinterpret_cast<const uint4*>(src + k * pstride));
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const __half2* hh = reinterpret_cast<const __half2*>(&u[k]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = __half22float2(hh[q]);
+          acc[2 * q] += f.x, acc[2 * q + 1] += f.y;
+        }
+      }
+    }
+    for (; pr < p1; ++pr, src += pstride) {
+      const uint4 u = __ldcs(reinterpret_cast<const uint4*>(src));
       const __half2* hh = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        float2 f = __half22float2(hh[q]);
+        const float2 f = __half22float2(hh[q]);
         acc[2 * q] += f.x, acc[2 * q + 1] += f.y;
       }
     }

@@ -271,6 +271,9 @@ __device__ __forceinline__ void epilogue_warps_tma2(const GemmParams& p, const C
       const int col = n0 + (wg + 2 * k) * 32 + lane;
       bl[k] = (e.bias && wg + 2 * k < nchunks && col < p.N) ? __ldg(e.bias + col) : 0.f;
     }
+    // (r2: a coalesced load of the GELU' input + transpose through the staging buffer was measured SLOWER than this
+    // thread = row load - 51 vs 48 us on 7840 x 2048 x 512 - because the transpose has to wait for the staging buffer's
+    // previous TMA store; see profiles/r2_gemm_ablation.md)
     auto load_aux = [&](uint4(&ax)[4], int c) {
       const int col0 = n0 + c * 32;
       const __half* xa = reinterpret_cast<const __half*>(e.aux) + (size_t)min(row, p.M - 1) * e.ldaux + col0;
@@ -688,7 +691,9 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       else if (st == ST_F32_RMW) LAV_EPI(LAV_ACT_NONE, 0, ST_F32_RMW);
       else LAV_EPI(LAV_ACT_NONE, 0, ST_F32);
     } else if constexpr (BMAJ == LAV_MAJOR_MN) {
-      if (p.tma_store) {
+      if (e.accumulate == LAV_ACCUMULATE) {  // split-K dgrad of a skinny problem (MLM decoder: M <= 160, K = vocab): fp32 atomics
+        LAV_EPI(LAV_ACT_NONE, 0, ST_F32_RED);
+      } else if (p.tma_store) {
         if (e.act == LAV_ACT_GELU_BWD) LAV_EPI_TMA(LAV_ACT_GELU_BWD, false);
         else if (st == ST_F16) LAV_EPI_TMA(LAV_ACT_NONE, false);
         else LAV_EPI_TMA(LAV_ACT_NONE, true);
@@ -820,8 +825,9 @@ extern "C" int lav_gemm_f16(const void* A, int64_t lda, int a_major, const void*
     bool ok;
     if (a_major == LAV_MAJOR_MN)        // wgrad: plain fp32 store / accumulate
       ok = epi->act == LAV_ACT_NONE && !f16o && !epi->residual && !epi->row_map && !epi->row_scale;
-    else if (b_major == LAV_MAJOR_MN)   // dgrad: plain / GELU' / fp32 residual
-      ok = epi->act != LAV_ACT_GELU && !acc && !(epi->residual && f16o) && !(epi->residual && epi->act != LAV_ACT_NONE);
+    else if (b_major == LAV_MAJOR_MN)   // dgrad: plain / GELU' / fp32 residual / plain fp32 accumulate (split-K)
+      ok = epi->act != LAV_ACT_GELU && !(epi->residual && f16o) && !(epi->residual && epi->act != LAV_ACT_NONE) &&
+           (!acc || (epi->act == LAV_ACT_NONE && !f16o && !epi->residual && !epi->row_map && !epi->row_scale && !epi->bias));
     else                                // forward
       ok = epi->act != LAV_ACT_GELU_BWD && !acc && !(epi->residual && f16o);
     LAV_REQUIRE(ok, "lav_gemm_f16: this (operand layout, epilogue) combination is not instantiated (a_major %d b_major %d "

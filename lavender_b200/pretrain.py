@@ -28,6 +28,7 @@ class LAVENDER_Pretrain_MLM(LAVENDER_Base):
         # one merged fusion-encoder pass for MLM + VTM (see forward); LAV_MERGE_PASSES=0 keeps the two passes
         self.merge_passes = os.environ.get("LAV_MERGE_PASSES", "1") != "0"
         self.vtm_last_token_only = os.environ.get("LAV_VTM_FULL_LOGITS", "0") != "1"
+        self.merge_heads = os.environ.get("LAV_MERGE_HEADS", "1") != "0"   # MLM + VTM rows through one head pass
 
     @staticmethod
     def draw_negatives(B, O):
@@ -96,8 +97,14 @@ class LAVENDER_Pretrain_MLM(LAVENDER_Base):
             # unlabelled row), so the gather has a static shape and the step stays CUDA-graph capturable; loss and
             # gradients are identical because unlabelled rows contribute nothing to the cross-entropy.
             h = out[:B, Lv + d:].reshape(B * Lt, Hh)
-            out_mtm = self.fc_mtm(h.index_select(0, rows)).unsqueeze(0)          # [1, capacity, vocab]
             ans_mtm = ans_mtm.reshape(-1).index_select(0, rows).unsqueeze(0)     # [1, capacity] (-1 on padding)
+            if self.vtm_last_token_only and self.merge_heads:
+                # both heads in ONE pass over the capacity + B*O labelled rows (BertOnlyMLMHead.forward_split)
+                hm = torch.cat([h.index_select(0, rows), out[B:, -1]], 0)
+                out_mtm, out_vtm = self.fc_mtm.forward_split(hm, rows.numel())
+                return {"out_vtm": out_vtm.unsqueeze(1), "out_mtm": out_mtm.unsqueeze(0), "ans_vtm": ans_vtm[:, -1:],
+                        "ans_mtm": ans_mtm}
+            out_mtm = self.fc_mtm(h.index_select(0, rows)).unsqueeze(0)          # [1, capacity, vocab]
         else:
             out_mtm = self.fc_mtm(out[:B, Lv + d:])   # (two head calls: one merged logits tensor would make autograd
             #                                            materialise two zero-padded [rows, vocab] gradients and add them)

@@ -203,7 +203,8 @@ def test_reference_style_loop_equals_batched_pairs():
 def test_merged_pass_and_last_token_head_equal_the_two_pass_formulation():
     """train()-mode step (DropPath active with a fixed seed, BERT dropout off) in three formulations that must agree:
     the reference's two fusion-encoder passes with full VTM logits; one merged pass (MLM rows padded with key-masked
-    dummy tokens); merged pass + the MLM head on the labelled (last) VTM position only."""
+    dummy tokens); merged pass + the MLM head on the labelled (last) VTM position only; + the MLM head on the gathered
+    labelled rows (two head calls); + both heads in one pass over the concatenated rows (forward_split)."""
     import lavender_oracle as O
     from lavender_b200.bert import CrossEntropyLoss
     m, cfg, sd = _build("tiny", 2, 3, True, 1)
@@ -213,14 +214,23 @@ def test_merged_pass_and_last_token_head_equal_the_two_pass_formulation():
     batch = {k: v.cuda() for k, v in O.make_batch(3, seed=1).items()}
     ce = CrossEntropyLoss(ignore_index=-1)
     res = []
-    for merge, last in ((False, False), (True, False), (True, True)):
-        m.merge_passes, m.vtm_last_token_only = merge, last
+    # the fixed-capacity list of labelled MLM rows the agent builds next to ans_mtm (agent.labelled_rows)
+    flat = batch["ans_mtm"].reshape(-1)
+    lab, un = (flat != -1).nonzero().reshape(-1), (flat == -1).nonzero().reshape(-1)
+    rows = torch.cat([lab, un[:1].expand(min(128, flat.numel()) - lab.numel())]).contiguous()
+    for merge, last, use_rows, heads in ((False, False, False, False), (True, False, False, False), (True, True, False, False),
+                                         (True, True, True, False), (True, True, True, True)):
+        m.merge_passes, m.vtm_last_token_only, m.merge_heads = merge, last, heads
         for p in m.parameters():
             p.grad = None
         torch.manual_seed(7)
         np.random.seed(7)
-        out = m(dict(batch))
+        b2 = dict(batch)
+        if use_rows:
+            b2["mtm_rows"] = rows
+        out = m(b2)
         assert out["out_vtm"].shape[1] == (1 if last else 34)
+        assert out["out_mtm"].shape[:2] == ((1, rows.numel()) if use_rows else batch["ans_mtm"].shape)
         l1 = ce(out["out_mtm"].flatten(0, 1), out["ans_mtm"].flatten())
         l2 = ce(out["out_vtm"].flatten(0, 1), out["ans_vtm"].flatten())
         ((l1 + l2) * 1024.0).backward()

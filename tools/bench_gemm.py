@@ -61,6 +61,13 @@ def main():
                   ("bert_ffn2_dgrad_gelu", 11360, 3072, 768, "dgrad_gelu"), ("bert_ffn1_dgrad", 11360, 768, 3072, "dgrad"),
                   ("bert_qkv_dgrad", 11360, 768, 2304, "dgrad"), ("bert_ffn1_wgrad", 3072, 768, 11360, "wgrad"),
                   ("bert_qkv_wgrad", 2304, 768, 11360, "wgrad")]
+    if "--head" in sys.argv:  # MLM head (vocab 30522) on the labelled rows: 128 MLM + 32 VTM, separately and merged
+        shapes = [("dec_fwd_128", 128, 30522, 768, "fwd32"), ("dec_fwd_32", 32, 30522, 768, "fwd32"),
+                  ("dec_fwd_160", 160, 30522, 768, "fwd32"),
+                  ("dec_dgrad_128", 128, 768, 30522, "dgrad"), ("dec_dgrad_32", 32, 768, 30522, "dgrad"),
+                  ("dec_dgrad_acc_128", 128, 768, 30522, "dgrad_acc"), ("dec_dgrad_acc_160", 160, 768, 30522, "dgrad_acc"),
+                  ("dec_wgrad_128", 30522, 768, 128, "wgrad"), ("dec_wgrad_32", 30522, 768, 32, "wgrad"),
+                  ("dec_wgrad_160", 30522, 768, 160, "wgrad")]
     only = [a for a in sys.argv[1:] if not a.startswith("-")]
     if only:
         shapes = [s_ for s_ in shapes if s_[0] in only]
@@ -69,8 +76,13 @@ def main():
             a = torch.randn(K, M, device="cuda").half()
             b = torch.randn(K, N, device="cuda").half()
             out = torch.zeros(M, N, device="cuda")
-            bg = torch.zeros(M, device="cuda") if "--hot" in sys.argv else None   # the path's wgrads carry the bias gradient
+            bg = torch.zeros(M, device="cuda") if ("--hot" in sys.argv or "--head" in sys.argv) else None   # the path's wgrads carry the bias gradient
             fn = lambda: ops.gemm(a, b, out, M=M, N=N, K=K, a_major=1, b_major=1, accumulate=True, bias_grad=bg)
+        elif mode == "dgrad_acc":   # split-K dgrad into a zeroed fp32 buffer (skinny M, huge K)
+            a = torch.randn(M, K, device="cuda").half()
+            b = torch.randn(K, N, device="cuda").half()
+            out = torch.zeros(M, N, device="cuda")
+            fn = lambda: ops.gemm(a, b, out, M=M, N=N, K=K, b_major=1, accumulate=True)
         elif mode in ("dgrad", "dgrad_gelu"):
             a = torch.randn(M, K, device="cuda").half()
             b = torch.randn(K, N, device="cuda").half()
@@ -105,7 +117,7 @@ def main():
             ms_t = float("nan")
         elif mode == "wgrad":
             ms_t = timeit(lambda: torch.matmul(a.t(), b), flush=flush)
-        elif mode in ("dgrad", "dgrad_gelu"):
+        elif mode in ("dgrad", "dgrad_gelu", "dgrad_acc"):
             ms_t = timeit(lambda: torch.matmul(a, b), flush=flush)
         else:
             ms_t = timeit(lambda: torch.matmul(a, b.t()), flush=flush)
