@@ -64,10 +64,10 @@ def main():
     if "--head" in sys.argv:  # MLM head (vocab 30522) on the labelled rows: 128 MLM + 32 VTM, separately and merged
         shapes = [("dec_fwd_128", 128, 30522, 768, "fwd32"), ("dec_fwd_32", 32, 30522, 768, "fwd32"),
                   ("dec_fwd_160", 160, 30522, 768, "fwd32"),
-                  ("dec_dgrad_128", 128, 768, 30522, "dgrad"), ("dec_dgrad_32", 32, 768, 30522, "dgrad"),
-                  ("dec_dgrad_acc_128", 128, 768, 30522, "dgrad_acc"), ("dec_dgrad_acc_160", 160, 768, 30522, "dgrad_acc"),
-                  ("dec_wgrad_128", 30522, 768, 128, "wgrad"), ("dec_wgrad_32", 30522, 768, 32, "wgrad"),
-                  ("dec_wgrad_160", 30522, 768, 160, "wgrad")]
+                  ("dec_dgrad_128", 128, 768, 30528, "dgrad"), ("dec_dgrad_32", 32, 768, 30528, "dgrad"),
+                  ("dec_dgrad_acc_128", 128, 768, 30528, "dgrad_acc"), ("dec_dgrad_acc_160", 160, 768, 30528, "dgrad_acc"),
+                  ("dec_wgrad_128", 30528, 768, 128, "wgrad"), ("dec_wgrad_32", 30528, 768, 32, "wgrad"),
+                  ("dec_wgrad_160", 30528, 768, 160, "wgrad")]   # (vocab padded to 30528: 16-byte aligned fp16 rows)
     only = [a for a in sys.argv[1:] if not a.startswith("-")]
     if only:
         shapes = [s_ for s_ in shapes if s_[0] in only]

@@ -47,6 +47,15 @@ for tag, rows, C, mapped in SHAPES:
     dg, db = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
     t_b = timeit(lambda: ops.layernorm_bwd(dy, x, gamma, mean, rstd, rows=rows, C=C, row_map=rmap, add32=add, dx32=dx,
                                            dgamma=dg, dbeta=db))
+    if tag == "bert":   # the two forms BERT's layer backward uses: fp32 dy, no residual gradient, dx32 + dx16 (+ dropout mask)
+        dy32 = dy.float()
+        dx16 = torch.empty(rows, C, dtype=torch.float16, device=dev)
+        rng = torch.tensor([1234, 7], dtype=torch.int64, device=dev)
+        for name, drop in (("bert_form", None), ("bert_form_dropout", (rng, 3, 0.1))):
+            t = timeit(lambda: ops.layernorm_bwd(dy32, x, gamma, mean, rstd, rows=rows, C=C, dx32=dx, dx16=dx16, dgamma=dg,
+                                                 dbeta=db, drop16=drop))
+            print(json.dumps({"tag": name, "rows": rows, "C": C, "ln_bwd_us": round(t, 1),
+                              "ln_bwd_GBps": round(rows * C * 14 / t / 1e3, 0)}))
     o16 = torch.empty(rows, C, dtype=torch.float16, device=dev)
     t_c = timeit(lambda: ops.scale_cast(x, o16, rows=rows, C=C))
     rec = {"tag": tag, "rows": rows, "C": C,
