@@ -457,8 +457,8 @@ class _MLMHeadFn(torch.autograd.Function):
             # tile walked all 477 k-blocks: 180-280 us per call for 6 GFLOP)
             dt = torch.zeros(M, H, dtype=F32, device=dev)
             ops.gemm(gl16, ar.w16(wdec), dt, M=M, N=H, K=V, b_major=L.MAJOR_MN, accumulate=True)
-        else:
-            dt = empty16(M, H, device=dev)
+        else:   # enough row blocks to fill the GPU: plain fp32 store (same precision as the split-K path above)
+            dt = empty32(M, H, device=dev)
             ops.gemm(gl16, ar.w16(wdec), dt, M=M, N=H, K=V, b_major=L.MAJOR_MN)
         dpre_g = empty16(M, H, device=dev)  # grad wrt gelu output (fp16), then through gelu'
         ops.layernorm_bwd(dt, t32, gamma, mean, rstd, rows=M, C=H, dx16=dpre_g, dgamma=ar.g(gamma), dbeta=ar.g(beta))
