@@ -260,8 +260,8 @@ __device__ __forceinline__ void stage_and_store(const CUtensorMap* tm, uint8_t* 
 // latency: the L1 is carved down to nothing by the 227 KB of shared memory) -> math -> stores.  Here the tcgen05.ld (and
 // the GELU' input) of the warp's NEXT chunk is issued before the math of the current one, so its latency hides under
 // math + stores; the TMEM stage is released one chunk earlier; the bias arrives as ONE coalesced load per lane per
-// chunk, issued before the accumulator is even ready, and is broadcast with shuffles; the epilogue warpgroups take the
-// registers the producer / MMA warps do not need (setmaxnreg), so two accumulator chunks fit without spills.
+// chunk, issued before the accumulator is even ready, and is broadcast with shuffles.  All 384 threads run at 168
+// registers (a setmaxnreg re-partition towards the epilogue warpgroups made ptxas spill kilobytes: not used).
 // ---------------------------------------------------------------------------------------------------------
 template <int BN, int NCTA, int ACT, bool F32>
 __device__ __forceinline__ void epilogue_warps_tma2(const GemmParams& p, const CUtensorMap* tmOut, const CUtensorMap* tmAux,
@@ -591,10 +591,6 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // Register re-partition (168 per thread at launch: 384 threads x 168 = 63 K of the 64 K registers): warps 0-3 (TMA
-  // producer, MMA issuer, allocator: a few dozen live values) hand theirs to the two epilogue warpgroups, which hold two
-  // in-flight 32-column accumulator chunks + prefetched epilogue inputs.  128 x 72 + 256 x 216 = 64 512 registers.
-  // (issued at the top of the two role branches below: after a join ptxas would assume the smaller budget for everyone)
   // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) touches no global data and
   // may overlap the tail of the previous kernel; from here on operands / outputs of earlier kernels are accessed.
   griddep_launch();
@@ -603,7 +599,6 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int total = p.m_blocks * p.n_blocks * p.splits;
 
   if (warp < 4) {
-  // (setmaxnreg re-partitioning made ptxas spill kilobytes in the epilogue branch on this toolchain: not used)
   if (warp == 0) {
     // ------------------------------------------------ TMA producer (one lane; in a pair, both CTAs run one)
     if (lane == 0 && !(p.debug & 64)) {   // (profiling bit 64: no operand loads - the MMA warp runs on stale smem)
