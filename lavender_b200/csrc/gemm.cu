@@ -314,20 +314,11 @@ __device__ __forceinline__ void epilogue_warps_tma2(const GemmParams& p, const C
       release_tmem_stage<NCTA>(tmem_empty + as, lane);
       continue;
     }
-    uint32_t accA[32], accB[32];
     uint4 axA[4], axB[4];
-    tmem_ld_32x32(taddr + wg * 32, accA);
     if (ACT == LAV_ACT_GELU_BWD) load_aux(axA, wg);
-    auto step = [&](uint32_t(&cur)[32], uint4(&axc)[4], uint32_t(&nxt)[32], uint4(&axn)[4], int c, float bias_lane) {
+    // math + stores of one chunk whose accumulator values (cur) and GELU' input (axc) are in registers
+    auto body = [&](uint32_t(&cur)[32], uint4(&axc)[4], int c, float bias_lane) {
       const int col0 = n0 + c * 32;
-      tmem_ld_wait();
-      if (c + 2 < nchunks) {  // next chunk's accumulator (and GELU' input) in flight under this chunk's math + stores
-        tmem_ld_32x32(taddr + (c + 2) * 32, nxt);
-        if (ACT == LAV_ACT_GELU_BWD) load_aux(axn, c + 2);
-      } else {                // the whole accumulator has been read: hand the TMEM stage back to the MMA warp
-        tc_fence_before();
-        release_tmem_stage<NCTA>(tmem_empty + as, lane);
-      }
       float v[32];
       if (e.alpha != 1.0f) {
 #pragma unroll
@@ -364,12 +355,49 @@ __device__ __forceinline__ void epilogue_warps_tma2(const GemmParams& p, const C
       }
       stage_and_store<F32>(tmOut, buf, nb, lane, v, col0, row_base, rows_valid, p.debug);
     };
+    if constexpr (ACT == LAV_ACT_NONE) {
+      // plain epilogue: the next chunk's accumulator is in flight under this chunk's conversion + stores
+      uint32_t accA[32], accB[32];
+      tmem_ld_32x32(taddr + wg * 32, accA);
+      auto step = [&](uint32_t(&cur)[32], uint32_t(&nxt)[32], int c, float bias_lane) {
+        tmem_ld_wait();
+        if (c + 2 < nchunks) {
+          tmem_ld_32x32(taddr + (c + 2) * 32, nxt);
+        } else {                // the whole accumulator has been read: hand the TMEM stage back to the MMA warp
+          tc_fence_before();
+          release_tmem_stage<NCTA>(tmem_empty + as, lane);
+        }
+        body(cur, axA, c, bias_lane);
+      };
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      const int c = wg + 2 * k;
-      if (c >= nchunks) break;
-      if (k & 1) step(accB, axB, accA, axA, c, bl[k]);
-      else step(accA, axA, accB, axB, c, bl[k]);
+      for (int k = 0; k < KMAX; ++k) {
+        const int c = wg + 2 * k;
+        if (c >= nchunks) break;
+        if (k & 1) step(accB, accA, c, bl[k]);
+        else step(accA, accB, c, bl[k]);
+      }
+    } else {
+      // GELU / GELU': a chunk is ~20 instructions per output, the tcgen05.ld round trip is noise next to it, and the
+      // second accumulator buffer's 32 registers are what ptxas needs to keep several GELU evaluations in flight
+      // (with both buffers live it evaluated the 32 outputs one after the other through the same three registers)
+      uint32_t acc[32];
+      auto step = [&](uint4(&axc)[4], uint4(&axn)[4], int c, float bias_lane) {
+        tmem_ld_32x32(taddr + c * 32, acc);
+        if (ACT == LAV_ACT_GELU_BWD && c + 2 < nchunks) load_aux(axn, c + 2);   // GELU' input of the next chunk (HBM latency)
+        tmem_ld_wait();
+        if (c + 2 >= nchunks) {
+          tc_fence_before();
+          release_tmem_stage<NCTA>(tmem_empty + as, lane);
+        }
+        body(acc, axc, c, bias_lane);
+      };
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        const int c = wg + 2 * k;
+        if (c >= nchunks) break;
+        if (k & 1) step(axB, axA, c, bl[k]);
+        else step(axA, axB, c, bl[k]);
+      }
     }
   }
   if (lane == 0) tma_store_wait_all();  // smem must outlive the reads; the writes complete before the grid does
