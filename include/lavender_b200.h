@@ -85,8 +85,8 @@ int lav_dropout_mask(uint8_t* keep, int rows, int C, int head, const LavDropout*
 #define LAV_MAJOR_MN 1
 
 #define LAV_ACT_NONE 0
-#define LAV_ACT_GELU 1       /* out = gelu_erf(v); if aux != NULL also aux = v (f16 pre-activation)      */
-#define LAV_ACT_GELU_BWD 2   /* out = v * gelu_erf'(aux)                                                  */
+#define LAV_ACT_GELU 1       /* out = gelu_erf(v); if aux != NULL also aux = gelu_erf'(v) (f16), saved for backward */
+#define LAV_ACT_GELU_BWD 2   /* out = v * aux, aux = the gelu_erf'(pre-activation) the forward epilogue saved   */
 
 #define LAV_OUT_F16 0
 #define LAV_OUT_F32 1
@@ -171,9 +171,9 @@ int lav_split3_f16(const float* x, int64_t ldx, void* out16, int64_t ldo, int ro
  * agent.py:219) */
 int lav_cast_f32_to_f16(const float* src, void* dst, int64_t n, void* stream);
 
-/* out16 = dy16 * gelu_erf'(pre16), flat fp16 (backward of BertPredictionHeadTransform's GELU,
- * main_pretrain_mlm.py:46-48; the other GELUs are fused into GEMM epilogues) */
-int lav_gelu_bwd_f16(const void* dy16, const void* pre16, void* out16, int64_t n, void* stream);
+/* out16 = dy16 * dgelu16, flat fp16, dgelu16 = gelu_erf'(pre-activation) as saved by the LAV_ACT_GELU epilogue (backward of
+ * BertPredictionHeadTransform's GELU, main_pretrain_mlm.py:46-48; the other GELUs are fused into GEMM epilogues) */
+int lav_gelu_bwd_f16(const void* dy16, const void* dgelu16, void* out16, int64_t n, void* stream);
 
 /* out[c] += alpha * sum_r x16[r, c]  (bias gradients of every nn.Linear on the path) */
 int lav_colsum_f16(const void* x16, int64_t ld, int rows, int N, float* out, float alpha, void* stream);

@@ -323,7 +323,7 @@ class _BertEncoderFn(torch.autograd.Function):
                               dgamma=ar.g(oo.LayerNorm.weight), dbeta=ar.g(oo.LayerNorm.bias), drop16=sv["d_oo"])
             linear_wgrad(go16, sv["i16"], ar.g(oo.dense.weight), ar.g(oo.dense.bias))
             dpre16 = empty16(M, FF, device=dev)
-            linear_dgrad(go16, ar.w16(oo.dense.weight), dpre16, act=L.ACT_GELU_BWD, aux=sv["pre16"])
+            linear_dgrad(go16, ar.w16(oo.dense.weight), dpre16, act=L.ACT_GELU_BWD, aux=sv["pre16"])   # pre16 = gelu'(pre-activation)
             linear_wgrad(dpre16, sv["a16"], ar.g(it.dense.weight), ar.g(it.dense.bias))
             da32 = empty32(M, H, device=dev)  # grad wrt a = residual path + FFN path
             linear_dgrad(dpre16, ar.w16(it.dense.weight), da32, residual=go32)

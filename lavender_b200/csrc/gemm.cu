@@ -192,7 +192,7 @@ __device__ __forceinline__ void store_phase(const GemmParams& p, const float* st
   }
 }
 
-// staged chunk -> aux (fp16 [row][col], identity rows): the GELU pre-activation
+// staged chunk -> aux (fp16 [row][col], identity rows): gelu'(pre-activation) for the backward
 __device__ __forceinline__ void store_aux_phase(const GemmParams& p, const float* stg, int row_base, int col, int rr, int cg) {
   const LavGemmEpilogue& e = p.epi;
   const int nv = p.N - col;
@@ -332,25 +332,23 @@ __device__ __forceinline__ void epilogue_warps_tma2(const GemmParams& p, const C
         for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bias_lane, j);
       }
       if (ACT == LAV_ACT_GELU) {
-        if (aux_out) stage_and_store<false>(tmAux, buf, nb, lane, v, col0, row_base, rows_valid, p.debug);
-        if (!(p.debug & 128)) {  // (profiling bit 128: no activation math)
+        // aux receives gelu'(pre-activation), not the pre-activation: the cdf / pdf are in registers here anyway (one FMA
+        // more per output), the backward epilogue becomes a multiply, and the saved tensor has the same size
+        if (aux_out) {
+          float g[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) gelu_erf_both(v[j], v[j], g[j]);
+          stage_and_store<false>(tmAux, buf, nb, lane, g, col0, row_base, rows_valid, p.debug);
+        } else if (!(p.debug & 128)) {  // (profiling bit 128: no activation math)
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
         }
       } else if (ACT == LAV_ACT_GELU_BWD) {
-        const __half2* h2 = reinterpret_cast<const __half2*>(axc);
-        if (p.debug & 128) {
+        const __half2* h2 = reinterpret_cast<const __half2*>(axc);   // gelu'(pre-activation), saved by the forward epilogue
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float2 x = __half22float2(h2[j]);
-            v[2 * j] *= x.x, v[2 * j + 1] *= x.y;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float2 x = __half22float2(h2[j]);
-            v[2 * j] *= gelu_erf_grad(x.x), v[2 * j + 1] *= gelu_erf_grad(x.y);
-          }
+        for (int j = 0; j < 16; ++j) {
+          const float2 x = __half22float2(h2[j]);
+          v[2 * j] *= x.x, v[2 * j + 1] *= x.y;
         }
       }
       stage_and_store<F32>(tmOut, buf, nb, lane, v, col0, row_base, rows_valid, p.debug);
@@ -513,16 +511,20 @@ __device__ __forceinline__ void epilogue_warps(const GemmParams& p, float* epi_s
         }
       }
       if (ACT == LAV_ACT_GELU) {
-        if (e.aux) {
-          stage_rows(stg, lane, v);
+        if (e.aux) {   // aux = gelu'(pre-activation) (see the TMA-store epilogue)
+          float g[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) gelu_erf_both(v[j], v[j], g[j]);
+          stage_rows(stg, lane, g);
           __syncwarp();
           store_aux_phase(p, stg, row_base, col, rr, cg);
           __syncwarp();
-        }
+        } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        }
       } else if (use_auxin) {
-        // pre-activation: (store-layout registers) -> smem -> (row-layout registers)
+        // gelu'(pre-activation): (store-layout registers) -> smem -> (row-layout registers)
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&cur[it].x));
@@ -533,8 +535,8 @@ __device__ __forceinline__ void epilogue_warps(const GemmParams& p, float* epi_s
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 x = *reinterpret_cast<const float4*>(stg + epi_slot(lane, j));
-          v[4 * j] *= gelu_erf_grad(x.x), v[4 * j + 1] *= gelu_erf_grad(x.y);
-          v[4 * j + 2] *= gelu_erf_grad(x.z), v[4 * j + 3] *= gelu_erf_grad(x.w);
+          v[4 * j] *= x.x, v[4 * j + 1] *= x.y;
+          v[4 * j + 2] *= x.z, v[4 * j + 3] *= x.w;
         }
         __syncwarp();
       }

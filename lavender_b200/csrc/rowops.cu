@@ -667,13 +667,13 @@ colsum_f16_kernel(const __half* x, int64_t ld, int rows, int N, float* out, floa
   }
 }
 
-// out16 = dy16 * gelu_erf'(pre16)   (flat, n % 2 == 0)
+// out16 = dy16 * dgelu16   (flat, n % 2 == 0; dgelu16 = gelu'(pre-activation) as saved by the forward GEMM epilogue)
 __global__ void __launch_bounds__(256) gelu_bwd_kernel(const __half2* dy, const __half2* pre, __half2* out, int64_t n2) {
   griddep_launch();  // the next kernel may start its prologue under this kernel's tail
   griddep_wait();    // (this one may have started under its predecessor's: wait before touching global data)
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
     float2 d = __half22float2(dy[i]), x = __half22float2(pre[i]);
-    out[i] = __floats2half2_rn(d.x * gelu_erf_grad(x.x), d.y * gelu_erf_grad(x.y));
+    out[i] = __floats2half2_rn(d.x * x.x, d.y * x.y);
   }
 }
 

@@ -318,6 +318,13 @@ __device__ __forceinline__ float gelu_erf(float x) {
   normal_cdf_pdf(x, c, d);
   return x * c;
 }
+// y = gelu(x) and dy = gelu'(x) from one evaluation (forward epilogues save dy for the backward: no erf there)
+__device__ __forceinline__ void gelu_erf_both(float x, float& y, float& dy) {
+  float c, d;
+  normal_cdf_pdf(x, c, d);
+  y = x * c;
+  dy = fmaf(x, d, c);
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   float c, d;
   normal_cdf_pdf(x, c, d);

@@ -242,6 +242,8 @@ def dropout_mask(rows, C, drop, head=-1):
 
 
 def gelu_bwd(dy16, pre16, out16):
+    """out16 = dy16 * pre16, where pre16 is the `aux` tensor of an ACT_GELU GEMM: since ABI v3 that epilogue saves
+    gelu'(pre-activation) rather than the pre-activation itself, so the backward needs no erf."""
     assert dy16.is_contiguous() and pre16.is_contiguous() and out16.is_contiguous()
     with _Timed("gelu_bwd"):
         L.check(L.lib().lav_gelu_bwd_f16(_p(dy16), _p(pre16), _p(out16), dy16.numel(), _stream()), "lav_gelu_bwd_f16")

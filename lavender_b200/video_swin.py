@@ -533,7 +533,7 @@ def _block_bwd(ar, blk, g, sv, ds_ws, dev, g16=None, emit=None):
         g16 = ops.scale_cast(g, empty16(M, C, device=dev), rows=M, C=C, row_scale=sv["k2"], rows_per_scale=rps)
     linear_wgrad(g16, sv["h16"], ar.g(fc2.weight), ar.g(fc2.bias))
     da16 = empty16(M, 4 * C, device=dev)
-    linear_dgrad(g16, ar.w16(fc2.weight), da16, act=L.ACT_GELU_BWD, aux=sv["a16"])
+    linear_dgrad(g16, ar.w16(fc2.weight), da16, act=L.ACT_GELU_BWD, aux=sv["a16"])   # a16 = gelu'(fc1 output), saved by fc1's epilogue
     linear_wgrad(da16, sv["y2"], ar.g(fc1.weight), ar.g(fc1.bias))
     dy2 = empty16(M, C, device=dev)
     linear_dgrad(da16, ar.w16(fc1.weight), dy2)

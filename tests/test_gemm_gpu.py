@@ -66,17 +66,17 @@ def test_gelu_with_aux_and_backward():
     out = torch.zeros(M, N, device="cuda", dtype=torch.float16)
     aux = torch.zeros(M, N, device="cuda", dtype=torch.float16)
     ops.gemm(a, b, out, M=M, N=N, K=K, bias=bias, act=L.ACT_GELU, aux=aux)
-    pre = _ref(a, b) + bias.double()
-    assert (aux.double() - pre).abs().max().item() < 5e-3
-    assert (out.double() - torch.nn.functional.gelu(pre)).abs().max().item() < 5e-3
-    # dgrad with GELU': dA = (dY @ W) * gelu'(aux)   [A=dY K-major, B=W MN-major]
+    pre = (_ref(a, b) + bias.double()).requires_grad_(True)
+    act = torch.nn.functional.gelu(pre)
+    act.sum().backward()
+    assert (aux.double() - pre.grad).abs().max().item() < 2e-3      # aux = gelu'(pre-activation), saved for the backward
+    assert (out.double() - act.detach()).abs().max().item() < 5e-3
+    # dgrad with GELU': dA = (dY @ W) * aux   [A=dY K-major, B=W MN-major]
     dy = _mk((M, K), 9, 0.3)          # pretend grad wrt fc2 input of width K... here: [M,K] x W2[K?]
     w = _mk((K, N), 10, 0.3)          # contraction over K: out[M,N] = dy[M,K] @ w[K,N]
     dout = torch.zeros(M, N, device="cuda", dtype=torch.float16)
     ops.gemm(dy, w, dout, M=M, N=N, K=K, b_major=L.MAJOR_MN, act=L.ACT_GELU_BWD, aux=aux)
-    x = aux.double().requires_grad_(True)
-    torch.nn.functional.gelu(x).sum().backward()
-    ref = (dy.double() @ w.double()) * x.grad
+    ref = (dy.double() @ w.double()) * pre.grad
     assert (dout.double() - ref).abs().max().item() < 1e-2
 
 
